@@ -1,0 +1,363 @@
+// kge_api.cu -- the extern "C" boundary of libkge_b200.so (see include/kge_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "kge_internal.h"
+
+using namespace kge;
+
+struct kge_handle {
+    kge_config cfg;
+    Layout L;
+    int sm_count;
+    int max_smem;
+    float score_scale;  // HolE 2/k
+    float rot_div;      // RotatE range/pi
+    float *rot;         // [n_rel, ld] rotation table workspace (RotatE)
+    // training launch geometry
+    int nit, G, warps, eta_pad, rows_bytes, region_bytes;
+    // ranking workspace (grown on demand)
+    long long ws_b;
+    float *ws_q;      // 3 * ws_b * ld floats: qvec_s | qvec_o | qaux
+    int32_t *ws_i;    // 4 * ws_b ints: qpos | cnt[3]
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(KGE_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+#define KGE_CUDA(call, what)                                 \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, what);   \
+    } while (0)
+
+extern "C" const char *kge_last_error(void) { return g_err; }
+extern "C" int kge_abi_version(void) { return KGE_B200_ABI_VERSION; }
+
+extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
+{
+    if (!cfg || !out) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: null argument");
+    if (cfg->struct_size != (int32_t)sizeof(kge_config))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: kge_config.struct_size %d != %d (ABI mismatch)",
+                    cfg->struct_size, (int)sizeof(kge_config));
+    if (cfg->scoring < KGE_TRANSE || cfg->scoring > KGE_ROTATE)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: unknown scoring_type id %d", cfg->scoring);
+    if (cfg->loss < KGE_LOSS_PAIRWISE || cfg->loss > KGE_LOSS_MULTICLASS_NLL)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "Could not interpret loss identifier: %d", cfg->loss);
+    if (cfg->reduction != KGE_REDUCE_SUM && cfg->reduction != KGE_REDUCE_MEAN)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for reduction!");
+    if (cfg->k < 1 || cfg->eta < 1 || cfg->n_ent < 1 || cfg->n_rel < 1)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: k, eta, n_ent, n_rel must be >= 1");
+    if (cfg->n_ent > 0x7fffffffLL || cfg->n_rel > 0x7fffffffLL)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: ids are int32 (n_ent, n_rel < 2^31)");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(KGE_ERR_CUDA, "kge_create: no CUDA device visible (%s) -- libkge_b200 has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: device %d out of range [0,%d)", cfg->device, ndev);
+    KGE_CUDA(cudaSetDevice(cfg->device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    KGE_CUDA(cudaGetDeviceProperties(&prop, cfg->device), "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        return fail(KGE_ERR_UNSUPPORTED, "kge_create: device is sm_%d%d; libkge_b200 is built for sm_100a only",
+                    prop.major, prop.minor);
+
+    kge_handle *h = new (std::nothrow) kge_handle();
+    if (!h) return fail(KGE_ERR_CUDA, "kge_create: out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    Layout &L = h->L;
+    L.model = cfg->scoring;
+    L.k = cfg->k;
+    L.halves = model_halves(cfg->scoring);
+    L.kp = (cfg->k + 3) / 4 * 4;
+    L.ld = L.halves * L.kp;
+    L.K = L.halves * cfg->k;
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    h->score_scale = (cfg->scoring == KGE_HOLE) ? hole_scale(L.K) : 1.f;
+    h->rot_div = (cfg->scoring == KGE_ROTATE) ? rotate_divisor(L.K, cfg->n_rel) : 1.f;
+
+    // ---- training geometry: one warp per positive, (3+G) rows resident per warp ----
+    const int nch = L.kp / 4;
+    const int nit_raw = (nch + 31) / 32;
+    h->nit = nit_raw <= 1 ? 1 : nit_raw <= 2 ? 2 : nit_raw <= 4 ? 4 : 0;
+    h->eta_pad = (cfg->eta + 3) / 4 * 4;
+    const int row_bytes = L.ld * 4, aux = 3 * h->eta_pad * 4 + 16;
+    const int min_warps = 4;
+    int G = cfg->neg_group > 0 ? (cfg->neg_group < cfg->eta ? cfg->neg_group : cfg->eta) : cfg->eta;
+    while (G > 1 && (long long)((3 + G) * (long long)row_bytes + aux) * min_warps > h->max_smem) --G;
+    h->G = G;
+    h->rows_bytes = (3 + G) * row_bytes;
+    h->region_bytes = h->rows_bytes + aux;
+    int warps = h->region_bytes > 0 ? h->max_smem / h->region_bytes : 0;
+    const int max_warps = h->nit ? KGE_TRAIN_THREADS_FOR_NIT(h->nit) / 32 : 0;
+    if (warps > max_warps) warps = max_warps;
+    h->warps = warps;  // 0 => training unsupported for this shape (reported by kge_train_step)
+
+    if (cfg->scoring == KGE_ROTATE) {
+        cudaError_t e2 = cudaMalloc(&h->rot, (size_t)cfg->n_rel * L.ld * sizeof(float));
+        if (e2 != cudaSuccess) { delete h; return cuda_fail(e2, "cudaMalloc(rotation table)"); }
+    }
+    *out = h;
+    return KGE_OK;
+}
+
+extern "C" void kge_destroy(kge_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->rot) cudaFree(h->rot);
+    if (h->ws_q) cudaFree(h->ws_q);
+    if (h->ws_i) cudaFree(h->ws_i);
+    delete h;
+}
+
+extern "C" int32_t kge_internal_k(const kge_handle *h) { return h ? h->L.K : 0; }
+extern "C" int32_t kge_half_stride(const kge_handle *h) { return h ? h->L.kp : 0; }
+extern "C" int32_t kge_row_stride(const kge_handle *h) { return h ? h->L.ld : 0; }
+
+#define KGE_CHECK_HANDLE(h, fn) \
+    if (!(h)) return fail(KGE_ERR_INVALID_ARGUMENT, fn ": null handle")
+
+extern "C" int kge_pack_rows(kge_handle *h, const float *dense_dev, float *table_dev, int64_t rows, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_pack_rows");
+    if (rows < 0 || (rows > 0 && (!dense_dev || !table_dev))) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_pack_rows: bad argument");
+    KGE_CUDA(launch_pack(h->L, dense_dev, table_dev, rows, false, (cudaStream_t)stream), "kge_pack_rows");
+    return KGE_OK;
+}
+extern "C" int kge_unpack_rows(kge_handle *h, const float *table_dev, float *dense_dev, int64_t rows, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_unpack_rows");
+    if (rows < 0 || (rows > 0 && (!dense_dev || !table_dev))) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_unpack_rows: bad argument");
+    KGE_CUDA(launch_pack(h->L, table_dev, dense_dev, rows, true, (cudaStream_t)stream), "kge_unpack_rows");
+    return KGE_OK;
+}
+
+extern "C" int kge_init_glorot_uniform(kge_handle *h, float *table_dev, int64_t rows, uint64_t seed, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_init_glorot_uniform");
+    if (rows < 0 || (rows > 0 && !table_dev)) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_init_glorot_uniform: bad argument");
+    KGE_CUDA(launch_glorot(h->L, table_dev, rows, seed, (cudaStream_t)stream), "kge_init_glorot_uniform");
+    return KGE_OK;
+}
+
+static int refresh_rotation(kge_handle *h, const float *rel_dev, cudaStream_t st)
+{
+    if (h->cfg.scoring != KGE_ROTATE) return KGE_OK;
+    KGE_CUDA(launch_rotation_table(rel_dev, h->rot, h->cfg.n_rel, h->L.kp, h->L.ld, h->rot_div, st),
+             "rotation table");
+    return KGE_OK;
+}
+
+extern "C" int kge_score_triples(kge_handle *h, const float *ent_dev, const float *rel_dev,
+                                 const int32_t *triples_dev, int64_t n, float *scores_dev, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_score_triples");
+    if (n < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_score_triples: n < 0");
+    if (n == 0) return KGE_OK;
+    if (!ent_dev || !rel_dev || !triples_dev || !scores_dev)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_score_triples: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = refresh_rotation(h, rel_dev, st)) return rc;
+    const float *rel = h->cfg.scoring == KGE_ROTATE ? h->rot : rel_dev;
+    KGE_CUDA(launch_score_triples(h->L, h->nit, ent_dev, rel, triples_dev, n, h->score_scale, scores_dev,
+                                  h->sm_count, st),
+             "kge_score_triples");
+    return KGE_OK;
+}
+
+extern "C" int kge_generate_corruptions(kge_handle *h, const int32_t *triples_dev, int64_t B, uint64_t seed,
+                                        uint64_t step, int32_t *corruptions_dev, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_generate_corruptions");
+    if (B < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_generate_corruptions: B < 0");
+    if (B == 0) return KGE_OK;
+    if (!triples_dev || !corruptions_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_generate_corruptions: null pointer");
+    KGE_CUDA(launch_corruptions(triples_dev, B, h->cfg.eta, seed, step, (unsigned)h->cfg.n_ent, corruptions_dev,
+                                (cudaStream_t)stream),
+             "kge_generate_corruptions");
+    return KGE_OK;
+}
+
+extern "C" int kge_train_step(kge_handle *h, int32_t mode, const float *ent_dev, const float *rel_dev,
+                              float *grad_ent_dev, float *grad_rel_dev, const int32_t *triples_dev, int64_t B,
+                              const int32_t *neg_ent_dev, const uint8_t *neg_keep_subj_dev, uint64_t seed,
+                              uint64_t step, double *loss_dev, float *scores_pos_dev, float *scores_neg_dev,
+                              const float *dpos_dev, const float *dneg_dev, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_train_step");
+    if (mode < KGE_STEP_FUSED || mode > KGE_STEP_BACKWARD_EXT)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step: unknown mode %d", mode);
+    if (B < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step: B < 0");
+    if (B == 0) return KGE_OK;
+    if (!ent_dev || !rel_dev || !triples_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step: null table/triples");
+    if (mode != KGE_STEP_FORWARD_ONLY && (!grad_ent_dev || !grad_rel_dev))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step: null gradient buffer");
+    if ((neg_ent_dev == nullptr) != (neg_keep_subj_dev == nullptr))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step: neg_ent_dev and neg_keep_subj_dev must be given together");
+    if (mode == KGE_STEP_BACKWARD_EXT && (!dpos_dev || !dneg_dev))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step: BACKWARD_EXT needs dpos_dev and dneg_dev");
+    if (mode == KGE_STEP_FORWARD_ONLY && (!scores_pos_dev || !scores_neg_dev))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step: FORWARD_ONLY needs both score outputs");
+    if (h->nit == 0)
+        return fail(KGE_ERR_UNSUPPORTED, "kge_train_step: k=%d exceeds the 512-float half-row limit of the "
+                    "warp-per-positive kernel", h->cfg.k);
+    if (h->warps < 1)
+        return fail(KGE_ERR_UNSUPPORTED, "kge_train_step: one positive's working set (%d B) exceeds shared memory (%d B)",
+                    h->region_bytes, h->max_smem);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = refresh_rotation(h, rel_dev, st)) return rc;
+
+    TrainParams p;
+    memset(&p, 0, sizeof(p));
+    p.ent = ent_dev;
+    p.rel = h->cfg.scoring == KGE_ROTATE ? h->rot : rel_dev;
+    p.grad_ent = grad_ent_dev;
+    p.grad_rel = grad_rel_dev;
+    p.triples = triples_dev;
+    p.B = B;
+    p.neg_ent = neg_ent_dev;
+    p.neg_keep = neg_keep_subj_dev;
+    p.seed = seed;
+    p.step = step;
+    p.n_ent = (unsigned)h->cfg.n_ent;
+    p.model = h->cfg.scoring;
+    p.eta = h->cfg.eta;
+    p.kp = h->L.kp;
+    p.ld = h->L.ld;
+    p.nch = h->L.kp / 4;
+    p.G = h->G;
+    p.eta_pad = h->eta_pad;
+    p.rows_bytes = h->rows_bytes;
+    p.region_bytes = h->region_bytes;
+    p.loss = h->cfg.loss;
+    p.reduction = h->cfg.reduction;
+    p.mode = mode;
+    p.margin = h->cfg.margin;
+    p.alpha = h->cfg.alpha;
+    p.score_scale = h->score_scale;
+    p.inv_div = 1.f / h->rot_div;
+    p.loss_out = loss_dev;
+    p.scores_pos = scores_pos_dev;
+    p.scores_neg = scores_neg_dev;
+    p.dpos = dpos_dev;
+    p.dneg = dneg_dev;
+    KGE_CUDA(launch_train(p, h->nit, h->sm_count, h->warps * 32, (size_t)h->warps * h->region_bytes, st),
+             "kge_train_step");
+    return KGE_OK;
+}
+
+extern "C" int kge_optimizer_step(kge_handle *h, const kge_optimizer_config *opt, int64_t t, float *table_dev,
+                                  float *grad_dev, float *slot0_dev, float *slot1_dev, int64_t rows,
+                                  double *reg_loss_dev, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_optimizer_step");
+    if (!opt || opt->struct_size != (int32_t)sizeof(kge_optimizer_config))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: bad kge_optimizer_config (ABI mismatch)");
+    if (opt->kind < KGE_OPT_SGD || opt->kind > KGE_OPT_ADAGRAD)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "Could not interpret optimizer identifier: %d", opt->kind);
+    if (rows < 0 || t < 1) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: rows >= 0 and t >= 1 required");
+    if (rows == 0) return KGE_OK;
+    if (!table_dev || !grad_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: null table/grad");
+    const bool need0 = opt->kind != KGE_OPT_SGD || opt->momentum != 0.f;
+    const bool need1 = opt->kind == KGE_OPT_ADAM;
+    if ((need0 && !slot0_dev) || (need1 && !slot1_dev))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: optimizer slot buffer missing");
+    if (opt->reg_p < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: reg_p < 0");
+    OptimParams o;
+    o.kind = opt->kind;
+    o.lr = opt->learning_rate;
+    o.beta1 = opt->beta_1;
+    o.beta2 = opt->beta_2;
+    o.eps = opt->epsilon;
+    o.momentum = opt->momentum;
+    o.reg_p = opt->reg_p;
+    o.reg_lambda = opt->reg_lambda;
+    // legacy Adam: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+    o.lr_t = (float)((double)opt->learning_rate * sqrt(1.0 - pow((double)opt->beta_2, (double)t)) /
+                     (1.0 - pow((double)opt->beta_1, (double)t)));
+    KGE_CUDA(launch_optimizer(o, table_dev, grad_dev, slot0_dev, slot1_dev, rows * (long long)h->L.ld, reg_loss_dev,
+                              h->sm_count, (cudaStream_t)stream),
+             "kge_optimizer_step");
+    return KGE_OK;
+}
+
+extern "C" int64_t kge_rank_workspace_bytes(const kge_handle *h, int64_t b)
+{
+    if (!h || b < 0) return 0;
+    return (int64_t)(3 * b * h->L.ld * sizeof(float) + 4 * b * sizeof(int32_t));
+}
+
+extern "C" int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const float *ent_dev, const float *rel_dev,
+                        const int32_t *triples_dev, int64_t b, const int32_t *cand_ids_dev, int64_t cand_begin,
+                        int64_t n_cand, const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
+                        int32_t *ranks_dev, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_rank");
+    if (side != KGE_SIDE_S && side != KGE_SIDE_O) return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for corrupt_side");
+    if (strategy < KGE_RANK_WORST || strategy > KGE_RANK_MIDDLE)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for ranking_strategy");
+    if (b < 0 || n_cand < 0 || cand_begin < 0 || n_filt < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: negative size");
+    if (b == 0) return KGE_OK;
+    if (!ent_dev || !rel_dev || !triples_dev || !ranks_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: null pointer");
+    if (cand_ids_dev && cand_begin != 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: cand_begin must be 0 with cand_ids_dev");
+    if (!cand_ids_dev && cand_begin + n_cand > h->cfg.n_ent)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: candidate range [%lld,%lld) exceeds n_ent %lld",
+                    (long long)cand_begin, (long long)(cand_begin + n_cand), (long long)h->cfg.n_ent);
+    if ((filt_off_dev == nullptr) != (filt_idx_dev == nullptr) && n_filt > 0)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: filter offsets and indices must be given together");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b > h->ws_b) {
+        KGE_CUDA(cudaStreamSynchronize(st), "kge_rank: sync before growing workspace");
+        if (h->ws_q) cudaFree(h->ws_q);
+        if (h->ws_i) cudaFree(h->ws_i);
+        h->ws_q = nullptr; h->ws_i = nullptr; h->ws_b = 0;
+        KGE_CUDA(cudaMalloc(&h->ws_q, (size_t)3 * b * h->L.ld * sizeof(float)), "kge_rank: cudaMalloc workspace");
+        KGE_CUDA(cudaMalloc(&h->ws_i, (size_t)4 * b * sizeof(int32_t)), "kge_rank: cudaMalloc workspace");
+        h->ws_b = b;
+    }
+    float *qs = h->ws_q, *qo = qs + (size_t)b * h->L.ld, *qaux = qo + (size_t)b * h->L.ld;
+    int32_t *qpos = h->ws_i, *cnt = qpos + b;
+    if (int rc = refresh_rotation(h, rel_dev, st)) return rc;
+    KGE_CUDA(launch_rank_prepare(h->L, ent_dev, rel_dev, h->rot, triples_dev, b, h->score_scale, qs, qo, qaux, qpos, st),
+             "kge_rank: prepare");
+    KGE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)3 * b * sizeof(int32_t), st), "kge_rank: memset");
+    RankParams p;
+    memset(&p, 0, sizeof(p));
+    p.L = h->L;
+    p.side = side;
+    p.strategy = strategy;
+    p.ent = ent_dev;
+    p.qvec = side == KGE_SIDE_S ? qs : qo;
+    p.qaux = qaux;
+    p.qpos = qpos;
+    p.cand_ids = cand_ids_dev;
+    p.cand_begin = cand_begin;
+    p.n_cand = n_cand;
+    p.b = b;
+    p.scale = h->score_scale;
+    KGE_CUDA(launch_rank_count(p, cnt, st), "kge_rank: count");
+    if (filt_off_dev && n_filt > 0)
+        KGE_CUDA(launch_rank_filter_n(p, (const long long *)filt_off_dev, filt_idx_dev, n_filt, cnt, st), "kge_rank: filter");
+    KGE_CUDA(launch_rank_finalize(cnt, b, strategy, ranks_dev, st), "kge_rank: finalize");
+    return KGE_OK;
+}

@@ -1,0 +1,80 @@
+// kge_internal.h -- internal launcher interfaces of libkge_b200 (not part of the C-ABI).
+#pragma once
+#include "kge_common.cuh"
+
+#define KGE_TRAIN_MAX_THREADS 512
+// per-lane register state grows with NIT (float4 chunks per lane): trade threads for registers
+#define KGE_TRAIN_THREADS_FOR_NIT(nit) ((nit) <= 1 ? 512 : (nit) == 2 ? 384 : 256)
+#define KGE_MAX_SMEM_PER_CTA (227 * 1024)
+
+namespace kge {
+
+struct TrainParams {
+    const float *ent;   // [n_ent, ld]
+    const float *rel;   // [n_rel, ld]; for RotatE the per-step rotation table [cos|sin]
+    float *grad_ent;
+    float *grad_rel;
+    const int32_t *triples;  // [B,3]
+    long long B;
+    const int32_t *neg_ent;  // [eta*B] or nullptr (Philox)
+    const uint8_t *neg_keep; // [eta*B] or nullptr
+    unsigned long long seed, step;
+    unsigned n_ent;
+    int model, eta, kp, ld, nch;  // nch = kp/4 float4 chunks per half
+    int G;                        // replaced rows resident per pass
+    int eta_pad;                  // round_up(eta,4)
+    int rows_bytes, region_bytes; // per-warp shared-memory carve-up
+    int loss, reduction, mode;
+    float margin, alpha, score_scale, inv_div;
+    double *loss_out;
+    float *scores_pos, *scores_neg;
+    const float *dpos, *dneg;
+};
+
+// grid = min(occupancy * sm_count, ceil(B / warps))
+cudaError_t launch_train(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_rotation_table(const float *rel, float *rot, long long n_rel, int kp, int ld, float div,
+                                  cudaStream_t st);
+cudaError_t launch_corruptions(const int32_t *triples, long long B, int eta, unsigned long long seed,
+                               unsigned long long step, unsigned n_ent, int32_t *out, cudaStream_t st);
+
+// kge_misc.cu
+cudaError_t launch_score_triples(const Layout &L, int nit, const float *ent, const float *rel_or_rot,
+                                 const int32_t *triples, long long n, float scale, float *out, int sm_count,
+                                 cudaStream_t st);
+cudaError_t launch_pack(const Layout &L, const float *src, float *dst, long long rows, bool unpack, cudaStream_t st);
+cudaError_t launch_glorot(const Layout &L, float *table, long long rows, unsigned long long seed, cudaStream_t st);
+
+// kge_optim.cu
+struct OptimParams {
+    int kind;
+    float lr, lr_t, beta1, beta2, eps, momentum;
+    int reg_p;
+    float reg_lambda;
+};
+cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
+                             long long n_floats, double *reg_loss, int sm_count, cudaStream_t st);
+cudaError_t launch_fill(float *p, long long n, float v, cudaStream_t st);
+
+// kge_rank.cu
+struct RankParams {
+    Layout L;
+    int side, strategy;
+    const float *ent;      // [n_ent, ld]
+    const float *qvec;     // [b, ld] prepared query vectors for this side
+    const float *qaux;     // [b, ld] object rows (RotatE subject side) or nullptr
+    const int32_t *qpos;   // [b] quantised positive scores
+    const int32_t *cand_ids;  // nullptr or [n_cand]
+    long long cand_begin, n_cand, b;
+    float scale;           // HolE
+};
+cudaError_t launch_rank_prepare(const Layout &L, const float *ent, const float *rel, const float *rot,
+                                const int32_t *triples, long long b, float scale, float *qvec_s, float *qvec_o,
+                                float *qaux, int32_t *qpos, cudaStream_t st);
+// cnt = [b,3] int32 workspace: #(qpos < qc), #(qpos == qc), #filtered
+cudaError_t launch_rank_count(const RankParams &p, int32_t *cnt, cudaStream_t st);
+cudaError_t launch_rank_filter_n(const RankParams &p, const long long *filt_off, const int32_t *filt_idx,
+                                 long long n_pairs, int32_t *cnt, cudaStream_t st);
+cudaError_t launch_rank_finalize(const int32_t *cnt, long long b, int strategy, int32_t *ranks, cudaStream_t st);
+
+}  // namespace kge

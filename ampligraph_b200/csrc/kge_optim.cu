@@ -1,0 +1,107 @@
+// kge_optim.cu -- dense optimizer update of one embedding table (sm_100a).
+//
+// Replaces OptimizerWrapper.minimize -> tf.keras.optimizers.legacy.*.apply_gradients
+// (optimizers.py:136-168) and the LP regulariser (regularizers.py:14-37), fused:
+// one streaming pass reads {table, grad, slots}, writes {table, slots} and zeroes
+// the gradient accumulator for the next step.  Semantics are the reference's
+// DENSE ones: legacy Keras sums duplicate IndexedSlices rows first and Adam then
+// decays m, v and moves EVERY row each step, touched or not.
+// Bound: HBM, 8 fp32 streams per element for Adam (4 read + 4 written).
+#include <math.h>
+
+#include "kge_internal.h"
+
+namespace kge {
+
+__device__ __forceinline__ float reg_grad(float x, int p, float lam, float *pow_out)
+{
+    // d/dx lam*|x|^p = lam*p*|x|^(p-1)*sign(x)
+    float ax = fabsf(x), sg = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+    float pm1 = (p == 2) ? ax : (p == 3) ? ax * ax : (p == 1) ? 1.f : powf(ax, (float)(p - 1));
+    *pow_out = pm1 * ax;
+    return lam * (float)p * pm1 * sg;
+}
+
+template <int KIND, bool REG>
+__global__ void __launch_bounds__(256) kge_optim_kernel(float4 *__restrict__ var, float4 *__restrict__ grad,
+                                                        float4 *__restrict__ s0, float4 *__restrict__ s1,
+                                                        long long n4, OptimParams o, double *reg_loss)
+{
+    float racc = 0.f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 x4 = var[i], g4 = grad[i];
+        float x[4] = {x4.x, x4.y, x4.z, x4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+        float a[4], b[4];
+        if (KIND != KGE_OPT_SGD || o.momentum != 0.f) { float4 t = s0[i]; a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+        if (KIND == KGE_OPT_ADAM) { float4 t = s1[i]; b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float gg = g[e];
+            if (REG) { float pw; gg += reg_grad(x[e], o.reg_p, o.reg_lambda, &pw); racc += pw; }
+            if (KIND == KGE_OPT_ADAM) {
+                a[e] = fmaf(gg - a[e], 1.f - o.beta1, a[e]);       // m += (g-m)(1-b1)
+                b[e] = fmaf(gg * gg - b[e], 1.f - o.beta2, b[e]);  // v += (g^2-v)(1-b2)
+                x[e] -= (a[e] * o.lr_t) / (sqrtf(b[e]) + o.eps);
+            } else if (KIND == KGE_OPT_ADAGRAD) {
+                a[e] = fmaf(gg, gg, a[e]);
+                x[e] -= o.lr * gg / (sqrtf(a[e]) + o.eps);
+            } else {  // SGD (momentum optional)
+                if (o.momentum != 0.f) { a[e] = o.momentum * a[e] - o.lr * gg; x[e] += a[e]; }
+                else x[e] -= o.lr * gg;
+            }
+        }
+        var[i] = make_float4(x[0], x[1], x[2], x[3]);
+        if (KIND != KGE_OPT_SGD || o.momentum != 0.f) s0[i] = make_float4(a[0], a[1], a[2], a[3]);
+        if (KIND == KGE_OPT_ADAM) s1[i] = make_float4(b[0], b[1], b[2], b[3]);
+        grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (REG && reg_loss) {
+        racc = warp_sum(racc);
+        __shared__ float part[8];
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = racc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)part[w];
+            if (t != 0.0) atomicAdd(reg_loss, (double)o.reg_lambda * t);
+        }
+    }
+}
+
+__global__ void kge_fill_kernel(float *p, long long n, float v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+cudaError_t launch_fill(float *p, long long n, float v, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    kge_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
+                             long long n_floats, double *reg_loss, int sm_count, cudaStream_t st)
+{
+    long long n4 = n_floats / 4;  // ld is a multiple of 4
+    if (n4 == 0) return cudaSuccess;
+    long long want = (n4 + 255) / 256;
+    int grid = (int)(want < (long long)sm_count * 8 ? want : (long long)sm_count * 8);
+    float4 *v = (float4 *)table, *g = (float4 *)grad, *a = (float4 *)slot0, *b = (float4 *)slot1;
+    const bool reg = o.reg_p > 0;
+#define KGE_OPT(K)                                                                            \
+    if (reg) kge_optim_kernel<K, true><<<grid, 256, 0, st>>>(v, g, a, b, n4, o, reg_loss);    \
+    else kge_optim_kernel<K, false><<<grid, 256, 0, st>>>(v, g, a, b, n4, o, reg_loss);
+    switch (o.kind) {
+    case KGE_OPT_SGD: KGE_OPT(KGE_OPT_SGD) break;
+    case KGE_OPT_ADAM: KGE_OPT(KGE_OPT_ADAM) break;
+    case KGE_OPT_ADAGRAD: KGE_OPT(KGE_OPT_ADAGRAD) break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef KGE_OPT
+    return cudaGetLastError();
+}
+
+}  // namespace kge

@@ -1,0 +1,397 @@
+// kge_rank.cu -- score every test triple against every candidate entity and count
+// ranks (sm_100a).
+//
+// Replaces AbstractScoringLayer.get_ranks (layers/scoring/AbstractScoringLayer.py:156-422)
+// and the five _get_subject_corruption_scores / _get_object_corruption_scores
+// (TransE.py:56-114, DistMult.py:51-99, ComplEx.py:65-151, HolE.py:47-89,
+// RotatE.py:107-217).  The reference materialises a [b, E, K] broadcast; here the
+// candidate table is streamed ONCE per batch of queries through shared memory and
+// only int32 counters leave the SM.
+//
+// Bit-exactness.  Ranks are counts of int32(score*1000) comparisons
+// (AbstractScoringLayer.py:11,:201), so every score must be bit-identical to the
+// oracle's.  Every (query, candidate) accumulator therefore runs the canonical
+// chain -- ascending column index, one explicitly-rounded operation at a time
+// (__fmaf_rn/__fadd_rn/__fsqrt_rn) -- the same sequence oracle/kge_oracle.c states
+// in C.  This rules out tensor cores (TF32/bf16 products, unspecified accumulation
+// order): the kernel is an fp32-FMA register-tiled contraction.  Zero pad columns
+// are exact no-ops in every chain (fma(0,0,a)=a, a+|0|=a, a+sqrt(0)=a).
+#include <math.h>
+
+#include "kge_internal.h"
+
+namespace kge {
+
+enum { OP_DOT = 0, OP_L1_ADD = 1, OP_L1_SUB = 2, OP_ROT_S = 3, OP_ROT_O = 4 };
+
+__host__ __device__ inline int rank_op(int model, int side)
+{
+    if (model == KGE_TRANSE) return side == KGE_SIDE_S ? OP_L1_ADD : OP_L1_SUB;
+    if (model == KGE_ROTATE) return side == KGE_SIDE_S ? OP_ROT_S : OP_ROT_O;
+    return OP_DOT;
+}
+
+// one canonical accumulation step (shared by the tile kernel and the filter kernel)
+template <int OP>
+__device__ __forceinline__ float rank_step(float acc, float e, float q)
+{
+    if (OP == OP_DOT) return __fmaf_rn(e, q, acc);                  // DistMult.py:71 / ComplEx.py:95
+    if (OP == OP_L1_ADD) return __fadd_rn(acc, fabsf(__fadd_rn(e, q)));  // TransE.py:78-84
+    return __fadd_rn(acc, fabsf(__fsub_rn(q, e)));                  // TransE.py:107-113
+}
+template <int OP>
+__device__ __forceinline__ float rank_step_rot(float acc, float er, float ei, float qa, float qb, float or_, float oi)
+{
+    float re, im;
+    if (OP == OP_ROT_S) {  // RotatE.py:151-163: qa=cos, qb=sin
+        re = __fsub_rn(__fmaf_rn(-ei, qb, __fmul_rn(er, qa)), or_);
+        im = __fsub_rn(__fmaf_rn(ei, qa, __fmul_rn(er, qb)), oi);
+    } else {  // RotatE.py:208-216: (qa,qb) = rotated subject
+        re = __fsub_rn(qa, er);
+        im = __fsub_rn(qb, ei);
+    }
+    return __fadd_rn(acc, __fsqrt_rn(__fmaf_rn(im, im, __fmul_rn(re, re))));
+}
+template <int OP>
+__device__ __forceinline__ float rank_finish(float acc, float scale)
+{
+    if (OP == OP_DOT) return (scale == 1.f) ? acc : __fmul_rn(scale, acc);  // HolE.py:67-69
+    return -acc;
+}
+
+// --------------------------------------------------------------------------
+// prepare: per-query vectors for both sides + quantised positive score
+// --------------------------------------------------------------------------
+__global__ void kge_rank_qvec_kernel(int model, const float *__restrict__ ent, const float *__restrict__ rel,
+                                     const float *__restrict__ rot, const int32_t *__restrict__ triples, long long b,
+                                     int kp, int ld, float *__restrict__ qs, float *__restrict__ qo,
+                                     float *__restrict__ qaux)
+{
+    const int halves = model_halves(model);
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b * kp) return;
+    long long i = idx / kp;
+    int d = (int)(idx - i * kp);
+    const float *s = ent + (size_t)triples[3 * i] * ld;
+    const float *o = ent + (size_t)triples[3 * i + 2] * ld;
+    const size_t prow = (size_t)triples[3 * i + 1] * ld;
+    float *os = qs + i * ld, *oo = qo + i * ld;
+    if (halves == 1) {
+        float p = rel[prow + d];
+        if (model == KGE_TRANSE) { os[d] = __fsub_rn(p, o[d]); oo[d] = __fadd_rn(s[d], p); }
+        else { os[d] = __fmul_rn(p, o[d]); oo[d] = __fmul_rn(s[d], p); }
+    } else if (model == KGE_ROTATE) {
+        float c = rot[prow + d], sn = rot[prow + kp + d];
+        os[d] = c; os[kp + d] = sn;
+        qaux[i * ld + d] = o[d]; qaux[i * ld + kp + d] = o[kp + d];
+        oo[d] = __fmaf_rn(-s[kp + d], sn, __fmul_rn(s[d], c));
+        oo[kp + d] = __fmaf_rn(s[kp + d], c, __fmul_rn(s[d], sn));
+    } else {
+        float pr = rel[prow + d], pi = rel[prow + kp + d];
+        os[d] = __fmaf_rn(pi, o[kp + d], __fmul_rn(pr, o[d]));        // ComplEx.py:95-99
+        os[kp + d] = __fmaf_rn(-pi, o[d], __fmul_rn(pr, o[kp + d]));   // ComplEx.py:101-106
+        oo[d] = __fmaf_rn(-s[kp + d], pi, __fmul_rn(s[d], pr));        // ComplEx.py:139-143
+        oo[kp + d] = __fmaf_rn(s[d], pi, __fmul_rn(s[kp + d], pr));    // ComplEx.py:145-149
+    }
+}
+
+// positive score, canonical order (one thread per query; b is small)
+__global__ void kge_rank_qpos_kernel(int model, const float *__restrict__ ent, const float *__restrict__ rel,
+                                     const float *__restrict__ rot, const int32_t *__restrict__ triples, long long b,
+                                     int kp, int ld, float scale, int32_t *__restrict__ qpos)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    const float *s = ent + (size_t)triples[3 * i] * ld;
+    const float *o = ent + (size_t)triples[3 * i + 2] * ld;
+    const size_t prow = (size_t)triples[3 * i + 1] * ld;
+    float acc = 0.f, score;
+    if (model == KGE_TRANSE) {
+        for (int d = 0; d < kp; ++d) acc = __fadd_rn(acc, fabsf(__fsub_rn(__fadd_rn(s[d], rel[prow + d]), o[d])));
+        score = -acc;
+    } else if (model == KGE_DISTMULT) {
+        for (int d = 0; d < kp; ++d) acc = __fmaf_rn(__fmul_rn(s[d], rel[prow + d]), o[d], acc);
+        score = acc;
+    } else if (model == KGE_ROTATE) {
+        for (int d = 0; d < kp; ++d) {
+            float c = rot[prow + d], sn = rot[prow + kp + d];
+            float re = __fsub_rn(__fmaf_rn(-s[kp + d], sn, __fmul_rn(s[d], c)), o[d]);
+            float im = __fsub_rn(__fmaf_rn(s[kp + d], c, __fmul_rn(s[d], sn)), o[kp + d]);
+            acc = __fadd_rn(acc, __fsqrt_rn(__fmaf_rn(im, im, __fmul_rn(re, re))));
+        }
+        score = -acc;
+    } else {
+        const float *p = rel + prow;
+        for (int d = 0; d < kp; ++d) acc = __fmaf_rn(s[d], __fmaf_rn(p[kp + d], o[kp + d], __fmul_rn(p[d], o[d])), acc);
+        for (int d = 0; d < kp; ++d) acc = __fmaf_rn(s[kp + d], __fmaf_rn(-p[kp + d], o[d], __fmul_rn(p[d], o[kp + d])), acc);
+        score = (model == KGE_HOLE) ? __fmul_rn(scale, acc) : acc;
+    }
+    qpos[i] = quantise(score);
+}
+
+cudaError_t launch_rank_prepare(const Layout &L, const float *ent, const float *rel, const float *rot,
+                                const int32_t *triples, long long b, float scale, float *qvec_s, float *qvec_o,
+                                float *qaux, int32_t *qpos, cudaStream_t st)
+{
+    if (b == 0) return cudaSuccess;
+    long long n = b * L.kp;
+    kge_rank_qvec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.model, ent, rel, rot, triples, b, L.kp, L.ld,
+                                                                       qvec_s, qvec_o, qaux);
+    kge_rank_qpos_kernel<<<(unsigned)((b + 127) / 128), 128, 0, st>>>(L.model, ent, rel, rot, triples, b, L.kp, L.ld,
+                                                                      scale, qpos);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------
+// tile kernel: CTA = 256 candidates x 32 queries, 8 warps = 2 candidate groups x 4
+// query groups, thread tile = 4 candidates (its own rows) x 8 queries (broadcast).
+// Operands are staged column-chunk by column-chunk with cp.async (16 B, zero-fill
+// past the row end), double buffered.  Shared rows are padded to 36 floats so the
+// per-thread 128-bit row reads are bank-conflict free.
+// --------------------------------------------------------------------------
+constexpr int RK_TC = 256, RK_TQ = 32, RK_DK = 32, RK_LDS = RK_DK + 4, RK_THREADS = 256;
+constexpr int RK_E_FLOATS = RK_TC * RK_LDS, RK_Q_FLOATS = RK_TQ * RK_LDS;
+constexpr int RK_STAGE_FLOATS = RK_E_FLOATS + 2 * RK_Q_FLOATS;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid)
+{
+    unsigned sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int OP>
+__global__ void __launch_bounds__(RK_THREADS) kge_rank_tile_kernel(const RankParams p, int32_t *__restrict__ cnt)
+{
+    constexpr bool ROT = (OP == OP_ROT_S || OP == OP_ROT_O);
+    extern __shared__ __align__(128) float smem[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int cg = warp & 1, qg = warp >> 1;
+    const long long c0 = (long long)blockIdx.x * RK_TC, q0 = (long long)blockIdx.y * RK_TQ;
+    const int ld = p.L.ld, kp = p.L.kp;
+    const int n_chunks = ROT ? (kp + 15) / 16 : (ld + RK_DK - 1) / RK_DK;
+    const int col_end = ROT ? kp : ld;  // valid columns per half (ROT) / per row
+
+    // rows this thread stages: E rows t/8 + 32n (n<8), column quad t%8; Q row t/8
+    const int lrow = t >> 3, c4 = t & 7;
+    const float *erow[8];
+    bool evalid[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        long long c = c0 + lrow + 32 * n;
+        evalid[n] = c < p.n_cand;
+        long long id = evalid[n] ? (p.cand_ids ? (long long)p.cand_ids[c] : p.cand_begin + c) : 0;
+        erow[n] = p.ent + (size_t)id * ld;
+    }
+    const bool qvalid = (q0 + lrow) < p.b;
+    const float *qrow = p.qvec + (size_t)(qvalid ? q0 + lrow : 0) * ld;
+    const float *arow = (OP == OP_ROT_S) ? p.qaux + (size_t)(qvalid ? q0 + lrow : 0) * ld : nullptr;
+
+    auto stage_load = [&](int chunk, int buf) {
+        float *Es = smem + buf * RK_STAGE_FLOATS, *Qs = Es + RK_E_FLOATS, *As = Qs + RK_Q_FLOATS;
+        int col;  // global column of this thread's float4
+        bool cvalid;
+        if (ROT) {
+            int d = chunk * 16 + 4 * (c4 & 3);
+            cvalid = d < col_end;
+            col = (c4 < 4 ? 0 : kp) + d;
+        } else {
+            col = chunk * RK_DK + 4 * c4;
+            cvalid = col < col_end;
+        }
+        if (!cvalid) col = 0;
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+            cp_async16(Es + (lrow + 32 * n) * RK_LDS + 4 * c4, erow[n] + col, cvalid && evalid[n]);
+        cp_async16(Qs + lrow * RK_LDS + 4 * c4, qrow + col, cvalid && qvalid);
+        if (OP == OP_ROT_S) cp_async16(As + lrow * RK_LDS + 4 * c4, arow + col, cvalid && qvalid);
+        cp_async_commit();
+    };
+
+    float acc[4][8];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[m][i] = 0.f;
+
+    stage_load(0, 0);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < n_chunks) { stage_load(ch + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const float *Es = smem + buf * RK_STAGE_FLOATS + (cg * 128 + lane) * RK_LDS;
+        const float *Qs = smem + buf * RK_STAGE_FLOATS + RK_E_FLOATS + (qg * 8) * RK_LDS;
+        const float *As = Qs + RK_Q_FLOATS;
+        if (!ROT) {
+#pragma unroll
+            for (int d4 = 0; d4 < RK_DK / 4; ++d4) {
+                float4 e[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) e[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 4 * d4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 q = *reinterpret_cast<const float4 *>(Qs + i * RK_LDS + 4 * d4);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        float a = acc[m][i];
+                        a = rank_step<OP>(a, e[m].x, q.x);
+                        a = rank_step<OP>(a, e[m].y, q.y);
+                        a = rank_step<OP>(a, e[m].z, q.z);
+                        a = rank_step<OP>(a, e[m].w, q.w);
+                        acc[m][i] = a;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int d4 = 0; d4 < 4; ++d4) {
+                float4 er[4], ei[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    er[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 4 * d4);
+                    ei[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 16 + 4 * d4);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 qa = *reinterpret_cast<const float4 *>(Qs + i * RK_LDS + 4 * d4);
+                    float4 qb = *reinterpret_cast<const float4 *>(Qs + i * RK_LDS + 16 + 4 * d4);
+                    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
+                    if (OP == OP_ROT_S) {
+                        oa = *reinterpret_cast<const float4 *>(As + i * RK_LDS + 4 * d4);
+                        ob = *reinterpret_cast<const float4 *>(As + i * RK_LDS + 16 + 4 * d4);
+                    }
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        float a = acc[m][i];
+                        a = rank_step_rot<OP>(a, er[m].x, ei[m].x, qa.x, qb.x, oa.x, ob.x);
+                        a = rank_step_rot<OP>(a, er[m].y, ei[m].y, qa.y, qb.y, oa.y, ob.y);
+                        a = rank_step_rot<OP>(a, er[m].z, ei[m].z, qa.z, qb.z, oa.z, ob.z);
+                        a = rank_step_rot<OP>(a, er[m].w, ei[m].w, qa.w, qb.w, oa.w, ob.w);
+                        acc[m][i] = a;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // epilogue: quantise, compare with the positive, count over this warp's 128 candidates
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long q = q0 + qg * 8 + i;
+        const bool qok = q < p.b;
+        const int qp = qok ? p.qpos[q] : 0;
+        int gt = 0, eq = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const bool cok = (c0 + cg * 128 + lane + 32 * m) < p.n_cand;
+            const int qc = quantise(rank_finish<OP>(acc[m][i], p.scale));
+            gt += __popc(__ballot_sync(0xffffffffu, cok && (qp < qc)));
+            eq += __popc(__ballot_sync(0xffffffffu, cok && (qp == qc)));
+        }
+        if (lane == 0 && qok) {
+            if (gt) atomicAdd(&cnt[3 * q + 0], gt);
+            if (eq) atomicAdd(&cnt[3 * q + 1], eq);
+        }
+    }
+}
+
+cudaError_t launch_rank_count(const RankParams &p, int32_t *cnt, cudaStream_t st)
+{
+    if (p.b == 0 || p.n_cand == 0) return cudaSuccess;
+    dim3 grid((unsigned)((p.n_cand + RK_TC - 1) / RK_TC), (unsigned)((p.b + RK_TQ - 1) / RK_TQ));
+    const size_t smem = 2 * RK_STAGE_FLOATS * sizeof(float);
+#define KGE_RK(OP)                                                                                           \
+    {                                                                                                        \
+        cudaError_t e = cudaFuncSetAttribute(kge_rank_tile_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem);                                                     \
+        if (e != cudaSuccess) return e;                                                                      \
+        kge_rank_tile_kernel<OP><<<grid, RK_THREADS, smem, st>>>(p, cnt);                                    \
+        break;                                                                                               \
+    }
+    switch (rank_op(p.L.model, p.side)) {
+    case OP_DOT: KGE_RK(OP_DOT)
+    case OP_L1_ADD: KGE_RK(OP_L1_ADD)
+    case OP_L1_SUB: KGE_RK(OP_L1_SUB)
+    case OP_ROT_S: KGE_RK(OP_ROT_S)
+    case OP_ROT_O: KGE_RK(OP_ROT_O)
+    }
+#undef KGE_RK
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------
+// filter kernel (AbstractScoringLayer.py:260-307): one thread per (query, known-true
+// candidate) pair recomputes that candidate's score with the same canonical chain and
+// counts qpos <= q_f (always '<=', whatever the tie strategy).
+// --------------------------------------------------------------------------
+template <int OP>
+__global__ void kge_rank_filter_kernel(const RankParams p, const long long *__restrict__ off,
+                                       const int32_t *__restrict__ idx, int32_t *__restrict__ cnt)
+{
+    constexpr bool ROT = (OP == OP_ROT_S || OP == OP_ROT_O);
+    const long long total = off[p.b];
+    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total) return;
+    long long lo = 0, hi = p.b;  // largest i with off[i] <= f
+    while (hi - lo > 1) {
+        long long mid = (lo + hi) >> 1;
+        if (off[mid] <= f) lo = mid; else hi = mid;
+    }
+    const long long i = lo;
+    const long long pos = idx[f];
+    if (pos < p.cand_begin || pos >= p.cand_begin + p.n_cand) return;  // :280-288
+    const long long id = p.cand_ids ? (long long)p.cand_ids[pos] : pos;
+    const float *e = p.ent + (size_t)id * p.L.ld;
+    const float *q = p.qvec + (size_t)i * p.L.ld;
+    float acc = 0.f;
+    if (!ROT) {
+        for (int d = 0; d < p.L.ld; ++d) acc = rank_step<OP>(acc, e[d], q[d]);
+    } else {
+        const int kp = p.L.kp;
+        const float *a = p.qaux + (size_t)i * p.L.ld;
+        for (int d = 0; d < kp; ++d)
+            acc = rank_step_rot<OP>(acc, e[d], e[kp + d], q[d], q[kp + d], OP == OP_ROT_S ? a[d] : 0.f,
+                                    OP == OP_ROT_S ? a[kp + d] : 0.f);
+    }
+    if (p.qpos[i] <= quantise(rank_finish<OP>(acc, p.scale))) atomicAdd(&cnt[3 * i + 2], 1);
+}
+
+cudaError_t launch_rank_filter_n(const RankParams &p, const long long *filt_off, const int32_t *filt_idx,
+                                 long long n_pairs, int32_t *cnt, cudaStream_t st)
+{
+    if (n_pairs == 0 || p.b == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n_pairs + 127) / 128);
+    switch (rank_op(p.L.model, p.side)) {
+    case OP_DOT: kge_rank_filter_kernel<OP_DOT><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
+    case OP_L1_ADD: kge_rank_filter_kernel<OP_L1_ADD><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
+    case OP_L1_SUB: kge_rank_filter_kernel<OP_L1_SUB><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
+    case OP_ROT_S: kge_rank_filter_kernel<OP_ROT_S><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
+    case OP_ROT_O: kge_rank_filter_kernel<OP_ROT_O><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
+    }
+    return cudaGetLastError();
+}
+
+// ranks[i] += f(strategy)(gt, eq) - filtered   (AbstractScoringLayer.py:218-258, :304-307)
+__global__ void kge_rank_finalize_kernel(const int32_t *__restrict__ cnt, long long b, int strategy,
+                                         int32_t *__restrict__ ranks)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    int gt = cnt[3 * i], eq = cnt[3 * i + 1], fl = cnt[3 * i + 2];
+    int r = (strategy == KGE_RANK_BEST) ? gt : (strategy == KGE_RANK_MIDDLE) ? gt + (eq + 1) / 2 : gt + eq;
+    ranks[i] += r - fl;
+}
+
+cudaError_t launch_rank_finalize(const int32_t *cnt, long long b, int strategy, int32_t *ranks, cudaStream_t st)
+{
+    if (b == 0) return cudaSuccess;
+    kge_rank_finalize_kernel<<<(unsigned)((b + 255) / 256), 256, 0, st>>>(cnt, b, strategy, ranks);
+    return cudaGetLastError();
+}
+
+}  // namespace kge

@@ -1,0 +1,194 @@
+"""KGEEngine: device-memory owner + thin call layer over the C-ABI.
+
+PyTorch tensors hold every byte of device memory (tables, gradient accumulators,
+optimizer slots, batches, outputs); all arithmetic happens in libkge_b200.so.
+This is the object the reference-facing facade
+(ampligraph_b200.latent_features.ScoringBasedEmbeddingModel) drives from its
+fit / predict / evaluate loops, mirroring train_function / predict_function /
+test_function of the reference (models/ScoringBasedEmbeddingModel.py:443, :1719, :1387).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class KGEEngine:
+    def __init__(self, scoring_type, k, eta, n_ent, n_rel, loss="pairwise", loss_params=None,
+                 optimizer="adam", optimizer_params=None, regularizer=None, device=0, neg_group=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("ampligraph_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        if scoring_type not in _lib.SCORING:
+            raise ValueError("Unknown scoring_type: %r" % (scoring_type,))
+        if loss not in _lib.LOSSES:
+            raise ValueError("Could not interpret loss identifier: %r" % (loss,))
+        lp = dict(loss_params or {})
+        reduction = lp.get("reduction", "sum")
+        if reduction not in _lib.REDUCTIONS:
+            raise AssertionError("Invalid value for reduction!")  # loss_functions.py:95-98
+        default_margin = 3.0 if loss == "self_adversarial" else 1.0  # loss_functions.py:23,:29
+        self.scoring_type, self.k, self.eta = scoring_type, int(k), int(eta)
+        self.n_ent, self.n_rel = int(n_ent), int(n_rel)
+        self.device = torch.device("cuda", device)
+        cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), _lib.SCORING[scoring_type], int(k), int(eta), int(n_ent),
+                             int(n_rel), _lib.LOSSES[loss], _lib.REDUCTIONS[reduction],
+                             float(lp.get("margin", default_margin)), float(lp.get("alpha", 0.5)), int(device),
+                             int(neg_group))
+        h = C.c_void_p()
+        _lib.check(self.lib.kge_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.internal_k = self.lib.kge_internal_k(h)
+        self.kp = self.lib.kge_half_stride(h)
+        self.ld = self.lib.kge_row_stride(h)
+        with torch.cuda.device(self.device):
+            z = lambda rows: torch.zeros((rows, self.ld), dtype=torch.float32, device=self.device)
+            self.ent, self.rel = z(self.n_ent), z(self.n_rel)
+            self.g_ent, self.g_rel = z(self.n_ent), z(self.n_rel)
+            self.loss_acc = torch.zeros(2, dtype=torch.float64, device=self.device)  # [batch loss, reg loss]
+        self.set_optimizer(optimizer, optimizer_params, regularizer)
+        self.launches = 0  # kernels launched by this engine (bench.py reports it)
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.kge_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- optimizer state (optimizers.py:255-291) ---------------------------
+    def set_optimizer(self, name="adam", params=None, regularizer=None):
+        name = name.lower()
+        if name not in _lib.OPTIMIZERS:
+            raise ValueError("Could not interpret optimizer identifier: %r" % (name,))
+        p = dict(params or {})
+        reg = dict(regularizer or {})
+        self.opt_cfg = _lib.KgeOptimizerConfig(
+            C.sizeof(_lib.KgeOptimizerConfig), _lib.OPTIMIZERS[name], float(p.get("learning_rate", 0.001)),
+            float(p.get("beta_1", 0.9)), float(p.get("beta_2", 0.999)), float(p.get("epsilon", 1e-7)),
+            float(p.get("momentum", 0.0)), float(p.get("initial_accumulator_value", 0.1)),
+            int(reg.get("p", 2)) if regularizer else 0, float(reg.get("lambda", 1e-5)))
+        self.opt_name = name
+        self.t = 0
+        mk = lambda rows, v=0.0: torch.full((rows, self.ld), v, dtype=torch.float32, device=self.device)
+        self.slots = {"ent": [None, None], "rel": [None, None]}
+        if name == "adam":
+            for key, rows in (("ent", self.n_ent), ("rel", self.n_rel)):
+                self.slots[key] = [mk(rows), mk(rows)]
+        elif name == "adagrad":
+            for key, rows in (("ent", self.n_ent), ("rel", self.n_rel)):
+                acc = mk(rows, self.opt_cfg.initial_accumulator_value)
+                self.slots[key] = [acc, None]
+        elif self.opt_cfg.momentum != 0.0:
+            for key, rows in (("ent", self.n_ent), ("rel", self.n_rel)):
+                self.slots[key] = [mk(rows), None]
+
+    # -- tables ------------------------------------------------------------
+    def set_embeddings(self, ent_dense=None, rel_dense=None):
+        """dense [rows, internal_k] (numpy / torch) -> padded device layout."""
+        for dense, table, rows in ((ent_dense, self.ent, self.n_ent), (rel_dense, self.rel, self.n_rel)):
+            if dense is None:
+                continue
+            d = torch.as_tensor(np.ascontiguousarray(dense, dtype=np.float32) if not torch.is_tensor(dense) else dense)
+            d = d.to(self.device, torch.float32).contiguous()
+            if tuple(d.shape) != (rows, self.internal_k):
+                raise ValueError("expected shape %s, got %s" % ((rows, self.internal_k), tuple(d.shape)))
+            _lib.check(self.lib.kge_pack_rows(self.h, _ptr(d), _ptr(table), rows, self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()  # d may be freed after return
+
+    def get_embeddings(self):
+        out = []
+        for table, rows in ((self.ent, self.n_ent), (self.rel, self.n_rel)):
+            d = torch.empty((rows, self.internal_k), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.kge_unpack_rows(self.h, _ptr(table), _ptr(d), rows, self._stream()))
+            out.append(d)
+        return out[0], out[1]
+
+    def init_glorot_uniform(self, seed=0):
+        _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.ent), self.n_ent, int(seed) * 2 + 0, self._stream()))
+        _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.rel), self.n_rel, int(seed) * 2 + 1, self._stream()))
+
+    # -- training ------------------------------------------------------------
+    def forward_backward(self, triples, negatives=None, seed=0, step=0, mode=_lib.STEP_FUSED,
+                         scores_pos=None, scores_neg=None, dpos=None, dneg=None):
+        """train_step up to tape.gradient: accumulates into g_ent/g_rel and loss_acc[0]."""
+        assert triples.dtype == torch.int32 and triples.is_cuda and triples.is_contiguous()
+        B = triples.shape[0]
+        neg_ent = neg_keep = None
+        if negatives is not None:
+            neg_ent, neg_keep = negatives
+            assert neg_ent.dtype == torch.int32 and neg_keep.dtype == torch.uint8
+            assert neg_ent.numel() == B * self.eta and neg_keep.numel() == B * self.eta
+        _lib.check(self.lib.kge_train_step(
+            self.h, mode, _ptr(self.ent), _ptr(self.rel), _ptr(self.g_ent), _ptr(self.g_rel), _ptr(triples), B,
+            _ptr(neg_ent), _ptr(neg_keep), int(seed), int(step), _ptr(self.loss_acc), _ptr(scores_pos),
+            _ptr(scores_neg), _ptr(dpos), _ptr(dneg), self._stream()))
+        self.launches += 2 if self.scoring_type == "RotatE" else 1
+
+    def apply_gradients(self):
+        """optimizer.apply_gradients on both tables (dense semantics) + LP regulariser."""
+        self.t += 1
+        for key, table, grad, rows in (("ent", self.ent, self.g_ent, self.n_ent),
+                                       ("rel", self.rel, self.g_rel, self.n_rel)):
+            s0, s1 = self.slots[key]
+            _lib.check(self.lib.kge_optimizer_step(
+                self.h, C.byref(self.opt_cfg), self.t, _ptr(table), _ptr(grad), _ptr(s0), _ptr(s1), rows,
+                C.c_void_p(self.loss_acc.data_ptr() + 8), self._stream()))
+        self.launches += 2
+
+    def train_step(self, triples, negatives=None, seed=0, step=None):
+        """One reference train_step (models/ScoringBasedEmbeddingModel.py:370-429)."""
+        self.forward_backward(triples, negatives, seed, self.t if step is None else step)
+        self.apply_gradients()
+
+    def read_loss(self, reset=True):
+        """(batch loss + regulariser loss) accumulated since the last reset; synchronises."""
+        v = self.loss_acc.sum().item()
+        if reset:
+            self.loss_acc.zero_()
+        return v
+
+    def generate_corruptions(self, triples, seed=0, step=0):
+        out = torch.empty((triples.shape[0] * self.eta, 3), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.kge_generate_corruptions(self.h, _ptr(triples), triples.shape[0], int(seed), int(step),
+                                                     _ptr(out), self._stream()))
+        return out
+
+    # -- inference -------------------------------------------------------------
+    def score(self, triples):
+        assert triples.dtype == torch.int32 and triples.is_cuda and triples.is_contiguous()
+        out = torch.empty(triples.shape[0], dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.kge_score_triples(self.h, _ptr(self.ent), _ptr(self.rel), _ptr(triples), triples.shape[0],
+                                              _ptr(out), self._stream()))
+        self.launches += 2 if self.scoring_type == "RotatE" else 1
+        return out
+
+    def rank(self, triples, side, strategy="worst", filt_off=None, filt_idx=None, cand_ids=None, cand_begin=0,
+             n_cand=None, out=None):
+        """get_ranks for one side: returns/accumulates int32 counts (caller adds 1)."""
+        assert triples.dtype == torch.int32 and triples.is_cuda and triples.is_contiguous()
+        b = triples.shape[0]
+        if out is None:
+            out = torch.zeros(b, dtype=torch.int32, device=self.device)
+        if n_cand is None:
+            n_cand = cand_ids.numel() if cand_ids is not None else self.n_ent - cand_begin
+        n_filt = int(filt_idx.numel()) if filt_idx is not None else 0
+        _lib.check(self.lib.kge_rank(self.h, _lib.SIDES[side], _lib.STRATEGIES[strategy], _ptr(self.ent), _ptr(self.rel),
+                                     _ptr(triples), b, _ptr(cand_ids), int(cand_begin), int(n_cand), _ptr(filt_off),
+                                     _ptr(filt_idx), n_filt, _ptr(out), self._stream()))
+        self.launches += 5
+        return out

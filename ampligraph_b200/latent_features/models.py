@@ -1,0 +1,311 @@
+"""ScoringBasedEmbeddingModel facade: the reference's fit / predict / evaluate surface
+(ampligraph/latent_features/models/ScoringBasedEmbeddingModel.py) re-hosted on
+KGEEngine.  Only the loops and the host-side data plumbing live here; every number is
+produced by libkge_b200.so.
+"""
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..datasets import DataIndexer, FilterIndex
+from ..engine import KGEEngine
+from ..evaluation import hits_at_n_score, mr_score, mrr_score
+from . import loss_functions, optimizers, regularizers
+from .layers.scoring import SCORING_LAYER_REGISTRY
+
+
+class History:
+    """Stand-in for the Keras History callback object returned by fit()."""
+
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+    def _log(self, epoch, logs):
+        self.epoch.append(epoch)
+        for k, v in logs.items():
+            self.history.setdefault(k, []).append(v)
+
+
+class ScoringBasedEmbeddingModel:
+    """Same constructor as the reference (ScoringBasedEmbeddingModel.py:100-171)."""
+
+    def __init__(self, eta, k, scoring_type="DistMult", seed=0, max_ent_size=None, max_rel_size=None):
+        if scoring_type not in SCORING_LAYER_REGISTRY:
+            raise KeyError(scoring_type)  # the reference indexes the registry directly (:146)
+        self.eta, self.k, self.scoring_type, self.seed = int(eta), int(k), scoring_type, seed
+        self.max_ent_size, self.max_rel_size = max_ent_size, max_rel_size
+        self.scoring_layer = SCORING_LAYER_REGISTRY[scoring_type](k)
+        self.internal_k = self.scoring_layer.internal_k
+        self.data_indexer = True
+        self.is_fitted = False
+        self.is_calibrated = False
+        self.is_partitioned_training = False
+        self._is_compiled = False
+        self.engine = None
+        self.device = 0
+        self._loss_sum, self._loss_cnt = 0.0, 0  # never-reset running Mean metric (loss_functions.py:101,:224)
+        self._initial_tables = None
+        self._step = 0
+
+    # ------------------------------------------------------------------ compile
+    def compile(self, optimizer="adam", loss=None, entity_relation_initializer="glorot_uniform",
+                entity_relation_regularizer=None, **kwargs):
+        """compile (:1145-1318).  entity_relation_initializer: 'glorot_uniform' | ndarray |
+        callable(shape)->ndarray | list of two of those (entities, relations)."""
+        self.optimizer = optimizers.get(optimizer)
+        self.compiled_loss = loss_functions.get(loss)
+        init = entity_relation_initializer
+        self._initializer = list(init) if isinstance(init, (list, tuple)) else [init, init]
+        assert len(self._initializer) == 2, "Incorrect length for initializer. Assumed 2 got {}".format(len(self._initializer))
+        if self.scoring_type == "RotatE":  # :1312-1315
+            assert isinstance(self._initializer[1], str) and self._initializer[1] == "glorot_uniform", \
+                "The relation initializer provided to a RotatE model must be glorot_uniform!"
+        self._regularizer = regularizers.get(entity_relation_regularizer)
+        self._loss_sum, self._loss_cnt = 0.0, 0
+        self._is_compiled = True
+        self.engine = None  # tables are (re)built lazily on the first fit, like EmbeddingLookupLayer.build
+
+    def _assert_compile_was_called(self):
+        if not self._is_compiled:
+            raise RuntimeError("You must compile your model before training/testing. Use `model.compile(optimizer, loss)`.")
+
+    def is_fit(self):
+        return self.is_fitted
+
+    # ------------------------------------------------------------------ engine
+    def _build_engine(self):
+        name, lp = self.compiled_loss.kernel_params()
+        reg = self._regularizer.kernel_params() if self._regularizer is not None else None
+        self.engine = KGEEngine(self.scoring_type, self.k, self.eta, self.max_ent_size, self.max_rel_size,
+                                loss=name or "pairwise", loss_params=lp, optimizer=self.optimizer.name,
+                                optimizer_params=self.optimizer.hyperparams, regularizer=reg, device=self.device)
+        dense = [None, None]
+        for n, (init, rows) in enumerate(zip(self._initializer, (self.max_ent_size, self.max_rel_size))):
+            if isinstance(init, str):
+                if init != "glorot_uniform":
+                    raise ValueError("Unknown initializer: %r (use 'glorot_uniform', an array or a callable)" % init)
+            elif callable(init):
+                dense[n] = np.asarray(init((rows, self.internal_k)), dtype=np.float32)
+            else:
+                dense[n] = np.asarray(init, dtype=np.float32)
+        self.engine.init_glorot_uniform(self.seed)
+        self.engine.set_embeddings(dense[0], dense[1])
+        self._step = 0
+
+    def _to_dev(self, a, dtype):
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).pin_memory().to(self.engine.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ indexing
+    def _index(self, x, fit=False):
+        x = np.asarray(x)
+        if self.data_indexer is False:  # use_indexer=False: data is already int ids
+            return np.ascontiguousarray(x[:, :3], dtype=np.int32)
+        if fit and not isinstance(self.data_indexer, DataIndexer):
+            self.data_indexer = DataIndexer(x[:, :3])
+        return self.data_indexer.get_indexes(x[:, :3], "t", "raw2ind")
+
+    def get_indexes(self, X, type_of="t", order="raw2ind"):
+        return self.data_indexer.get_indexes(X, type_of, order)
+
+    def get_count(self, concept_type="e"):
+        if concept_type == "e":
+            return self.data_indexer.get_entities_count()
+        if concept_type == "r":
+            return self.data_indexer.get_relations_count()
+        raise ValueError("Invalid Concept Type (expected 'e' or 'r')")
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, x=None, batch_size=1000, epochs=100, verbose=True, callbacks=None, validation_split=0.0,
+            validation_data=None, shuffle=True, initial_epoch=0, validation_batch_size=10,
+            validation_corrupt_side="s,o", validation_freq=10, validation_burn_in=0, validation_filter=False,
+            validation_entities_subset=None, partitioning_k=1, focusE=False, focusE_params={}):
+        """fit (:544-883).  `shuffle` is accepted and ignored exactly like the reference
+        (batches are the sequential slices of graph_data_loader.py:495-500)."""
+        self._assert_compile_was_called()
+        if partitioning_k != 1:
+            raise NotImplementedError("bucket partitioning is replaced by HBM-resident tables (DESIGN.md)")
+        if focusE:
+            raise NotImplementedError("FocusE is outside the hot-path scope of this round (SURVEY.md 8f)")
+        triples = self._index(x, fit=True)
+        if self.data_indexer is not False:
+            self.max_ent_size = self.data_indexer.get_entities_count()
+            self.max_rel_size = self.data_indexer.get_relations_count()
+        elif self.max_ent_size is None or self.max_rel_size is None:
+            self.max_ent_size = int(max(triples[:, 0].max(), triples[:, 2].max())) + 1
+            self.max_rel_size = int(triples[:, 1].max()) + 1
+        if self.engine is None:
+            self._build_engine()
+        eng = self.engine
+        data = self._to_dev(triples, np.int32)  # uploaded once; batches are device-side slices
+        n = data.shape[0]
+        batch_size = int(batch_size)
+        history = History()
+        user_loss = isinstance(self.compiled_loss, loss_functions.LossFunctionWrapper)
+        for epoch in range(initial_epoch, epochs):
+            for start in range(0, n, batch_size):
+                batch = data[start:start + batch_size]
+                if user_loss:
+                    self._user_loss_step(batch)
+                else:
+                    eng.forward_backward(batch, None, seed=self.seed, step=self._step)
+                    eng.apply_gradients()
+                self._step += 1
+                self._loss_cnt += 1
+            # per-batch losses accumulate on the device; one read-back per epoch (the logged value is
+            # the reference's never-reset running mean of per-batch SUM losses)
+            self._loss_sum += eng.read_loss()
+            logs = {"loss": self._loss_sum / max(self._loss_cnt, 1)}
+            validate = (epoch >= (validation_burn_in - 1) and validation_data is not None
+                        and (epoch + 1) % validation_freq == 0)
+            if validate:
+                self.is_fitted = True
+                ranks = self.evaluate(validation_data, batch_size=validation_batch_size or batch_size, verbose=False,
+                                      use_filter=validation_filter, corrupt_side=validation_corrupt_side,
+                                      entities_subset=validation_entities_subset, dataset_type="valid")
+                logs.update({"val_mrr": mrr_score(ranks), "val_mr": mr_score(ranks),
+                             "val_hits@1": hits_at_n_score(ranks, 1), "val_hits@10": hits_at_n_score(ranks, 10),
+                             "val_hits@100": hits_at_n_score(ranks, 100)})
+            history._log(epoch, logs)
+            if verbose:
+                print("Epoch %d/%d - " % (epoch + 1, epochs) + " - ".join("%s: %.4f" % kv for kv in logs.items()))
+        self.is_fitted = True
+        self.history = history
+        return history
+
+    def train_on_batch(self, x):
+        """Keras Model.train_on_batch (the reference model is a tf.keras.Model): one train_step on ONE
+        host batch -- H2D copy of the batch, fused step, D2H read of the batch loss, which is returned.
+        x: [B,3] raw triples (numpy) or an int32 torch tensor of already indexed ids (pinned for speed)."""
+        self._assert_compile_was_called()
+        if torch.is_tensor(x):
+            host = x
+        else:
+            host = torch.as_tensor(self._index(x, fit=self.engine is None))
+        if self.engine is None:
+            if self.data_indexer is not False:
+                self.max_ent_size = self.data_indexer.get_entities_count()
+                self.max_rel_size = self.data_indexer.get_relations_count()
+            self._build_engine()
+        batch = host.to(self.engine.device, non_blocking=True)
+        if isinstance(self.compiled_loss, loss_functions.LossFunctionWrapper):
+            self._user_loss_step(batch)
+        else:
+            self.engine.forward_backward(batch, None, seed=self.seed, step=self._step)
+            self.engine.apply_gradients()
+        self._step += 1
+        loss = self.engine.read_loss()
+        self._loss_sum += loss
+        self._loss_cnt += 1
+        self.is_fitted = True
+        return loss
+
+    def _user_loss_step(self, batch):
+        """LossFunctionWrapper path: scores from the kernel, dL/dscore from torch autograd."""
+        eng, B = self.engine, batch.shape[0]
+        neg = eng.generate_corruptions(batch, self.seed, self._step)
+        tiled = batch.repeat(self.eta, 1)
+        keep = (neg[:, 0] == tiled[:, 0]).to(torch.uint8).contiguous()
+        repl = torch.where(keep.bool(), neg[:, 2], neg[:, 0]).contiguous()
+        sp = torch.empty(B, dtype=torch.float32, device=eng.device)
+        sn = torch.empty(B * self.eta, dtype=torch.float32, device=eng.device)
+        eng.forward_backward(batch, (repl, keep), mode=_lib.STEP_FORWARD_ONLY, scores_pos=sp, scores_neg=sn)
+        spg, sng = sp.requires_grad_(True), sn.requires_grad_(True)
+        loss = self.compiled_loss._user_losses(spg, sng.reshape(self.eta, -1)).sum()
+        loss.backward()
+        eng.forward_backward(batch, (repl, keep), mode=_lib.STEP_BACKWARD_EXT, dpos=spg.grad.contiguous(),
+                             dneg=sng.grad.contiguous())
+        eng.apply_gradients()
+        eng.loss_acc[0] += loss.detach().double()
+
+    # ------------------------------------------------------------------ predict
+    def predict(self, x, batch_size=32, verbose=0, callbacks=None):
+        """predict (:1736-1823): fp32 scores; triples with unknown labels are dropped."""
+        if not self.is_fitted:
+            raise RuntimeError("Model has not been fitted.")
+        t = self._index(x)
+        if len(t) == 0:
+            return np.zeros(0, np.float32)
+        return self.engine.score(self._to_dev(t, np.int32)).cpu().numpy()
+
+    # ------------------------------------------------------------------ evaluate
+    def evaluate(self, x=None, batch_size=10, verbose=True, use_filter=False, corrupt_side="s,o",
+                 entities_subset=None, ranking_strategy="worst", callbacks=None, dataset_type="test"):
+        """evaluate (:1516-1692) -> int32 ranks [n, 2] for 's,o', [n, 1] otherwise.
+        `batch_size` only lower-bounds the device chunk: results do not depend on it."""
+        assert corrupt_side in ["s", "o", "s,o", "s+o"], "Invalid value for corrupt_side"
+        assert ranking_strategy in ["best", "middle", "worst"], "Invalid value for ranking_strategy"
+        if not self.is_fitted:
+            raise RuntimeError("Model has not been fitted.")
+        eng = self.engine
+        t = self._index(x)
+        n = len(t)
+        sides = [s for s in ("s", "o") if s in corrupt_side]
+        # candidates: all entities or a subset (:1634-1643)
+        cand_ids, position_of = None, None
+        if entities_subset is not None:
+            sub = self.get_indexes(np.asarray(entities_subset), "e") if self.data_indexer is not False \
+                else np.asarray(entities_subset, np.int32)
+            cand_ids = self._to_dev(sub, np.int32)
+            position_of = np.full(self.max_ent_size, -1, np.int64)
+            position_of[sub] = np.arange(len(sub))
+        # filters: dict of datasets (train/valid/test), or True = the evaluated data itself
+        findex = None
+        if isinstance(use_filter, dict) or use_filter is True:
+            parts = [t] if use_filter is True else [self._index(v) for v in use_filter.values()]
+            findex = FilterIndex(np.concatenate(parts), self.max_ent_size)
+        out = np.zeros((n, len(sides)), np.int32)
+        chunk = max(int(batch_size), 4096)
+        for start in range(0, n, chunk):
+            tb = t[start:start + chunk]
+            td = self._to_dev(tb, np.int32)
+            for j, side in enumerate(sides):
+                off = idx = None
+                if findex is not None:
+                    o_np, i_np = findex.lookup(tb, side, position_of)
+                    off, idx = self._to_dev(o_np, np.int64), self._to_dev(i_np, np.int32)
+                r = eng.rank(td, side, ranking_strategy, off, idx, cand_ids=cand_ids)
+                out[start:start + len(tb), j] = r.cpu().numpy()
+        if corrupt_side == "s+o":  # :1459-1463 sum BEFORE the +1
+            out = out.sum(1, keepdims=True)
+        return (out + 1).astype(np.int32)  # :1684
+
+    # ------------------------------------------------------------------ embeddings / weights
+    def get_embeddings(self, entities, embedding_type="e"):
+        """get_embeddings (:2214): rows of the dense [rows, internal_k] tables."""
+        if not self.is_fitted:
+            raise RuntimeError("Model has not been fitted.")
+        if embedding_type not in ("e", "r"):
+            raise ValueError("Invalid entity type: %s" % embedding_type)
+        ent, rel = self.engine.get_embeddings()
+        idx = self.get_indexes(np.asarray(entities), embedding_type) if self.data_indexer is not False \
+            else np.asarray(entities, np.int64)
+        table = ent if embedding_type == "e" else rel
+        return table[torch.as_tensor(idx, dtype=torch.long, device=table.device)].cpu().numpy()
+
+    def save_weights(self, filepath):
+        """Tables + optimizer slots + indexer in one pickle (the reference's Keras format is TF-specific)."""
+        ent, rel = self.engine.get_embeddings()
+        state = {"ent": ent.cpu().numpy(), "rel": rel.cpu().numpy(), "t": self.engine.t, "step": self._step,
+                 "slots": {k: [None if s is None else s.cpu().numpy() for s in v] for k, v in self.engine.slots.items()},
+                 "indexer": self.data_indexer, "max_ent_size": self.max_ent_size, "max_rel_size": self.max_rel_size}
+        with open(filepath, "wb") as f:
+            pickle.dump(state, f)
+
+    def load_weights(self, filepath):
+        self._assert_compile_was_called()
+        with open(filepath, "rb") as f:
+            state = pickle.load(f)
+        self.data_indexer = state["indexer"]
+        self.max_ent_size, self.max_rel_size = state["max_ent_size"], state["max_rel_size"]
+        self._build_engine()
+        self.engine.set_embeddings(state["ent"], state["rel"])
+        self.engine.t, self._step = state["t"], state["step"]
+        for k, v in state["slots"].items():
+            for n, s in enumerate(v):
+                if s is not None:
+                    self.engine.slots[k][n].copy_(torch.as_tensor(s))
+        self.is_fitted = True

@@ -1,0 +1,191 @@
+/*
+ * kge_b200.h -- C-ABI of libkge_b200.so, the sm_100a replacement for AmpliGraph's
+ * per-batch training step and all-entity ranking step.
+ *
+ * The reference has no FFI: its boundary is two Python registries and three
+ * step closures.  Each entry point below names the reference
+ * code it replaces (paths under ampligraph/latent_features/ of the reference).
+ * A Python maintainer binds these with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every `*_dev` / table / output pointer is a DEVICE
+ *     pointer owned by the caller (PyTorch tensors in the shipped facade); the
+ *     library borrows it for the duration of the call and allocates nothing
+ *     persistent except the small per-handle workspace created by kge_create.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
+ *     work is stream-ordered, no entry point synchronises the device.
+ *   - return value: 0 = ok, otherwise a kge_status; text via kge_last_error().
+ *   - one caller thread per handle; different handles (one per GPU) may be
+ *     driven from different threads.
+ *
+ * Embedding-table layout in HBM ("row-padded split-complex")
+ *   A table is [rows, ld] fp32, row-major.  TransE/DistMult rows hold k values
+ *   padded with zeros to kp = round_up(k,4) floats (ld = kp).  ComplEx/HolE/
+ *   RotatE rows hold the real half then the imaginary half, EACH padded to kp
+ *   floats (ld = 2*kp).  Rows are therefore 16-byte multiples, which is what
+ *   cp.async.bulk / cp.reduce.async.bulk need.  Pad columns are zero and stay
+ *   zero.  kge_pack_rows / kge_unpack_rows convert from/to the reference's
+ *   dense [rows, internal_k] layout (EmbeddingLookupLayer.py:194-237).
+ */
+#ifndef KGE_B200_H
+#define KGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGE_B200_ABI_VERSION 1
+
+typedef struct kge_handle kge_handle;
+
+enum kge_status {
+    KGE_OK = 0,
+    KGE_ERR_INVALID_ARGUMENT = 1, /* facade raises ValueError */
+    KGE_ERR_CUDA = 2,             /* facade raises RuntimeError */
+    KGE_ERR_UNSUPPORTED = 3       /* facade raises NotImplementedError */
+};
+
+/* SCORING_LAYER_REGISTRY names, layers/scoring/AbstractScoringLayer.py:15 */
+enum kge_scoring { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_COMPLEX = 2, KGE_HOLE = 3, KGE_ROTATE = 4 };
+
+/* LOSS_REGISTRY names, loss_functions.py:17; KGE_LOSS_EXTERNAL = LossFunctionWrapper
+ * (:657): the caller differentiates its own loss on the scores and hands back
+ * d loss / d score (see kge_train_step). */
+enum kge_loss {
+    KGE_LOSS_PAIRWISE = 0,
+    KGE_LOSS_NLL = 1,
+    KGE_LOSS_ABSOLUTE_MARGIN = 2,
+    KGE_LOSS_SELF_ADVERSARIAL = 3,
+    KGE_LOSS_MULTICLASS_NLL = 4
+};
+enum kge_reduction { KGE_REDUCE_SUM = 0, KGE_REDUCE_MEAN = 1 }; /* loss_functions.py:124-129 */
+enum kge_optimizer { KGE_OPT_SGD = 0, KGE_OPT_ADAM = 1, KGE_OPT_ADAGRAD = 2 };
+enum kge_side { KGE_SIDE_S = 0, KGE_SIDE_O = 1 };
+enum kge_rank_strategy { KGE_RANK_WORST = 0, KGE_RANK_BEST = 1, KGE_RANK_MIDDLE = 2 };
+enum kge_step_mode {
+    KGE_STEP_FUSED = 0,         /* scores -> built-in loss -> gradients, one kernel */
+    KGE_STEP_FORWARD_ONLY = 1,  /* scores only (user-callable loss / FocusE, phase 1) */
+    KGE_STEP_BACKWARD_EXT = 2   /* gradients from caller-supplied dL/dscore (phase 2) */
+};
+
+/* ScoringBasedEmbeddingModel.__init__ (models/ScoringBasedEmbeddingModel.py:100-171)
+ * + compile(loss=...) (:1303) + loss hyper-parameters (loss_functions.py:23-29). */
+typedef struct kge_config {
+    int32_t struct_size;  /* sizeof(kge_config), ABI guard */
+    int32_t scoring;      /* enum kge_scoring */
+    int32_t k;            /* user-facing embedding size; internal_k = k or 2k */
+    int32_t eta;          /* negatives per positive */
+    int64_t n_ent;        /* max_ent_size: rows of ent_emb; corruptions are drawn from [0,n_ent) */
+    int64_t n_rel;        /* max_rel_size: rows of rel_emb (RotatE phase normalisation uses it) */
+    int32_t loss;         /* enum kge_loss */
+    int32_t reduction;    /* enum kge_reduction */
+    float margin;         /* pairwise / absolute_margin / self_adversarial */
+    float alpha;          /* self_adversarial temperature */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t neg_group;    /* 0 = auto; >0 forces that many negatives resident per pass (testing) */
+} kge_config;
+
+/* optimizers.get (optimizers.py:255-291) -> tf.keras.optimizers.legacy.{SGD,Adam,Adagrad};
+ * regularizers.LP_regularizer (regularizers.py:14-37) folded into the update. */
+typedef struct kge_optimizer_config {
+    int32_t struct_size;
+    int32_t kind;         /* enum kge_optimizer */
+    float learning_rate;  /* default 0.001 (optimizers.py:284) */
+    float beta_1, beta_2; /* Adam: 0.9, 0.999 */
+    float epsilon;        /* 1e-7 */
+    float momentum;       /* SGD: 0 */
+    float initial_accumulator_value; /* Adagrad: 0.1 */
+    int32_t reg_p;        /* 0 = no regulariser, else p of LP (2, 3, ...) */
+    float reg_lambda;     /* LP lambda (default 1e-5) */
+} kge_optimizer_config;
+
+const char *kge_last_error(void);
+int kge_abi_version(void);
+
+int kge_create(const kge_config *cfg, kge_handle **out);
+void kge_destroy(kge_handle *h);
+
+/* layout queries: internal_k (ComplEx.py:37, RotatE.py:57), padded half, row stride */
+int32_t kge_internal_k(const kge_handle *h);
+int32_t kge_half_stride(const kge_handle *h); /* kp */
+int32_t kge_row_stride(const kge_handle *h);  /* ld, floats */
+
+/* dense [rows, internal_k] <-> padded device layout [rows, ld]; both device pointers. */
+int kge_pack_rows(kge_handle *h, const float *dense_dev, float *table_dev, int64_t rows, void *stream);
+int kge_unpack_rows(kge_handle *h, const float *table_dev, float *dense_dev, int64_t rows, void *stream);
+
+/* EmbeddingLookupLayer.build with the default 'glorot_uniform' initialiser
+ * (EmbeddingLookupLayer.py:194-201): U(-l, l), l = sqrt(6/(rows+internal_k)),
+ * from a Philox4x32-10 counter stream (TF's own stream is not reproducible). */
+int kge_init_glorot_uniform(kge_handle *h, float *table_dev, int64_t rows, uint64_t seed, void *stream);
+
+/* predict_step (ScoringBasedEmbeddingModel.py:1694-1699): gather + _compute_scores. */
+int kge_score_triples(kge_handle *h, const float *ent_dev, const float *rel_dev,
+                      const int32_t *triples_dev /*[n,3]*/, int64_t n, float *scores_dev /*[n]*/,
+                      void *stream);
+
+/* CorruptionGenerationLayerTrain.call (CorruptionGenerationLayerTrain.py:35-94):
+ * writes the [eta*B,3] corruption tensor (row j*B+i = j-th corruption of positive i)
+ * the fused kernel would draw for (seed, step).  Needed only for inspection / parity. */
+int kge_generate_corruptions(kge_handle *h, const int32_t *triples_dev, int64_t B, uint64_t seed,
+                             uint64_t step, int32_t *corruptions_dev /*[eta*B,3]*/, void *stream);
+
+/* train_step forward+backward (ScoringBasedEmbeddingModel.py:370-429, call :237-269,
+ * Loss.__call__ loss_functions.py:185-225, tape.gradient optimizers.py:166).
+ *   triples_dev     [B,3] int32 positives
+ *   neg_ent_dev     [eta*B] int32 replacement entity ids in tile order, or NULL to draw
+ *                   them in-kernel from Philox(seed, step)
+ *   neg_keep_subj_dev [eta*B] uint8, 1 = subject kept / object replaced (the reference's
+ *                   keep_subj_mask); must be non-NULL iff neg_ent_dev is
+ *   grad_*_dev      [rows, ld] fp32 gradient accumulators, ADDED to (zero them or let
+ *                   kge_optimizer_step do it)
+ *   loss_dev        double accumulator, += sum over the batch of the per-positive loss
+ *                   (FUSED mode only; may be NULL)
+ *   scores_pos_dev  [B] (may be NULL); scores_neg_dev [eta*B] tile order (may be NULL):
+ *                   written in FUSED and FORWARD_ONLY modes
+ *   dpos_dev/dneg_dev  dL/dscore inputs for BACKWARD_EXT mode (else NULL) */
+int kge_train_step(kge_handle *h, int32_t mode, const float *ent_dev, const float *rel_dev,
+                   float *grad_ent_dev, float *grad_rel_dev, const int32_t *triples_dev, int64_t B,
+                   const int32_t *neg_ent_dev, const uint8_t *neg_keep_subj_dev, uint64_t seed,
+                   uint64_t step, double *loss_dev, float *scores_pos_dev, float *scores_neg_dev,
+                   const float *dpos_dev, const float *dneg_dev, void *stream);
+
+/* OptimizerWrapper.minimize -> legacy apply_gradients (optimizers.py:136-168) for ONE
+ * table, dense semantics, plus the LP regulariser's loss/gradient over the whole table
+ * (regularizers.py:14-37; added to the loss at loss_functions.py:215-223).
+ *   t            1-based iteration count (Adam bias correction)
+ *   slot0/slot1  Adam m,v / SGD momentum,- / Adagrad accumulator,-  ([rows,ld] or NULL)
+ *   reg_loss_dev double accumulator += lambda*sum|x|^p of the PRE-update table (may be NULL)
+ * The gradient buffer is zeroed on the way out. */
+int kge_optimizer_step(kge_handle *h, const kge_optimizer_config *opt, int64_t t, float *table_dev,
+                       float *grad_dev, float *slot0_dev, float *slot1_dev, int64_t rows,
+                       double *reg_loss_dev, void *stream);
+
+/* test_function / get_ranks (ScoringBasedEmbeddingModel.py:1387-1465,
+ * layers/scoring/AbstractScoringLayer.py:156-422) for one corruption side.
+ *   cand_ids_dev  NULL: candidates are entity rows [cand_begin, cand_begin+n_cand) of
+ *                 ent_dev (get_emb_matrix_test :1329; a row shard when sharded);
+ *                 else [n_cand] int32 entity ids (entities_subset, :1634-1643)
+ *   filt_off_dev  [b+1] int64 CSR offsets or NULL (unfiltered); filt_idx_dev = candidate
+ *                 POSITIONS (entity id when cand_ids_dev is NULL, subset position
+ *                 otherwise) of the known-true entities; positions outside
+ *                 [cand_begin, cand_begin+n_cand) are ignored (:280-288);
+ *                 n_filt = total number of filter entries (= filt_off[b], known to the host)
+ *   ranks_dev     [b] int32, += count (so shards/sides can accumulate); the caller
+ *                 adds 1 (ScoringBasedEmbeddingModel.py:1684) */
+int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const float *ent_dev,
+             const float *rel_dev, const int32_t *triples_dev, int64_t b,
+             const int32_t *cand_ids_dev, int64_t cand_begin, int64_t n_cand,
+             const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
+             int32_t *ranks_dev, void *stream);
+
+/* size in bytes of the device workspace kge_rank needs for b queries (allocated
+ * internally and cached on the handle; exposed so callers can budget HBM). */
+int64_t kge_rank_workspace_bytes(const kge_handle *h, int64_t b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGE_B200_H */

@@ -1,0 +1,186 @@
+"""CPU tests (no GPU): host-side logic of the facade, the C-ABI surface, and the N>1 host path."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    """libkge_b200.so loads on a CPU-only box and exports every function include/kge_b200.h declares."""
+    from ampligraph_b200 import _lib
+    if not os.path.exists(_lib.SO_PATH):
+        _lib.build()
+    lib = _lib.load()
+    header = open(_lib.HEADER).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(kge_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), "missing export: " + name
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert lib.kge_abi_version() == 1
+
+
+def test_library_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ctypes as C
+    from ampligraph_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0)
+    h = C.c_void_p()
+    rc = lib.kge_create(C.byref(cfg), C.byref(h))
+    assert rc == _lib.KGE_ERR_CUDA and b"no CPU path" in lib.kge_last_error()
+    from ampligraph_b200.engine import KGEEngine
+    with pytest.raises(RuntimeError):
+        KGEEngine("TransE", 4, 1, 10, 2)
+
+
+def test_config_struct_matches_header():
+    import ctypes as C
+    from ampligraph_b200 import _lib
+    assert C.sizeof(_lib.KgeConfig) == 56 and C.sizeof(_lib.KgeOptimizerConfig) == 40
+    bad = _lib.KgeConfig(12, 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0)
+    h = C.c_void_p()
+    assert _lib.load().kge_create(C.byref(bad), C.byref(h)) == _lib.KGE_ERR_INVALID_ARGUMENT  # ABI guard first
+
+
+def test_registries_and_error_convention():
+    from ampligraph_b200.latent_features import LOSS_REGISTRY, SCORING_LAYER_REGISTRY, loss_functions, optimizers, regularizers
+    assert set(SCORING_LAYER_REGISTRY) == {"TransE", "DistMult", "ComplEx", "HolE", "RotatE"}
+    assert set(LOSS_REGISTRY) == {"pairwise", "nll", "absolute_margin", "self_adversarial", "multiclass_nll"}
+    assert SCORING_LAYER_REGISTRY["ComplEx"](3).internal_k == 6 and SCORING_LAYER_REGISTRY["TransE"](7).internal_k == 7
+    assert loss_functions.get("self_adversarial")._loss_parameters == {"reduction": "sum", "margin": 3, "alpha": 0.5}
+    assert loss_functions.get("pairwise", {"margin": 2})._loss_parameters["margin"] == 2
+    with pytest.raises(ValueError):
+        loss_functions.get("nope")
+    with pytest.raises(AssertionError):
+        loss_functions.get("nll", {"reduction": "max"})
+    assert isinstance(loss_functions.get(lambda p, n: p), loss_functions.LossFunctionWrapper)
+    assert optimizers.get("adam").hyperparams["learning_rate"] == 0.001
+    with pytest.raises(ValueError):
+        optimizers.get("lion")
+    assert regularizers.get("l3", {"lambda": 1e-3}).kernel_params() == {"p": 3, "lambda": 1e-3}
+    assert regularizers.get("LP").kernel_params() == {"p": 2, "lambda": 1e-5}
+    from ampligraph_b200.latent_features import ScoringBasedEmbeddingModel
+    m = ScoringBasedEmbeddingModel(eta=2, k=4, scoring_type="RotatE")
+    with pytest.raises(AssertionError):  # ScoringBasedEmbeddingModel.py:1312-1315
+        m.compile(loss="nll", entity_relation_initializer=[np.zeros((3, 8)), np.zeros((2, 8))])
+    with pytest.raises(RuntimeError):
+        ScoringBasedEmbeddingModel(eta=2, k=4).fit(np.zeros((1, 3)))  # not compiled
+
+
+def test_data_indexer_first_seen_order():
+    """data_indexer.py:385-397: ids in first-seen order scanning s, o per row; p separately."""
+    from ampligraph_b200.datasets import DataIndexer
+    X = np.array([["b", "r2", "a"], ["c", "r1", "b"], ["a", "r2", "d"]])
+    ix = DataIndexer(X)
+    assert list(ix.ent_labels) == ["b", "a", "c", "d"] and list(ix.rel_labels) == ["r2", "r1"]
+    t = ix.get_indexes(X)
+    assert t.dtype == np.int32 and t.tolist() == [[0, 0, 1], [2, 1, 0], [1, 0, 3]]
+    assert (ix.get_indexes(t, "t", "ind2raw") == X).all()
+    # unknown labels are dropped (data_indexer.py:525-542)
+    assert ix.get_indexes(np.array([["a", "r1", "zzz"], ["a", "r1", "b"]])).tolist() == [[1, 1, 0]]
+    assert ix.get_indexes(np.array(["d", "q", "a"]), "e").tolist() == [3, 1]
+    # integer inputs are labels too (Appendix A.11)
+    ix2 = DataIndexer(np.array([[7, 0, 5], [5, 1, 9]]))
+    assert ix2.get_indexes(np.array([[9, 1, 7]])).tolist() == [[2, 1, 0]]
+
+
+def test_filter_index_matches_bruteforce():
+    """graph_data_loader.py:287-350/:382-439: known-true subjects for (?,p,o), objects for (s,p,?)."""
+    from ampligraph_b200.datasets import FilterIndex
+    rng = np.random.default_rng(0)
+    E, R = 30, 4
+    data = np.stack([rng.integers(0, E, 400), rng.integers(0, R, 400), rng.integers(0, E, 400)], 1)
+    test = data[rng.choice(400, 25)]
+    test[0] = [E - 1, R - 1, E - 1]
+    fi = FilterIndex(data, E)
+    for side, (a, b, c) in (("s", (1, 2, 0)), ("o", (0, 1, 2))):
+        off, ids = fi.lookup(test, side)
+        assert off[0] == 0 and off[-1] == len(ids)
+        for i, t in enumerate(test):
+            want = sorted(set(data[(data[:, a] == t[a]) & (data[:, b] == t[b])][:, c].tolist()))
+            assert ids[off[i]:off[i + 1]].tolist() == want
+    # entities_subset: ids are remapped to subset positions, others dropped (AbstractScoringLayer.py:266-275)
+    subset = np.array([3, 7, 8, 20, 29])
+    pos = np.full(E, -1, np.int64)
+    pos[subset] = np.arange(len(subset))
+    off, ids = fi.lookup(test, "o", pos)
+    for i, t in enumerate(test):
+        objs = set(data[(data[:, 0] == t[0]) & (data[:, 1] == t[1])][:, 2].tolist())
+        assert sorted(ids[off[i]:off[i + 1]].tolist()) == sorted(pos[o] for o in objs if pos[o] >= 0)
+
+
+def test_metrics():
+    from ampligraph_b200.evaluation import hits_at_n_score, mr_score, mrr_score
+    r = np.array([[1, 2], [4, 10]])
+    assert mr_score(r) == 4.25 and abs(mrr_score(r) - (1 + .5 + .25 + .1) / 4) < 1e-12
+    assert hits_at_n_score(r, 3) == 0.5
+
+
+def test_row_shards_cover_table():
+    from ampligraph_b200.parallel import batch_slot, row_shard
+    for n, w in ((14505, 8), (10, 4), (3, 8)):
+        parts = [row_shard(n, w, r) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(parts[:-1], parts[1:]))
+    assert [batch_slot(1, 4, r, 10) for r in range(4)] == [4, 5, 6, 7]
+
+
+_GLOO_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import c_oracle, ref_step
+from ampligraph_b200.parallel import allreduce_sum_, batch_slot, row_shard
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(0)
+E, R, k, eta, B = 40, 3, 6, 3, 16
+K = 2 * k
+ent = rng.uniform(-.5, .5, (E, K)).astype(np.float32); rel = rng.uniform(-.5, .5, (R, K)).astype(np.float32)
+data = np.stack([rng.integers(0, E, 4 * B), rng.integers(0, R, 4 * B), rng.integers(0, E, 4 * B)], 1).astype(np.int32)
+keep = rng.integers(0, 2, (4, B * eta)).astype(np.uint8); repl = rng.integers(0, E, (4, B * eta)).astype(np.int32)
+# data-parallel step: each rank differentiates ITS batch (oracle stands in for the kernel), gradients are summed
+rs = ref_step.RefStep("ComplEx", K, ent, rel, eta, loss="self_adversarial")
+j = batch_slot(0, world, rank, 4)
+_, _, _, g_ent, g_rel = rs.loss_and_grads(data[j*B:(j+1)*B], c_oracle.corrupt(data[j*B:(j+1)*B], eta, keep[j], repl[j]))
+g_ent, g_rel = g_ent.clone(), g_rel.clone()
+allreduce_sum_([g_ent, g_rel])
+# single-process gradient of the GLOBAL batch (both ranks' batches together)
+full = ref_step.RefStep("ComplEx", K, ent, rel, eta, loss="self_adversarial")
+tot_e, tot_r = torch.zeros_like(g_ent), torch.zeros_like(g_rel)
+for r in range(world):
+    jj = batch_slot(0, world, r, 4)
+    _, _, _, a, b = full.loss_and_grads(data[jj*B:(jj+1)*B], c_oracle.corrupt(data[jj*B:(jj+1)*B], eta, keep[jj], repl[jj]))
+    tot_e += a; tot_r += b
+assert torch.allclose(g_ent, tot_e, rtol=1e-5, atol=1e-6) and torch.allclose(g_rel, tot_r, rtol=1e-5, atol=1e-6)
+# sharded ranking: per-shard counts summed == full ranking
+q = data[:8]
+lo, hi = row_shard(E, world, rank)
+cnt = torch.as_tensor(c_oracle.rank_triples("ComplEx", "s", "worst", ent, rel, q, start_id=lo, n_cand=hi - lo).astype(np.int32))
+allreduce_sum_([cnt])
+assert (cnt.numpy() == c_oracle.rank_triples("ComplEx", "s", "worst", ent, rel, q)).all()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_data_parallel_host_path_gloo_world2(tmp_path):
+    """world_size-2 gloo run of the N>1 host logic: gradient all-reduce == global-batch gradient,
+    row-sharded rank counts sum to the full ranking."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29613", str(script), ROOT]
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert out.stdout.count("ok") >= 2
