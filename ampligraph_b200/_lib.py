@@ -21,12 +21,14 @@ OPTIMIZERS = {"sgd": 0, "adam": 1, "adagrad": 2}
 SIDES = {"s": 0, "o": 1}
 STRATEGIES = {"worst": 0, "best": 1, "middle": 2}
 STEP_FUSED, STEP_FORWARD_ONLY, STEP_BACKWARD_EXT = 0, 1, 2
+SCATTER = {"bulk": 0, "red_v4": 1}
 
 
 class KgeConfig(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("scoring", C.c_int32), ("k", C.c_int32), ("eta", C.c_int32),
                 ("n_ent", C.c_int64), ("n_rel", C.c_int64), ("loss", C.c_int32), ("reduction", C.c_int32),
-                ("margin", C.c_float), ("alpha", C.c_float), ("device", C.c_int32), ("neg_group", C.c_int32)]
+                ("margin", C.c_float), ("alpha", C.c_float), ("device", C.c_int32), ("neg_group", C.c_int32),
+                ("scatter_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class KgeOptimizerConfig(C.Structure):

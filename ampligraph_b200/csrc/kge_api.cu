@@ -60,6 +60,8 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
         return fail(KGE_ERR_INVALID_ARGUMENT, "Could not interpret loss identifier: %d", cfg->loss);
     if (cfg->reduction != KGE_REDUCE_SUM && cfg->reduction != KGE_REDUCE_MEAN)
         return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for reduction!");
+    if (cfg->scatter_mode != KGE_SCATTER_BULK && cfg->scatter_mode != KGE_SCATTER_RED_V4)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: unknown scatter_mode %d", cfg->scatter_mode);
     if (cfg->k < 1 || cfg->eta < 1 || cfg->n_ent < 1 || cfg->n_rel < 1)
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: k, eta, n_ent, n_rel must be >= 1");
     if (cfg->n_ent > 0x7fffffffLL || cfg->n_rel > 0x7fffffffLL)
@@ -252,6 +254,7 @@ extern "C" int kge_train_step(kge_handle *h, int32_t mode, const float *ent_dev,
     p.loss = h->cfg.loss;
     p.reduction = h->cfg.reduction;
     p.mode = mode;
+    p.scatter_mode = h->cfg.scatter_mode;
     p.margin = h->cfg.margin;
     p.alpha = h->cfg.alpha;
     p.score_scale = h->score_scale;

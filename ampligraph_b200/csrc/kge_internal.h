@@ -25,6 +25,7 @@ struct TrainParams {
     int eta_pad;                  // round_up(eta,4)
     int rows_bytes, region_bytes; // per-warp shared-memory carve-up
     int loss, reduction, mode;
+    int scatter_mode;             // enum kge_scatter
     float margin, alpha, score_scale, inv_div;
     double *loss_out;
     float *scores_pos, *scores_neg;

@@ -15,7 +15,8 @@
 // computed from shared memory; gradient rows are written IN PLACE over the
 // gathered rows and pushed to the gradient tables by the copy engine again
 // (cp.reduce.async.bulk ... .add.f32 -- an element-wise fp32 atomic add of a
-// whole row).  The reference re-gathers s,p,o for every corruption
+// whole row; scatter mode KGE_SCATTER_BULK) or, alternatively, emitted straight from
+// registers with red.global.add.v4.f32 (KGE_SCATTER_RED_V4).  The reference re-gathers s,p,o for every corruption
 // (3(1+eta) rows per positive); here each needed row moves once: (3+eta) rows
 // in, (3+eta) gradient rows out = 2(3+eta)*ld*4 bytes per positive.
 #include <math.h>
@@ -49,15 +50,43 @@ __device__ __forceinline__ float4 f4sgn(float4 a) { return make_float4(sgnf(a.x)
 __device__ __forceinline__ float f4abssum(float4 a) { return (fabsf(a.x) + fabsf(a.y)) + (fabsf(a.z) + fabsf(a.w)); }
 
 // --------------------------------------------------------------------------
-// Per-model scorers.  Each lane owns float4 chunks c = lane + 32*it (it < NIT)
-// of every (padded) half-row; pad columns are zero in HBM and produce zero
-// scores / gradients.  Methods (all warp-synchronous, no cross-lane traffic):
-//   prep(s,p,o)          load per-positive state; returns this lane's partial of f(s,p,o)
-//   neg_partial(r,side)  partial of f for a corruption whose replaced row is r
-//                        side 0 = subject replaced (keep_subj = 0), 1 = object replaced
-//   neg_grad(r,side,g)   overwrite r with g * df/dr and accumulate what the kept
-//                        rows will need
-//   finish(s,p,o,gP)     overwrite s,p,o with their total gradient rows
+// gradient sinks: where a computed gradient float4 goes.
+//   SinkSmem  overwrite the gathered row in shared memory (pushed later, whole row at a
+//             time, by cp.reduce.async.bulk -- the copy engine does the atomics)
+//   SinkRed   red.global.add.v4.f32 straight from registers into the gradient table
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float *g, float4 v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+struct SinkSmem {
+    static constexpr bool kDirect = false;
+    static __device__ __forceinline__ void put(float *slot, float *, int off, float4 v) { f4st(slot + off, v); }
+};
+struct SinkRed {
+    static constexpr bool kDirect = true;
+    static __device__ __forceinline__ void put(float *, float *grow, int off, float4 v) { red_add_v4(grow + off, v); }
+};
+
+__device__ __forceinline__ float4 f4neg(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
+__device__ __forceinline__ float f4mod_sum(float4 re, float4 im)
+{
+    return (sqrtf(fmaf(im.x, im.x, re.x * re.x)) + sqrtf(fmaf(im.y, im.y, re.y * re.y))) +
+           (sqrtf(fmaf(im.z, im.z, re.z * re.z)) + sqrtf(fmaf(im.w, im.w, re.w * re.w)));
+}
+
+// --------------------------------------------------------------------------
+// Per-model scorers.  Each lane owns float4 chunks c = lane + 32*it (it < NIT) of every
+// (padded) half-row; pad columns are zero in HBM and produce zero scores / gradients.
+// All methods are warp-synchronous with no cross-lane traffic.  SIDE is a template
+// argument (0 = subject replaced, 1 = object replaced): the caller partitions a
+// positive's corruptions by side so the inner loops are branch-free, and feeds them in
+// PAIRS (a, b) so two independent dependency chains are in flight.
+//   prep(s,p,o)                      per-positive state; returns this lane's partial of f(s,p,o)
+//   partial2<SIDE>(ra,rb,pa,pb)      partials of f for two corruptions with replaced rows ra, rb
+//   grad2<SIDE,Sink>(...)            emit g * df/dr for both rows, accumulate what the kept rows need
+//   finish<Sink>(...)                emit the total gradient rows of s, p, o
 // Unscaled f; HolE's 2/k factor is folded into g by the caller.
 // --------------------------------------------------------------------------
 template <int MODEL, int NIT>
@@ -68,10 +97,10 @@ template <int NIT>
 struct Scorer<KGE_DISTMULT, NIT> {
     float4 A[NIT], C[NIT], Ws[NIT], Wo[NIT];
     int lane, nch;
-    __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, const TrainParams &, int ln)
+    __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
-        float acc = 0.f;
+        float4 acc = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
@@ -81,33 +110,47 @@ struct Scorer<KGE_DISTMULT, NIT> {
             C[it] = vs * vp;
             Ws[it] = f4zero();
             Wo[it] = f4zero();
-            acc += f4dot(vs, A[it]);
+            acc = f4fma(vs, A[it], acc);
         }
-        return acc;
+        return f4hsum(acc);
     }
-    __device__ __forceinline__ float neg_partial(const float *r, int side) const
+    template <int SIDE>
+    __device__ __forceinline__ void partial2(const float *ra, const float *rb, float &pa, float &pb) const
     {
-        float acc = 0.f;
+        float4 a = f4zero(), b = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
-            if (c < nch) acc += f4dot(f4ld(r + 4 * c), side ? C[it] : A[it]);
+            if (c < nch) {
+                const float4 q = SIDE ? C[it] : A[it];
+                a = f4fma(f4ld(ra + 4 * c), q, a);
+                b = f4fma(f4ld(rb + 4 * c), q, b);
+            }
         }
-        return acc;
+        pa = f4hsum(a);
+        pb = f4hsum(b);
     }
-    __device__ __forceinline__ void neg_grad(float *r, int side, float g)
+    template <int SIDE, class Sink>
+    __device__ __forceinline__ void grad2(float *ra, float *rb, float *ga_row, float *gb_row, float ga, float gb,
+                                          bool has_b)
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 v = f4ld(r + 4 * c);
-                if (side) { Wo[it] = f4fma(g, v, Wo[it]); f4st(r + 4 * c, g * C[it]); }
-                else { Ws[it] = f4fma(g, v, Ws[it]); f4st(r + 4 * c, g * A[it]); }
+                float4 va = f4ld(ra + 4 * c), vb = f4ld(rb + 4 * c);
+                const float4 q = SIDE ? C[it] : A[it];
+                float4 &W = SIDE ? Wo[it] : Ws[it];
+                W = f4fma(ga, va, W);
+                W = f4fma(gb, vb, W);
+                Sink::put(ra, ga_row, 4 * c, ga * q);
+                if (has_b) Sink::put(rb, gb_row, 4 * c, gb * q);
             }
         }
     }
-    __device__ __forceinline__ void finish(float *s, float *p, float *o, float gP)
+    template <class Sink>
+    __device__ __forceinline__ void finish(float *s, float *p, float *o, float *gs, float *gp, float *go, float gP,
+                                           float)
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
@@ -116,9 +159,9 @@ struct Scorer<KGE_DISTMULT, NIT> {
                 float4 vs = f4ld(s + 4 * c), vp = f4ld(p + 4 * c), vo = f4ld(o + 4 * c);
                 float4 U = f4fma(gP, vs, Ws[it]);  // everything that sat in the subject slot
                 float4 X = f4fma(gP, vo, Wo[it]);  // everything that sat in the object slot
-                f4st(s + 4 * c, vp * X);
-                f4st(o + 4 * c, U * vp);
-                f4st(p + 4 * c, f4fma(U, vo, vs * Wo[it]));
+                Sink::put(s, gs, 4 * c, vp * X);
+                Sink::put(o, go, 4 * c, U * vp);
+                Sink::put(p, gp, 4 * c, f4fma(U, vo, vs * Wo[it]));
             }
         }
     }
@@ -132,10 +175,10 @@ struct ComplexScorer {
     float4 A[NIT], Bv[NIT], C[NIT], D[NIT];          // subject-side / object-side query vectors
     float4 Wsr[NIT], Wsi[NIT], Wor[NIT], Woi[NIT];   // sum_j g_j r_j per side (re, im)
     int lane, nch, kp;
-    __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, const TrainParams &, int ln)
+    __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
-        float acc = 0.f;
+        float4 acc = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
@@ -150,41 +193,56 @@ struct ComplexScorer {
             C[it] = sr * pr - si * pi;
             D[it] = f4fma(sr, pi, si * pr);
             Wsr[it] = Wsi[it] = Wor[it] = Woi[it] = f4zero();
-            acc += f4dot(sr, A[it]) + f4dot(si, Bv[it]);
+            acc = f4fma(sr, A[it], acc);
+            acc = f4fma(si, Bv[it], acc);
         }
-        return acc;
+        return f4hsum(acc);
     }
-    __device__ __forceinline__ float neg_partial(const float *r, int side) const
+    template <int SIDE>
+    __device__ __forceinline__ void partial2(const float *ra, const float *rb, float &pa, float &pb) const
     {
-        float acc = 0.f;
+        float4 a = f4zero(), b = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 rr = f4ld(r + 4 * c), ri = f4ld(r + kp + 4 * c);
-                acc += side ? (f4dot(rr, C[it]) + f4dot(ri, D[it])) : (f4dot(rr, A[it]) + f4dot(ri, Bv[it]));
+                const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
+                a = f4fma(f4ld(ra + 4 * c), qr, a);
+                b = f4fma(f4ld(rb + 4 * c), qr, b);
+                a = f4fma(f4ld(ra + kp + 4 * c), qi, a);
+                b = f4fma(f4ld(rb + kp + 4 * c), qi, b);
             }
         }
-        return acc;
+        pa = f4hsum(a);
+        pb = f4hsum(b);
     }
-    __device__ __forceinline__ void neg_grad(float *r, int side, float g)
+    template <int SIDE, class Sink>
+    __device__ __forceinline__ void grad2(float *ra, float *rb, float *ga_row, float *gb_row, float ga, float gb,
+                                          bool has_b)
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 rr = f4ld(r + 4 * c), ri = f4ld(r + kp + 4 * c);
-                if (side) {
-                    Wor[it] = f4fma(g, rr, Wor[it]); Woi[it] = f4fma(g, ri, Woi[it]);
-                    f4st(r + 4 * c, g * C[it]); f4st(r + kp + 4 * c, g * D[it]);
-                } else {
-                    Wsr[it] = f4fma(g, rr, Wsr[it]); Wsi[it] = f4fma(g, ri, Wsi[it]);
-                    f4st(r + 4 * c, g * A[it]); f4st(r + kp + 4 * c, g * Bv[it]);
+                float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + kp + 4 * c);
+                float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + kp + 4 * c);
+                const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
+                float4 &Wr = SIDE ? Wor[it] : Wsr[it];
+                float4 &Wi = SIDE ? Woi[it] : Wsi[it];
+                Wr = f4fma(ga, ar, Wr); Wi = f4fma(ga, ai, Wi);
+                Wr = f4fma(gb, br, Wr); Wi = f4fma(gb, bi, Wi);
+                Sink::put(ra, ga_row, 4 * c, ga * qr);
+                Sink::put(ra, ga_row, kp + 4 * c, ga * qi);
+                if (has_b) {
+                    Sink::put(rb, gb_row, 4 * c, gb * qr);
+                    Sink::put(rb, gb_row, kp + 4 * c, gb * qi);
                 }
             }
         }
     }
-    __device__ __forceinline__ void finish(float *s, float *p, float *o, float gP)
+    template <class Sink>
+    __device__ __forceinline__ void finish(float *s, float *p, float *o, float *gs, float *gp, float *go, float gP,
+                                           float)
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
@@ -196,14 +254,14 @@ struct ComplexScorer {
                 float4 Ur = f4fma(gP, sr, Wsr[it]), Ui = f4fma(gP, si, Wsi[it]);    // subject-slot mass
                 float4 Xr = f4fma(gP, orr, Wor[it]), Xi = f4fma(gP, oi, Woi[it]);   // object-slot mass
                 // d/ds f(s,p,X)
-                f4st(s + 4 * c, f4fma(pi, Xi, pr * Xr));
-                f4st(s + kp + 4 * c, pr * Xi - pi * Xr);
+                Sink::put(s, gs, 4 * c, f4fma(pi, Xi, pr * Xr));
+                Sink::put(s, gs, kp + 4 * c, pr * Xi - pi * Xr);
                 // d/do f(U,p,o)
-                f4st(o + 4 * c, Ur * pr - Ui * pi);
-                f4st(o + kp + 4 * c, f4fma(Ur, pi, Ui * pr));
+                Sink::put(o, go, 4 * c, Ur * pr - Ui * pi);
+                Sink::put(o, go, kp + 4 * c, f4fma(Ur, pi, Ui * pr));
                 // d/dp [f(U,p,o) + f(s,p,Wo)]
-                f4st(p + 4 * c, f4fma(Ur, orr, Ui * oi) + f4fma(sr, Wor[it], si * Woi[it]));
-                f4st(p + kp + 4 * c, (Ur * oi - Ui * orr) + (sr * Woi[it] - si * Wor[it]));
+                Sink::put(p, gp, 4 * c, f4fma(Ur, orr, Ui * oi) + f4fma(sr, Wor[it], si * Woi[it]));
+                Sink::put(p, gp, kp + 4 * c, (Ur * oi - Ui * orr) + (sr * Woi[it] - si * Wor[it]));
             }
         }
     }
@@ -216,7 +274,7 @@ template <int NIT>
 struct Scorer<KGE_TRANSE, NIT> {
     float4 Qs[NIT], Qo[NIT], Vs[NIT], Vo[NIT];  // p-o, s+p, sum g*sign per side
     int lane, nch;
-    __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, const TrainParams &, int ln)
+    __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
         float acc = 0.f;
@@ -232,39 +290,44 @@ struct Scorer<KGE_TRANSE, NIT> {
         }
         return acc;
     }
-    __device__ __forceinline__ float neg_partial(const float *r, int side) const
+    template <int SIDE>
+    __device__ __forceinline__ void partial2(const float *ra, const float *rb, float &pa, float &pb) const
     {
-        float acc = 0.f;
+        float a = 0.f, b = 0.f;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 v = f4ld(r + 4 * c);
-                acc -= f4abssum(side ? (Qo[it] - v) : (v + Qs[it]));
+                float4 va = f4ld(ra + 4 * c), vb = f4ld(rb + 4 * c);
+                a -= f4abssum(SIDE ? (Qo[it] - va) : (va + Qs[it]));
+                b -= f4abssum(SIDE ? (Qo[it] - vb) : (vb + Qs[it]));
             }
         }
-        return acc;
+        pa = a;
+        pb = b;
     }
-    __device__ __forceinline__ void neg_grad(float *r, int side, float g)
+    template <int SIDE, class Sink>
+    __device__ __forceinline__ void grad2(float *ra, float *rb, float *ga_row, float *gb_row, float ga, float gb,
+                                          bool has_b)
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 v = f4ld(r + 4 * c);
-                if (side) {  // t = (s+p) - r ; f = -|t| ; df/dr = +sign(t)
-                    float4 gs = g * f4sgn(Qo[it] - v);
-                    Vo[it] = Vo[it] + gs;
-                    f4st(r + 4 * c, gs);
-                } else {  // t = r + (p-o) ; df/dr = -sign(t)
-                    float4 gs = g * f4sgn(v + Qs[it]);
-                    Vs[it] = Vs[it] + gs;
-                    f4st(r + 4 * c, -1.f * gs);
-                }
+                float4 va = f4ld(ra + 4 * c), vb = f4ld(rb + 4 * c);
+                // SIDE 1: t = (s+p) - r, df/dr = +sign(t);  SIDE 0: t = r + (p-o), df/dr = -sign(t)
+                float4 sa = ga * f4sgn(SIDE ? (Qo[it] - va) : (va + Qs[it]));
+                float4 sb = gb * f4sgn(SIDE ? (Qo[it] - vb) : (vb + Qs[it]));
+                float4 &V = SIDE ? Vo[it] : Vs[it];
+                V = V + sa + sb;
+                Sink::put(ra, ga_row, 4 * c, SIDE ? sa : f4neg(sa));
+                if (has_b) Sink::put(rb, gb_row, 4 * c, SIDE ? sb : f4neg(sb));
             }
         }
     }
-    __device__ __forceinline__ void finish(float *s, float *p, float *o, float gP)
+    template <class Sink>
+    __device__ __forceinline__ void finish(float *s, float *p, float *o, float *gs, float *gp, float *go, float gP,
+                                           float)
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
@@ -272,9 +335,9 @@ struct Scorer<KGE_TRANSE, NIT> {
             if (c < nch) {
                 float4 vo = f4ld(o + 4 * c);
                 float4 Vp = gP * f4sgn(Qo[it] - vo);
-                f4st(s + 4 * c, -1.f * (Vp + Vo[it]));
-                f4st(p + 4 * c, -1.f * (Vp + Vs[it] + Vo[it]));
-                f4st(o + 4 * c, Vp + Vs[it]);
+                Sink::put(s, gs, 4 * c, f4neg(Vp + Vo[it]));
+                Sink::put(p, gp, 4 * c, f4neg(Vp + Vs[it] + Vo[it]));
+                Sink::put(o, go, 4 * c, Vp + Vs[it]);
             }
         }
     }
@@ -291,17 +354,16 @@ struct Scorer<KGE_ROTATE, NIT> {
     float4 Cs[NIT], Sn[NIT], Yr[NIT], Yi[NIT], Or_[NIT], Oi[NIT];
     float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], Aphi[NIT];
     int lane, nch, kp;
-    static __device__ __forceinline__ void unit(float4 re, float4 im, float4 &a, float4 &b, float &msum)
+    static __device__ __forceinline__ void unit(float4 re, float4 im, float g, float4 &a, float4 &b)
     {
         float m0 = sqrtf(fmaf(im.x, im.x, re.x * re.x)), m1 = sqrtf(fmaf(im.y, im.y, re.y * re.y));
         float m2 = sqrtf(fmaf(im.z, im.z, re.z * re.z)), m3 = sqrtf(fmaf(im.w, im.w, re.w * re.w));
-        msum = (m0 + m1) + (m2 + m3);
-        float i0 = m0 > 0.f ? 1.f / m0 : 0.f, i1 = m1 > 0.f ? 1.f / m1 : 0.f;
-        float i2 = m2 > 0.f ? 1.f / m2 : 0.f, i3 = m3 > 0.f ? 1.f / m3 : 0.f;
+        float i0 = m0 > 0.f ? g / m0 : 0.f, i1 = m1 > 0.f ? g / m1 : 0.f;
+        float i2 = m2 > 0.f ? g / m2 : 0.f, i3 = m3 > 0.f ? g / m3 : 0.f;
         a = make_float4(re.x * i0, re.y * i1, re.z * i2, re.w * i3);
         b = make_float4(im.x * i0, im.y * i1, im.z * i2, im.w * i3);
     }
-    __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, const TrainParams &, int ln)
+    __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
         float acc = 0.f;
@@ -318,75 +380,83 @@ struct Scorer<KGE_ROTATE, NIT> {
             Yr[it] = sr * Cs[it] - si * Sn[it];
             Yi[it] = f4fma(sr, Sn[it], si * Cs[it]);
             Zor[it] = Zoi[it] = Zsr[it] = Zsi[it] = Aphi[it] = f4zero();
-            float4 re = Yr[it] - Or_[it], im = Yi[it] - Oi[it];
-            acc -= (sqrtf(fmaf(im.x, im.x, re.x * re.x)) + sqrtf(fmaf(im.y, im.y, re.y * re.y))) +
-                   (sqrtf(fmaf(im.z, im.z, re.z * re.z)) + sqrtf(fmaf(im.w, im.w, re.w * re.w)));
+            acc -= f4mod_sum(Yr[it] - Or_[it], Yi[it] - Oi[it]);
         }
         return acc;
     }
-    __device__ __forceinline__ float neg_partial(const float *r, int side) const
+    template <int SIDE>
+    __device__ __forceinline__ void partial2(const float *ra, const float *rb, float &pa, float &pb) const
     {
-        float acc = 0.f;
+        float a = 0.f, b = 0.f;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 rr = f4ld(r + 4 * c), ri = f4ld(r + kp + 4 * c), re, im;
-                if (side) { re = Yr[it] - rr; im = Yi[it] - ri; }
-                else {
-                    re = (rr * Cs[it] - ri * Sn[it]) - Or_[it];
-                    im = f4fma(rr, Sn[it], ri * Cs[it]) - Oi[it];
+                float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + kp + 4 * c);
+                float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + kp + 4 * c);
+                if (SIDE) {
+                    a -= f4mod_sum(Yr[it] - ar, Yi[it] - ai);
+                    b -= f4mod_sum(Yr[it] - br, Yi[it] - bi);
+                } else {
+                    a -= f4mod_sum((ar * Cs[it] - ai * Sn[it]) - Or_[it], f4fma(ar, Sn[it], ai * Cs[it]) - Oi[it]);
+                    b -= f4mod_sum((br * Cs[it] - bi * Sn[it]) - Or_[it], f4fma(br, Sn[it], bi * Cs[it]) - Oi[it]);
                 }
-                acc -= (sqrtf(fmaf(im.x, im.x, re.x * re.x)) + sqrtf(fmaf(im.y, im.y, re.y * re.y))) +
-                       (sqrtf(fmaf(im.z, im.z, re.z * re.z)) + sqrtf(fmaf(im.w, im.w, re.w * re.w)));
             }
         }
-        return acc;
+        pa = a;
+        pb = b;
     }
-    __device__ __forceinline__ void neg_grad(float *r, int side, float g)
+    template <int SIDE, class Sink>
+    __device__ __forceinline__ void grad1(float *r, float *grow, float g, int it, int c, bool emit)
+    {
+        float4 rr = f4ld(r + 4 * c), ri = f4ld(r + kp + 4 * c), a, b;
+        if (SIDE) {  // residual = y(s) - r ; df/dr = +(a,b)
+            unit(Yr[it] - rr, Yi[it] - ri, g, a, b);
+            Zor[it] = Zor[it] + a; Zoi[it] = Zoi[it] + b;
+            if (emit) { Sink::put(r, grow, 4 * c, a); Sink::put(r, grow, kp + 4 * c, b); }
+        } else {  // residual = R(phi) r - o ; df/dr = -R(-phi)(a,b)
+            float4 yr = rr * Cs[it] - ri * Sn[it], yi = f4fma(rr, Sn[it], ri * Cs[it]);
+            unit(yr - Or_[it], yi - Oi[it], g, a, b);
+            Zsr[it] = Zsr[it] + a; Zsi[it] = Zsi[it] + b;
+            Aphi[it] = Aphi[it] + (a * yi - b * yr);
+            if (emit) {
+                Sink::put(r, grow, 4 * c, f4neg(f4fma(a, Cs[it], b * Sn[it])));
+                Sink::put(r, grow, kp + 4 * c, a * Sn[it] - b * Cs[it]);
+            }
+        }
+    }
+    template <int SIDE, class Sink>
+    __device__ __forceinline__ void grad2(float *ra, float *rb, float *ga_row, float *gb_row, float ga, float gb,
+                                          bool has_b)
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 rr = f4ld(r + 4 * c), ri = f4ld(r + kp + 4 * c), a, b;
-                float ms;
-                if (side) {  // residual = y(s) - r ; df/dr = +(a,b)
-                    unit(Yr[it] - rr, Yi[it] - ri, a, b, ms);
-                    a = g * a; b = g * b;
-                    Zor[it] = Zor[it] + a; Zoi[it] = Zoi[it] + b;
-                    f4st(r + 4 * c, a); f4st(r + kp + 4 * c, b);
-                } else {  // residual = R(phi) r - o ; df/dr = -R(-phi)(a,b)
-                    float4 yr = rr * Cs[it] - ri * Sn[it], yi = f4fma(rr, Sn[it], ri * Cs[it]);
-                    unit(yr - Or_[it], yi - Oi[it], a, b, ms);
-                    a = g * a; b = g * b;
-                    Zsr[it] = Zsr[it] + a; Zsi[it] = Zsi[it] + b;
-                    Aphi[it] = Aphi[it] + (a * yi - b * yr);
-                    f4st(r + 4 * c, -1.f * f4fma(a, Cs[it], b * Sn[it]));
-                    f4st(r + kp + 4 * c, a * Sn[it] - b * Cs[it]);
-                }
+                grad1<SIDE, Sink>(ra, ga_row, ga, it, c, true);
+                grad1<SIDE, Sink>(rb, gb_row, gb, it, c, has_b);  // gb == 0 when !has_b: contributes nothing
             }
         }
     }
     // p row receives d/dtheta = (1/div) d/dphi in its first half, zeros in the second
     // (the second half of a RotatE relation row is allocated but unused, RotatE.py:76).
-    __device__ __forceinline__ void finish(float *s, float *p, float *o, float gP, float inv_div)
+    template <class Sink>
+    __device__ __forceinline__ void finish(float *s, float *p, float *o, float *gs, float *gp, float *go, float gP,
+                                           float inv_div)
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
                 float4 a, b;
-                float ms;
-                unit(Yr[it] - Or_[it], Yi[it] - Oi[it], a, b, ms);
-                a = gP * a; b = gP * b;
+                unit(Yr[it] - Or_[it], Yi[it] - Oi[it], gP, a, b);
                 float4 Zr = a + Zor[it], Zi = b + Zoi[it];  // everything with y = R(phi) s
-                f4st(s + 4 * c, -1.f * f4fma(Zr, Cs[it], Zi * Sn[it]));
-                f4st(s + kp + 4 * c, Zr * Sn[it] - Zi * Cs[it]);
-                f4st(o + 4 * c, a + Zsr[it]);
-                f4st(o + kp + 4 * c, b + Zsi[it]);
-                f4st(p + 4 * c, inv_div * (Aphi[it] + (Zr * Yi[it] - Zi * Yr[it])));
-                f4st(p + kp + 4 * c, f4zero());
+                Sink::put(s, gs, 4 * c, f4neg(f4fma(Zr, Cs[it], Zi * Sn[it])));
+                Sink::put(s, gs, kp + 4 * c, Zr * Sn[it] - Zi * Cs[it]);
+                Sink::put(o, go, 4 * c, a + Zsr[it]);
+                Sink::put(o, go, kp + 4 * c, b + Zsi[it]);
+                Sink::put(p, gp, 4 * c, inv_div * (Aphi[it] + (Zr * Yi[it] - Zi * Yr[it])));
+                if (!Sink::kDirect) Sink::put(p, gp, kp + 4 * c, f4zero());
             }
         }
     }
@@ -495,7 +565,39 @@ __device__ float loss_and_dscores(const TrainParams &p, float P, float *sc, int 
 // --------------------------------------------------------------------------
 // the kernel
 // --------------------------------------------------------------------------
-template <int MODEL, int NIT>
+__device__ __forceinline__ void warp_sum2(float &a, float &b)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+}
+
+// Visit the resident corruptions [0, gs) of one group, partitioned by side and two at a
+// time: f(side_tag, slot_a, slot_b, has_b).  nside[] holds keep_subj (1 = object replaced).
+template <class F0, class F1>
+__device__ __forceinline__ void for_each_pair_by_side(const int *nside, int gs, int lane, F0 f0, F1 f1)
+{
+    for (int base = 0; base < gs; base += 32) {
+        const int jl = base + lane;
+        const int sd = (jl < gs) ? nside[jl] : -1;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            unsigned m = __ballot_sync(0xffffffffu, sd == side);
+            while (m) {
+                const int a = base + __ffs(m) - 1;
+                m &= m - 1;
+                int b = a;
+                const bool has_b = m != 0;
+                if (has_b) { b = base + __ffs(m) - 1; m &= m - 1; }
+                if (side == 0) f0(a, b, has_b); else f1(a, b, has_b);
+            }
+        }
+    }
+}
+
+template <int MODEL, int NIT, class Sink>
 __global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kernel(const TrainParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -516,6 +618,7 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kern
     const uint32_t row_bytes = (uint32_t)ld * 4u;
     const int n_groups = (eta + G - 1) / G;
     float *srow = rows, *prow = rows + ld, *orow = rows + 2 * ld, *nrows = rows + 3 * ld;
+    const float scale = p.score_scale;  // HolE 2/k, else 1
     uint32_t phase = 0;
     double loss_acc = 0.0;
 
@@ -549,7 +652,7 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kern
         Scorer<MODEL, NIT> S;
         S.nch = p.nch;
         if constexpr (MODEL != KGE_TRANSE && MODEL != KGE_DISTMULT) S.kp = p.kp;
-        const float P = warp_sum(S.prep(srow, prow, orow, p, lane));
+        const float P = warp_sum(S.prep(srow, prow, orow, lane));
 
         // ---- pass A: scores of all corruptions (A4) ----
         for (int g = 0; g < n_groups; ++g) {
@@ -563,15 +666,24 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kern
                 mbar_wait(bar, phase);
                 phase ^= 1u;
             }
-            for (int jj = 0; jj < gs; ++jj) {
-                float v = warp_sum(S.neg_partial(nrows + (size_t)jj * ld, nside[j0 + jj]));
-                if (lane == 0) sc[j0 + jj] = v;
-            }
+            for_each_pair_by_side(
+                nside + j0, gs, lane,
+                [&](int a, int b, bool has_b) {
+                    float pa, pb;
+                    S.template partial2<0>(nrows + (size_t)a * ld, nrows + (size_t)b * ld, pa, pb);
+                    warp_sum2(pa, pb);
+                    if (lane == 0) { sc[j0 + a] = pa; if (has_b) sc[j0 + b] = pb; }
+                },
+                [&](int a, int b, bool has_b) {
+                    float pa, pb;
+                    S.template partial2<1>(nrows + (size_t)a * ld, nrows + (size_t)b * ld, pa, pb);
+                    warp_sum2(pa, pb);
+                    if (lane == 0) { sc[j0 + a] = pa; if (has_b) sc[j0 + b] = pb; }
+                });
         }
         __syncwarp();
 
         // ---- loss and dL/dscore (A5) ----
-        const float scale = p.score_scale;  // HolE 2/k, else 1
         float dP;
         if (p.mode != KGE_STEP_BACKWARD_EXT) {
             if (scale != 1.f)
@@ -593,7 +705,7 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kern
         for (int g = n_groups - 1; g >= 0; --g) {
             const int j0 = g * G, gs = min(G, eta - j0);
             if (g != n_groups - 1) {
-                bulk_wait_read_all();  // the copy engine must be done reading the previous group's rows
+                if (!Sink::kDirect) bulk_wait_read_all();  // copy engine done reading the previous group's rows
                 __syncwarp();
                 if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)gs * row_bytes);
                 __syncwarp();
@@ -602,25 +714,41 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kern
                 mbar_wait(bar, phase);
                 phase ^= 1u;
             }
-            for (int jj = 0; jj < gs; ++jj) S.neg_grad(nrows + (size_t)jj * ld, nside[j0 + jj], scale * sc[j0 + jj]);
+            for_each_pair_by_side(
+                nside + j0, gs, lane,
+                [&](int a, int b, bool has_b) {
+                    S.template grad2<0, Sink>(nrows + (size_t)a * ld, nrows + (size_t)b * ld,
+                                              p.grad_ent + (size_t)nid[j0 + a] * ld, p.grad_ent + (size_t)nid[j0 + b] * ld,
+                                              scale * sc[j0 + a], has_b ? scale * sc[j0 + b] : 0.f, has_b);
+                },
+                [&](int a, int b, bool has_b) {
+                    S.template grad2<1, Sink>(nrows + (size_t)a * ld, nrows + (size_t)b * ld,
+                                              p.grad_ent + (size_t)nid[j0 + a] * ld, p.grad_ent + (size_t)nid[j0 + b] * ld,
+                                              scale * sc[j0 + a], has_b ? scale * sc[j0 + b] : 0.f, has_b);
+                });
+            if (!Sink::kDirect) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                for (int r = lane; r < gs; r += 32)
+                    bulk_reduce_add_f32(p.grad_ent + (size_t)nid[j0 + r] * ld, nrows + (size_t)r * ld, row_bytes);
+                bulk_commit();
+            }
+        }
+        float *gs_row = p.grad_ent + (size_t)s_id * ld, *gp_row = p.grad_rel + (size_t)p_id * ld,
+              *go_row = p.grad_ent + (size_t)o_id * ld;
+        S.template finish<Sink>(srow, prow, orow, gs_row, gp_row, go_row, scale * dP, p.inv_div);
+        if (!Sink::kDirect) {
             fence_proxy_async_smem();
             __syncwarp();
-            for (int r = lane; r < gs; r += 32)
-                bulk_reduce_add_f32(p.grad_ent + (size_t)nid[j0 + r] * ld, nrows + (size_t)r * ld, row_bytes);
+            if (lane == 0) bulk_reduce_add_f32(gs_row, srow, row_bytes);
+            if (lane == 1) bulk_reduce_add_f32(gp_row, prow, row_bytes);
+            if (lane == 2) bulk_reduce_add_f32(go_row, orow, row_bytes);
             bulk_commit();
+            bulk_wait_read_all();  // slot is reused by the next positive's gather
         }
-        if constexpr (MODEL == KGE_ROTATE) S.finish(srow, prow, orow, scale * dP, p.inv_div);
-        else S.finish(srow, prow, orow, scale * dP);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) bulk_reduce_add_f32(p.grad_ent + (size_t)s_id * ld, srow, row_bytes);
-        if (lane == 1) bulk_reduce_add_f32(p.grad_rel + (size_t)p_id * ld, prow, row_bytes);
-        if (lane == 2) bulk_reduce_add_f32(p.grad_ent + (size_t)o_id * ld, orow, row_bytes);
-        bulk_commit();
-        bulk_wait_read_all();  // slot is reused by the next positive's gather
         __syncwarp();
     }
-    bulk_wait_all();
+    if (!Sink::kDirect) bulk_wait_all();
     if (p.loss_out && p.mode == KGE_STEP_FUSED && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_out, loss_acc);
 }
 
@@ -667,7 +795,8 @@ static cudaError_t launch_train_model(const TrainParams &p, int nit, int sm_coun
 {
 #define KGE_LAUNCH(N)                                                                                       \
     {                                                                                                       \
-        auto kern = kge_train_kernel<MODEL, N>;                                                             \
+        auto kern = p.scatter_mode == KGE_SCATTER_RED_V4 ? kge_train_kernel<MODEL, N, SinkRed>              \
+                                                         : kge_train_kernel<MODEL, N, SinkSmem>;            \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                                     \
         int occ = 0;                                                                                        \

@@ -8,6 +8,7 @@ fit / predict / evaluate loops, mirroring train_function / predict_function /
 test_function of the reference (models/ScoringBasedEmbeddingModel.py:443, :1719, :1387).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -21,7 +22,8 @@ def _ptr(t):
 
 class KGEEngine:
     def __init__(self, scoring_type, k, eta, n_ent, n_rel, loss="pairwise", loss_params=None,
-                 optimizer="adam", optimizer_params=None, regularizer=None, device=0, neg_group=0):
+                 optimizer="adam", optimizer_params=None, regularizer=None, device=0, neg_group=0,
+                 scatter=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("ampligraph_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -40,7 +42,7 @@ class KGEEngine:
         cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), _lib.SCORING[scoring_type], int(k), int(eta), int(n_ent),
                              int(n_rel), _lib.LOSSES[loss], _lib.REDUCTIONS[reduction],
                              float(lp.get("margin", default_margin)), float(lp.get("alpha", 0.5)), int(device),
-                             int(neg_group))
+                             int(neg_group), _lib.SCATTER[scatter or os.environ.get("KGE_B200_SCATTER", "bulk")], 0)
         h = C.c_void_p()
         _lib.check(self.lib.kge_create(C.byref(cfg), C.byref(h)))
         self.h = h

@@ -64,6 +64,10 @@ enum kge_reduction { KGE_REDUCE_SUM = 0, KGE_REDUCE_MEAN = 1 }; /* loss_function
 enum kge_optimizer { KGE_OPT_SGD = 0, KGE_OPT_ADAM = 1, KGE_OPT_ADAGRAD = 2 };
 enum kge_side { KGE_SIDE_S = 0, KGE_SIDE_O = 1 };
 enum kge_rank_strategy { KGE_RANK_WORST = 0, KGE_RANK_BEST = 1, KGE_RANK_MIDDLE = 2 };
+enum kge_scatter {
+    KGE_SCATTER_BULK = 0,   /* rows staged in shared memory, cp.reduce.async.bulk .add.f32 (copy engine) */
+    KGE_SCATTER_RED_V4 = 1  /* red.global.add.v4.f32 straight from registers */
+};
 enum kge_step_mode {
     KGE_STEP_FUSED = 0,         /* scores -> built-in loss -> gradients, one kernel */
     KGE_STEP_FORWARD_ONLY = 1,  /* scores only (user-callable loss / FocusE, phase 1) */
@@ -85,6 +89,8 @@ typedef struct kge_config {
     float alpha;          /* self_adversarial temperature */
     int32_t device;       /* CUDA device ordinal */
     int32_t neg_group;    /* 0 = auto; >0 forces that many negatives resident per pass (testing) */
+    int32_t scatter_mode; /* enum kge_scatter: how gradient rows reach the gradient tables */
+    int32_t reserved;     /* must be 0 */
 } kge_config;
 
 /* optimizers.get (optimizers.py:255-291) -> tf.keras.optimizers.legacy.{SGD,Adam,Adagrad};

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmark (development aid): times kge_train_step alone for the BASELINE
+config shapes under different scatter modes / residency groups.  CUDA events, L2 flushed
+between iterations.  Usage: python scripts/kbench.py [cfg2 cfg3 cfg4 ...]"""
+import os
+import sys
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ampligraph_b200.engine import KGEEngine  # noqa: E402
+
+CFGS = {
+    "cfg1": dict(model="TransE", k=50, eta=2, E=1000, R=10, B=1000, loss="pairwise"),
+    "cfg2": dict(model="ComplEx", k=200, eta=10, E=14505, R=237, B=27212, loss="self_adversarial"),
+    "cfg2u": dict(model="ComplEx", k=200, eta=10, E=14505, R=237, B=27212, loss="self_adversarial", uniform=True),
+    "cfg3": dict(model="DistMult", k=400, eta=20, E=40943, R=11, B=8684, loss="pairwise"),
+    "cfg4": dict(model="RotatE", k=200, eta=30, E=123182, R=37, B=10791, loss="self_adversarial"),
+    "big": dict(model="ComplEx", k=200, eta=10, E=2000000, R=1000, B=65536, loss="self_adversarial", uniform=True),
+}
+
+
+def triples(c, rng):
+    E, R, B = c["E"], c["R"], c["B"]
+    if c.get("uniform"):
+        s, o = rng.integers(0, E, B), rng.integers(0, E, B)
+    else:
+        w = 1.0 / np.arange(1, E + 1)
+        cdf = np.cumsum(w / w.sum())
+        perm = rng.permutation(E)
+        s, o = perm[np.searchsorted(cdf, rng.random(B))], perm[np.searchsorted(cdf, rng.random(B))]
+    return np.stack([s, rng.integers(0, R, B), o], 1).astype(np.int32)
+
+
+def run(name, scatter, neg_group=0, iters=20):
+    c = CFGS[name]
+    rng = np.random.default_rng(0)
+    eng = KGEEngine(c["model"], c["k"], c["eta"], c["E"], c["R"], loss=c["loss"], scatter=scatter, neg_group=neg_group)
+    eng.init_glorot_uniform(1)
+    t = torch.as_tensor(triples(c, rng)).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for i in range(3):
+        eng.forward_backward(t, None, seed=1, step=i)
+    torch.cuda.synchronize()
+    ms = []
+    for i in range(iters):
+        flush.fill_(i & 255)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.forward_backward(t, None, seed=1, step=10 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms = np.array(ms)
+    row_bytes = eng.ld * 4
+    alg = 2 * (3 + c["eta"]) * row_bytes * c["B"]
+    g = eng.g_ent.double().abs().sum().item()
+    print("%-6s %-7s G=%-2d  med %8.1f us  min %8.1f us  %7.1f GB/s alg  %6.2f Mpos/s  %8.1f Mtriples/s  |g|=%.6e"
+          % (name, scatter, neg_group, np.median(ms) * 1e3, ms.min() * 1e3, alg / np.median(ms) / 1e6,
+             c["B"] / np.median(ms) / 1e3, c["B"] * (1 + c["eta"]) / np.median(ms) / 1e3, g), flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or ["cfg2", "cfg2u", "cfg3", "cfg4", "cfg1", "big"]
+    for n in names:
+        for scatter in ("bulk", "red_v4"):
+            run(n, scatter)
+        if n in ("cfg2", "cfg4"):
+            run(n, "red_v4", neg_group=5)
+            run(n, "bulk", neg_group=5)

@@ -1,0 +1,129 @@
+"""GPU tests of the reference-facing facade (ScoringBasedEmbeddingModel) against the oracle:
+BASELINE.json configs[0] (TransE k=50 eta=2, 1k entities / 10 relations) end to end."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _kg(E, R, n, seed=1, labels=True):
+    rng = np.random.default_rng(seed)
+    t = np.unique(np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1), axis=0)
+    rng.shuffle(t)
+    if not labels:
+        return t
+    return np.stack([np.char.add("e", t[:, 0].astype(str)), np.char.add("r", t[:, 1].astype(str)),
+                     np.char.add("e", t[:, 2].astype(str))], 1)
+
+
+def _fit_pair(model_name, k, eta, loss, X, batch_size, epochs, optimizer="adam", loss_params=None, opt_params=None):
+    """fit the facade and replay the same batches/corruptions through the CPU restatement."""
+    from ampligraph_b200.latent_features import ScoringBasedEmbeddingModel, loss_functions
+    from oracle import ref_step
+    from ampligraph_b200.datasets import DataIndexer
+    ix = DataIndexer(X)
+    E, R = ix.get_entities_count(), ix.get_relations_count()
+    K = k if model_name in ("TransE", "DistMult") else 2 * k
+    rng = np.random.default_rng(0)
+    ent0 = rng.uniform(-0.3, 0.3, (E, K)).astype(np.float32)
+    rel0 = rng.uniform(-0.3, 0.3, (R, K)).astype(np.float32)
+    inits = [ent0, rel0] if model_name != "RotatE" else [ent0, "glorot_uniform"]
+    m = ScoringBasedEmbeddingModel(eta=eta, k=k, scoring_type=model_name, seed=7)
+    from ampligraph_b200.latent_features import optimizers
+    m.compile(optimizer=optimizers.get(optimizer, dict(opt_params or {})), loss=loss_functions.get(loss, loss_params or {}),
+              entity_relation_initializer=inits)
+    hist = m.fit(X, batch_size=batch_size, epochs=epochs, verbose=False)
+    # replay
+    t = ix.get_indexes(X)
+    if model_name == "RotatE":  # relations came from the engine's Glorot stream; rebuild the same start
+        from ampligraph_b200.engine import KGEEngine
+        e2 = KGEEngine(model_name, k, eta, E, R)
+        e2.init_glorot_uniform(7)
+        rel0 = e2.get_embeddings()[1].cpu().numpy()
+        e2.close()
+    rs = ref_step.RefStep(model_name, K, ent0, rel0, eta, loss=loss, loss_params=loss_params or {}, optimizer=optimizer,
+                          optimizer_params=dict(opt_params or {}))
+    step, losses = 0, []
+    for _ in range(epochs):
+        for s in range(0, len(t), batch_size):
+            b = np.ascontiguousarray(t[s:s + batch_size])
+            corr = m.engine.generate_corruptions(torch.as_tensor(b).cuda(), seed=7, step=step).cpu().numpy()
+            losses.append(rs.train_step(b, corr))
+            step += 1
+    return m, rs, hist, losses, ix
+
+
+def test_cfg1_transe_fit_predict_evaluate():
+    """configs[0]: TransE k=50 eta=2 on a 1k-entity / 10-relation synthetic KG."""
+    from oracle import c_oracle
+    X = _kg(1000, 10, 10000)
+    m, rs, hist, losses, ix = _fit_pair("TransE", 50, 2, "pairwise", X, batch_size=1000, epochs=3)
+    # the logged loss is the never-reset running mean of per-batch SUM losses
+    assert abs(hist.history["loss"][-1] - np.mean(losses)) <= 2e-4 * abs(np.mean(losses))
+    ent = m.get_embeddings(ix.ent_labels, "e")
+    rel = m.get_embeddings(ix.rel_labels, "r")
+    assert ent.shape == (ix.get_entities_count(), 50)
+    assert np.allclose(ent, rs.ent.detach().numpy(), rtol=1e-3, atol=2e-5)
+    assert np.allclose(rel, rs.rel.detach().numpy(), rtol=1e-3, atol=2e-5)
+    # predict == oracle scores on the SAME (GPU-trained) tables; unknown labels are dropped
+    Xt = X[:200]
+    sc = m.predict(np.concatenate([Xt, np.array([["nope", "r0", "e1"]])]))
+    assert sc.shape == (200,)
+    assert np.allclose(sc, c_oracle.score_triples("TransE", ent, rel, ix.get_indexes(Xt)), rtol=1e-4, atol=1e-5)
+    # evaluate: filtered ranks bit-exact against the oracle (+1, ScoringBasedEmbeddingModel.py:1684)
+    test = X[:150]
+    ranks = m.evaluate(test, use_filter={"train": X}, corrupt_side="s,o", verbose=False)
+    assert ranks.shape == (150, 2) and ranks.dtype == np.int32
+    tt, full = ix.get_indexes(test), ix.get_indexes(X)
+    for j, (side, a, b, c) in enumerate((("s", 1, 2, 0), ("o", 0, 1, 2))):
+        filt = [sorted(set(full[(full[:, a] == q[a]) & (full[:, b] == q[b])][:, c].tolist())) for q in tt]
+        ref = c_oracle.rank_triples("TransE", side, "worst", ent, rel, tt, filters=filt)
+        assert (ranks[:, j] == ref + 1).all()
+    # MR('s,o') equals MR over separate 's' and 'o' runs (tests/ampligraph/evaluation/test_evaluate.py:66,:129)
+    rs_ = m.evaluate(test, use_filter={"train": X}, corrupt_side="s", verbose=False)
+    ro_ = m.evaluate(test, use_filter={"train": X}, corrupt_side="o", verbose=False)
+    assert (rs_[:, 0] == ranks[:, 0]).all() and (ro_[:, 0] == ranks[:, 1]).all()
+    rso = m.evaluate(test, use_filter={"train": X}, corrupt_side="s+o", verbose=False)
+    assert (rso[:, 0] == ranks.sum(1) - 1).all()  # counts summed BEFORE the +1
+    # entities_subset
+    subset = ix.ent_labels[::7]
+    rsub = m.evaluate(test, corrupt_side="o", entities_subset=subset, verbose=False)
+    ref = c_oracle.rank_triples("TransE", "o", "worst", ent, rel, tt, cand_ids=ix.get_indexes(subset, "e"))
+    assert (rsub[:, 0] == ref + 1).all()
+
+
+@pytest.mark.parametrize("model_name,loss,optimizer", [("ComplEx", "self_adversarial", "adam"),
+                                                       ("DistMult", "multiclass_nll", "adagrad"),
+                                                       ("RotatE", "nll", "sgd"), ("HolE", "absolute_margin", "adam")])
+def test_fit_tracks_oracle(model_name, loss, optimizer):
+    X = _kg(300, 6, 3000, seed=3)
+    # RotatE: phase = theta * pi/range (x17.8 here) makes the sum-over-batch SGD trajectory chaotic at the
+    # default lr; a small lr keeps the two fp32 evaluations on the same trajectory
+    opt_params = {"learning_rate": 1e-5} if model_name == "RotatE" else None
+    m, rs, hist, losses, ix = _fit_pair(model_name, 16, 4, loss, X, batch_size=700, epochs=2, optimizer=optimizer,
+                                        opt_params=opt_params)
+    assert abs(hist.history["loss"][-1] - np.mean(losses)) <= 5e-4 * abs(np.mean(losses))
+    ent = m.get_embeddings(ix.ent_labels, "e")
+    assert np.allclose(ent, rs.ent.detach().numpy(), rtol=2e-3, atol=5e-5), np.abs(ent - rs.ent.detach().numpy()).max()
+
+
+def test_user_callable_loss_and_validation_and_weights(tmp_path):
+    from ampligraph_b200.latent_features import ScoringBasedEmbeddingModel
+    X = _kg(200, 5, 2000, seed=5)
+
+    def user_loss(scores_pos, scores_neg):  # torch tensors instead of the reference's TF tensors
+        return torch.nn.functional.softplus(1.0 - scores_pos + scores_neg).sum(0)
+
+    m = ScoringBasedEmbeddingModel(eta=3, k=8, scoring_type="DistMult", seed=1)
+    m.compile(optimizer="adam", loss=user_loss)
+    h = m.fit(X[:1800], batch_size=600, epochs=4, validation_data=X[1800:], validation_freq=2, verbose=False)
+    assert h.history["loss"][-1] < h.history["loss"][0]
+    assert len(h.history["val_mrr"]) == 2 and 0 < h.history["val_mrr"][-1] <= 1
+    p = str(tmp_path / "w.pkl")
+    m.save_weights(p)
+    m2 = ScoringBasedEmbeddingModel(eta=3, k=8, scoring_type="DistMult", seed=1)
+    m2.compile(optimizer="adam", loss=user_loss)
+    m2.load_weights(p)
+    assert np.array_equal(m.predict(X[:50]), m2.predict(X[:50]))
+    assert (m.evaluate(X[:20], verbose=False) == m2.evaluate(X[:20], verbose=False)).all()

@@ -33,7 +33,7 @@ def test_library_fails_loudly_without_gpu():
     import ctypes as C
     from ampligraph_b200 import _lib
     lib = _lib.load()
-    cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0)
+    cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0, 0, 0)
     h = C.c_void_p()
     rc = lib.kge_create(C.byref(cfg), C.byref(h))
     assert rc == _lib.KGE_ERR_CUDA and b"no CPU path" in lib.kge_last_error()
@@ -45,8 +45,8 @@ def test_library_fails_loudly_without_gpu():
 def test_config_struct_matches_header():
     import ctypes as C
     from ampligraph_b200 import _lib
-    assert C.sizeof(_lib.KgeConfig) == 56 and C.sizeof(_lib.KgeOptimizerConfig) == 40
-    bad = _lib.KgeConfig(12, 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0)
+    assert C.sizeof(_lib.KgeConfig) == 64 and C.sizeof(_lib.KgeOptimizerConfig) == 40
+    bad = _lib.KgeConfig(12, 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0, 0, 0)
     h = C.c_void_p()
     assert _lib.load().kge_create(C.byref(bad), C.byref(h)) == _lib.KGE_ERR_INVALID_ARGUMENT  # ABI guard first
 
