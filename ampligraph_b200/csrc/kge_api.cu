@@ -18,7 +18,7 @@ struct kge_handle {
     float rot_div;      // RotatE range/pi
     float *rot;         // [n_rel, ld] rotation table workspace (RotatE)
     // training launch geometry
-    int nit, G, warps, eta_pad, rows_bytes, region_bytes;
+    int nit, G, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats;
     // ranking workspace (grown on demand)
     long long ws_b;
     float *ws_q;      // 3 * ws_b * ld floats: qvec_s | qvec_o | qaux
@@ -97,22 +97,36 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     h->score_scale = (cfg->scoring == KGE_HOLE) ? hole_scale(L.K) : 1.f;
     h->rot_div = (cfg->scoring == KGE_ROTATE) ? rotate_divisor(L.K, cfg->n_rel) : 1.f;
 
-    // ---- training geometry: one warp per positive, (3+G) rows resident per warp ----
+    // ---- training geometry: one warp per positive; its slot holds (3+G) row windows ----
+    // window = wk floats per half (<= 128*NIT so that NIT float4 per lane cover it); rows wider than
+    // 512 floats per half are processed in n_cb column windows, eta > G negatives in groups of G.
     const int nch = L.kp / 4;
     const int nit_raw = (nch + 31) / 32;
-    h->nit = nit_raw <= 1 ? 1 : nit_raw <= 2 ? 2 : nit_raw <= 4 ? 4 : 0;
+    h->nit = nit_raw <= 1 ? 1 : nit_raw <= 2 ? 2 : 4;
+    h->wk = L.kp <= 512 ? L.kp : 512;
+    h->n_cb = (L.kp + h->wk - 1) / h->wk;
     h->eta_pad = (cfg->eta + 3) / 4 * 4;
-    const int row_bytes = L.ld * 4, aux = 3 * h->eta_pad * 4 + 16;
-    const int min_warps = 4;
-    int G = cfg->neg_group > 0 ? (cfg->neg_group < cfg->eta ? cfg->neg_group : cfg->eta) : cfg->eta;
-    while (G > 1 && (long long)((3 + G) * (long long)row_bytes + aux) * min_warps > h->max_smem) --G;
+    // layout experiments (kge_config.reserved): bit0 pads each row slot to a 128-byte multiple,
+    // bit1 pads the per-warp region to a 128-byte multiple
+    int row_bytes = L.halves * h->wk * 4, aux = 3 * h->eta_pad * 4 + 16;
+    if (cfg->reserved & 1) row_bytes = (row_bytes + 127) / 128 * 128;
+    h->slot_floats = row_bytes / 4;
+    const int max_warps = KGE_TRAIN_THREADS(cfg->scoring, h->nit) / 32;
+    // prefer everything resident (one gather per row) as long as >= KGE_MIN_RESIDENT_WARPS warps fit;
+    // otherwise shrink G until that many warps fit (the gradient pass then re-gathers the other groups)
+    int G = cfg->eta;
+    if (cfg->neg_group > 0) G = cfg->neg_group < cfg->eta ? cfg->neg_group : cfg->eta;
+    else {
+        const int want = max_warps < KGE_MIN_RESIDENT_WARPS ? max_warps : KGE_MIN_RESIDENT_WARPS;
+        while (G > 1 && (long long)((3 + G) * (long long)row_bytes + aux) * want > h->max_smem) --G;
+    }
     h->G = G;
     h->rows_bytes = (3 + G) * row_bytes;
     h->region_bytes = h->rows_bytes + aux;
-    int warps = h->region_bytes > 0 ? h->max_smem / h->region_bytes : 0;
-    const int max_warps = h->nit ? KGE_TRAIN_THREADS_FOR_NIT(h->nit) / 32 : 0;
+    if (cfg->reserved & 2) h->region_bytes = (h->region_bytes + 127) / 128 * 128;
+    int warps = h->max_smem / h->region_bytes;
     if (warps > max_warps) warps = max_warps;
-    h->warps = warps;  // 0 => training unsupported for this shape (reported by kge_train_step)
+    h->warps = warps;  // 0 => even (3+1) windows do not fit (reported by kge_train_step)
 
     if (cfg->scoring == KGE_ROTATE) {
         cudaError_t e2 = cudaMalloc(&h->rot, (size_t)cfg->n_rel * L.ld * sizeof(float));
@@ -220,9 +234,6 @@ extern "C" int kge_train_step(kge_handle *h, int32_t mode, const float *ent_dev,
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step: BACKWARD_EXT needs dpos_dev and dneg_dev");
     if (mode == KGE_STEP_FORWARD_ONLY && (!scores_pos_dev || !scores_neg_dev))
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step: FORWARD_ONLY needs both score outputs");
-    if (h->nit == 0)
-        return fail(KGE_ERR_UNSUPPORTED, "kge_train_step: k=%d exceeds the 512-float half-row limit of the "
-                    "warp-per-positive kernel", h->cfg.k);
     if (h->warps < 1)
         return fail(KGE_ERR_UNSUPPORTED, "kge_train_step: one positive's working set (%d B) exceeds shared memory (%d B)",
                     h->region_bytes, h->max_smem);
@@ -248,6 +259,9 @@ extern "C" int kge_train_step(kge_handle *h, int32_t mode, const float *ent_dev,
     p.ld = h->L.ld;
     p.nch = h->L.kp / 4;
     p.G = h->G;
+    p.wk = h->wk;
+    p.n_cb = h->n_cb;
+    p.slot_floats = h->slot_floats;
     p.eta_pad = h->eta_pad;
     p.rows_bytes = h->rows_bytes;
     p.region_bytes = h->region_bytes;
@@ -301,6 +315,51 @@ extern "C" int kge_optimizer_step(kge_handle *h, const kge_optimizer_config *opt
     KGE_CUDA(launch_optimizer(o, table_dev, grad_dev, slot0_dev, slot1_dev, rows * (long long)h->L.ld, reg_loss_dev,
                               h->sm_count, (cudaStream_t)stream),
              "kge_optimizer_step");
+    return KGE_OK;
+}
+
+static int fill_optim(const kge_optimizer_config *opt, int64_t t, OptimParams &o)
+{
+    o.kind = opt->kind;
+    o.lr = opt->learning_rate;
+    o.beta1 = opt->beta_1;
+    o.beta2 = opt->beta_2;
+    o.eps = opt->epsilon;
+    o.momentum = opt->momentum;
+    o.reg_p = opt->reg_p;
+    o.reg_lambda = opt->reg_lambda;
+    o.lr_t = (float)((double)opt->learning_rate * sqrt(1.0 - pow((double)opt->beta_2, (double)t)) /
+                     (1.0 - pow((double)opt->beta_1, (double)t)));
+    return 0;
+}
+
+extern "C" int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_config *opt, int64_t t, int32_t world,
+                                          int32_t rank, float *const *peer_tables, float *const *peer_grads,
+                                          float *slot0_shard_dev, float *slot1_shard_dev, int64_t row_begin,
+                                          int64_t row_end, double *reg_loss_dev, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_optimizer_step_sharded");
+    if (!opt || opt->struct_size != (int32_t)sizeof(kge_optimizer_config))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: bad kge_optimizer_config (ABI mismatch)");
+    if (opt->kind < KGE_OPT_SGD || opt->kind > KGE_OPT_ADAGRAD)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "Could not interpret optimizer identifier: %d", opt->kind);
+    if (world < 1 || world > KGE_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: world must be 1..%d and 0 <= rank < world", KGE_MAX_PEERS);
+    if (row_begin < 0 || row_end < row_begin || t < 1) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: bad row range / t");
+    if (row_end == row_begin) return KGE_OK;
+    if (!peer_tables || !peer_grads) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: null pointer arrays");
+    for (int q = 0; q < world; ++q)
+        if (!peer_tables[q] || !peer_grads[q]) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: null peer pointer for rank %d", q);
+    const bool need0 = opt->kind != KGE_OPT_SGD || opt->momentum != 0.f;
+    const bool need1 = opt->kind == KGE_OPT_ADAM;
+    if ((need0 && !slot0_shard_dev) || (need1 && !slot1_shard_dev))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: optimizer slot buffer missing");
+    OptimParams o;
+    fill_optim(opt, t, o);
+    KGE_CUDA(launch_optimizer_sharded(o, world, rank, peer_tables, peer_grads, slot0_shard_dev, slot1_shard_dev,
+                                      row_begin * (long long)h->L.ld, (row_end - row_begin) * (long long)h->L.ld,
+                                      reg_loss_dev, h->sm_count, (cudaStream_t)stream),
+             "kge_optimizer_step_sharded");
     return KGE_OK;
 }
 

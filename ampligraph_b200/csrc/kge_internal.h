@@ -4,8 +4,10 @@
 
 #define KGE_TRAIN_MAX_THREADS 512
 // per-lane register state grows with NIT (float4 chunks per lane): trade threads for registers
-#define KGE_TRAIN_THREADS_FOR_NIT(nit) ((nit) <= 1 ? 512 : (nit) == 2 ? 384 : 256)
+// (RotatE carries 11 float4 vectors of per-positive state per chunk: give it more registers)
+#define KGE_TRAIN_THREADS(model, nit) ((nit) <= 1 ? 512 : (nit) == 2 ? ((model) == KGE_ROTATE ? 256 : 384) : 256)
 #define KGE_MAX_SMEM_PER_CTA (227 * 1024)
+#define KGE_MIN_RESIDENT_WARPS 8  // tuned on B200: fewer warps/SM than this costs more than re-gathering
 
 namespace kge {
 
@@ -22,6 +24,8 @@ struct TrainParams {
     unsigned n_ent;
     int model, eta, kp, ld, nch;  // nch = kp/4 float4 chunks per half
     int G;                        // replaced rows resident per pass
+    int wk, n_cb;                 // column window (floats per half) and number of windows per row
+    int slot_floats;              // stride between row windows in the shared-memory slot
     int eta_pad;                  // round_up(eta,4)
     int rows_bytes, region_bytes; // per-warp shared-memory carve-up
     int loss, reduction, mode;
@@ -56,6 +60,11 @@ struct OptimParams {
 cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
                              long long n_floats, double *reg_loss, int sm_count, cudaStream_t st);
 cudaError_t launch_fill(float *p, long long n, float v, cudaStream_t st);
+#define KGE_MAX_PEERS 8
+// tables/grads: HOST arrays of `world` device pointers (own rank first is NOT required; index = rank)
+cudaError_t launch_optimizer_sharded(const OptimParams &o, int world, int rank, float *const *tables, float *const *grads,
+                                     float *slot0, float *slot1, long long off_floats, long long n_floats,
+                                     double *reg_loss, int sm_count, cudaStream_t st);
 
 // kge_rank.cu
 struct RankParams {

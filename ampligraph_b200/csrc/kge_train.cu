@@ -31,17 +31,60 @@ namespace kge {
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4ld(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void f4st(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
-__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
-__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-__device__ __forceinline__ float4 operator*(float a, float4 b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
+// Blackwell packed fp32: fma/mul/add.rn.f32x2 (SASS FFMA2/FMUL2/FADD2) do two IEEE fp32 operations per
+// issue slot on a 64-bit register pair.  The kernel is issue-bound, so every float4 op is two f32x2 ops.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float4 f4from(f32x2_t lo, f32x2_t hi)
+{
+    float4 r;
+    upk2(lo, r.x, r.y);
+    upk2(hi, r.z, r.w);
+    return r;
+}
+#define KGE_LO(v) pk2((v).x, (v).y)
+#define KGE_HI(v) pk2((v).z, (v).w)
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return f4from(add2(KGE_LO(a), KGE_LO(b)), add2(KGE_HI(a), KGE_HI(b))); }
+__device__ __forceinline__ float4 f4neg(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return a + f4neg(b); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return f4from(mul2(KGE_LO(a), KGE_LO(b)), mul2(KGE_HI(a), KGE_HI(b))); }
+__device__ __forceinline__ float4 operator*(float a, float4 b)
+{
+    const f32x2_t aa = pk2(a, a);
+    return f4from(mul2(aa, KGE_LO(b)), mul2(aa, KGE_HI(b)));
+}
 __device__ __forceinline__ float4 f4fma(float4 a, float4 b, float4 c)
 {
-    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+    return f4from(fma2(KGE_LO(a), KGE_LO(b), KGE_LO(c)), fma2(KGE_HI(a), KGE_HI(b), KGE_HI(c)));
 }
 __device__ __forceinline__ float4 f4fma(float a, float4 b, float4 c)
 {
-    return make_float4(fmaf(a, b.x, c.x), fmaf(a, b.y, c.y), fmaf(a, b.z, c.z), fmaf(a, b.w, c.w));
+    const f32x2_t aa = pk2(a, a);
+    return f4from(fma2(aa, KGE_LO(b), KGE_LO(c)), fma2(aa, KGE_HI(b), KGE_HI(c)));
 }
 __device__ __forceinline__ float f4hsum(float4 a) { return (a.x + a.y) + (a.z + a.w); }
 __device__ __forceinline__ float f4dot(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
@@ -62,14 +105,13 @@ __device__ __forceinline__ void red_add_v4(float *g, float4 v)
 }
 struct SinkSmem {
     static constexpr bool kDirect = false;
-    static __device__ __forceinline__ void put(float *slot, float *, int off, float4 v) { f4st(slot + off, v); }
+    static __device__ __forceinline__ void put(float *slot, float *, int soff, int, float4 v) { f4st(slot + soff, v); }
 };
 struct SinkRed {
     static constexpr bool kDirect = true;
-    static __device__ __forceinline__ void put(float *, float *grow, int off, float4 v) { red_add_v4(grow + off, v); }
+    static __device__ __forceinline__ void put(float *, float *grow, int, int goff, float4 v) { red_add_v4(grow + goff, v); }
 };
 
-__device__ __forceinline__ float4 f4neg(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
 __device__ __forceinline__ float f4mod_sum(float4 re, float4 im)
 {
     return (sqrtf(fmaf(im.x, im.x, re.x * re.x)) + sqrtf(fmaf(im.y, im.y, re.y * re.y))) +
@@ -143,8 +185,8 @@ struct Scorer<KGE_DISTMULT, NIT> {
                 float4 &W = SIDE ? Wo[it] : Ws[it];
                 W = f4fma(ga, va, W);
                 W = f4fma(gb, vb, W);
-                Sink::put(ra, ga_row, 4 * c, ga * q);
-                if (has_b) Sink::put(rb, gb_row, 4 * c, gb * q);
+                Sink::put(ra, ga_row, 4 * c, 4 * c, ga * q);
+                if (has_b) Sink::put(rb, gb_row, 4 * c, 4 * c, gb * q);
             }
         }
     }
@@ -159,9 +201,9 @@ struct Scorer<KGE_DISTMULT, NIT> {
                 float4 vs = f4ld(s + 4 * c), vp = f4ld(p + 4 * c), vo = f4ld(o + 4 * c);
                 float4 U = f4fma(gP, vs, Ws[it]);  // everything that sat in the subject slot
                 float4 X = f4fma(gP, vo, Wo[it]);  // everything that sat in the object slot
-                Sink::put(s, gs, 4 * c, vp * X);
-                Sink::put(o, go, 4 * c, U * vp);
-                Sink::put(p, gp, 4 * c, f4fma(U, vo, vs * Wo[it]));
+                Sink::put(s, gs, 4 * c, 4 * c, vp * X);
+                Sink::put(o, go, 4 * c, 4 * c, U * vp);
+                Sink::put(p, gp, 4 * c, 4 * c, f4fma(U, vo, vs * Wo[it]));
             }
         }
     }
@@ -174,7 +216,7 @@ template <int NIT>
 struct ComplexScorer {
     float4 A[NIT], Bv[NIT], C[NIT], D[NIT];          // subject-side / object-side query vectors
     float4 Wsr[NIT], Wsi[NIT], Wor[NIT], Woi[NIT];   // sum_j g_j r_j per side (re, im)
-    int lane, nch, kp;
+    int lane, nch, kp, hs;  // kp: half stride in HBM rows, hs: half stride of the staged row window
     __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
@@ -184,9 +226,9 @@ struct ComplexScorer {
             int c = lane + 32 * it;
             float4 sr = f4zero(), si = f4zero(), pr = f4zero(), pi = f4zero(), orr = f4zero(), oi = f4zero();
             if (c < nch) {
-                sr = f4ld(s + 4 * c); si = f4ld(s + kp + 4 * c);
-                pr = f4ld(p + 4 * c); pi = f4ld(p + kp + 4 * c);
-                orr = f4ld(o + 4 * c); oi = f4ld(o + kp + 4 * c);
+                sr = f4ld(s + 4 * c); si = f4ld(s + hs + 4 * c);
+                pr = f4ld(p + 4 * c); pi = f4ld(p + hs + 4 * c);
+                orr = f4ld(o + 4 * c); oi = f4ld(o + hs + 4 * c);
             }
             A[it] = f4fma(pi, oi, pr * orr);
             Bv[it] = pr * oi - pi * orr;
@@ -209,8 +251,8 @@ struct ComplexScorer {
                 const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
                 a = f4fma(f4ld(ra + 4 * c), qr, a);
                 b = f4fma(f4ld(rb + 4 * c), qr, b);
-                a = f4fma(f4ld(ra + kp + 4 * c), qi, a);
-                b = f4fma(f4ld(rb + kp + 4 * c), qi, b);
+                a = f4fma(f4ld(ra + hs + 4 * c), qi, a);
+                b = f4fma(f4ld(rb + hs + 4 * c), qi, b);
             }
         }
         pa = f4hsum(a);
@@ -224,18 +266,18 @@ struct ComplexScorer {
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + kp + 4 * c);
-                float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + kp + 4 * c);
+                float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + hs + 4 * c);
+                float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + hs + 4 * c);
                 const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
                 float4 &Wr = SIDE ? Wor[it] : Wsr[it];
                 float4 &Wi = SIDE ? Woi[it] : Wsi[it];
                 Wr = f4fma(ga, ar, Wr); Wi = f4fma(ga, ai, Wi);
                 Wr = f4fma(gb, br, Wr); Wi = f4fma(gb, bi, Wi);
-                Sink::put(ra, ga_row, 4 * c, ga * qr);
-                Sink::put(ra, ga_row, kp + 4 * c, ga * qi);
+                Sink::put(ra, ga_row, 4 * c, 4 * c, ga * qr);
+                Sink::put(ra, ga_row, hs + 4 * c, kp + 4 * c, ga * qi);
                 if (has_b) {
-                    Sink::put(rb, gb_row, 4 * c, gb * qr);
-                    Sink::put(rb, gb_row, kp + 4 * c, gb * qi);
+                    Sink::put(rb, gb_row, 4 * c, 4 * c, gb * qr);
+                    Sink::put(rb, gb_row, hs + 4 * c, kp + 4 * c, gb * qi);
                 }
             }
         }
@@ -248,20 +290,20 @@ struct ComplexScorer {
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 sr = f4ld(s + 4 * c), si = f4ld(s + kp + 4 * c);
-                float4 pr = f4ld(p + 4 * c), pi = f4ld(p + kp + 4 * c);
-                float4 orr = f4ld(o + 4 * c), oi = f4ld(o + kp + 4 * c);
+                float4 sr = f4ld(s + 4 * c), si = f4ld(s + hs + 4 * c);
+                float4 pr = f4ld(p + 4 * c), pi = f4ld(p + hs + 4 * c);
+                float4 orr = f4ld(o + 4 * c), oi = f4ld(o + hs + 4 * c);
                 float4 Ur = f4fma(gP, sr, Wsr[it]), Ui = f4fma(gP, si, Wsi[it]);    // subject-slot mass
                 float4 Xr = f4fma(gP, orr, Wor[it]), Xi = f4fma(gP, oi, Woi[it]);   // object-slot mass
                 // d/ds f(s,p,X)
-                Sink::put(s, gs, 4 * c, f4fma(pi, Xi, pr * Xr));
-                Sink::put(s, gs, kp + 4 * c, pr * Xi - pi * Xr);
+                Sink::put(s, gs, 4 * c, 4 * c, f4fma(pi, Xi, pr * Xr));
+                Sink::put(s, gs, hs + 4 * c, kp + 4 * c, pr * Xi - pi * Xr);
                 // d/do f(U,p,o)
-                Sink::put(o, go, 4 * c, Ur * pr - Ui * pi);
-                Sink::put(o, go, kp + 4 * c, f4fma(Ur, pi, Ui * pr));
+                Sink::put(o, go, 4 * c, 4 * c, Ur * pr - Ui * pi);
+                Sink::put(o, go, hs + 4 * c, kp + 4 * c, f4fma(Ur, pi, Ui * pr));
                 // d/dp [f(U,p,o) + f(s,p,Wo)]
-                Sink::put(p, gp, 4 * c, f4fma(Ur, orr, Ui * oi) + f4fma(sr, Wor[it], si * Woi[it]));
-                Sink::put(p, gp, kp + 4 * c, (Ur * oi - Ui * orr) + (sr * Woi[it] - si * Wor[it]));
+                Sink::put(p, gp, 4 * c, 4 * c, f4fma(Ur, orr, Ui * oi) + f4fma(sr, Wor[it], si * Woi[it]));
+                Sink::put(p, gp, hs + 4 * c, kp + 4 * c, (Ur * oi - Ui * orr) + (sr * Woi[it] - si * Wor[it]));
             }
         }
     }
@@ -320,8 +362,8 @@ struct Scorer<KGE_TRANSE, NIT> {
                 float4 sb = gb * f4sgn(SIDE ? (Qo[it] - vb) : (vb + Qs[it]));
                 float4 &V = SIDE ? Vo[it] : Vs[it];
                 V = V + sa + sb;
-                Sink::put(ra, ga_row, 4 * c, SIDE ? sa : f4neg(sa));
-                if (has_b) Sink::put(rb, gb_row, 4 * c, SIDE ? sb : f4neg(sb));
+                Sink::put(ra, ga_row, 4 * c, 4 * c, SIDE ? sa : f4neg(sa));
+                if (has_b) Sink::put(rb, gb_row, 4 * c, 4 * c, SIDE ? sb : f4neg(sb));
             }
         }
     }
@@ -335,9 +377,9 @@ struct Scorer<KGE_TRANSE, NIT> {
             if (c < nch) {
                 float4 vo = f4ld(o + 4 * c);
                 float4 Vp = gP * f4sgn(Qo[it] - vo);
-                Sink::put(s, gs, 4 * c, f4neg(Vp + Vo[it]));
-                Sink::put(p, gp, 4 * c, f4neg(Vp + Vs[it] + Vo[it]));
-                Sink::put(o, go, 4 * c, Vp + Vs[it]);
+                Sink::put(s, gs, 4 * c, 4 * c, f4neg(Vp + Vo[it]));
+                Sink::put(p, gp, 4 * c, 4 * c, f4neg(Vp + Vs[it] + Vo[it]));
+                Sink::put(o, go, 4 * c, 4 * c, Vp + Vs[it]);
             }
         }
     }
@@ -353,7 +395,7 @@ template <int NIT>
 struct Scorer<KGE_ROTATE, NIT> {
     float4 Cs[NIT], Sn[NIT], Yr[NIT], Yi[NIT], Or_[NIT], Oi[NIT];
     float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], Aphi[NIT];
-    int lane, nch, kp;
+    int lane, nch, kp, hs;  // kp: half stride in HBM rows, hs: half stride of the staged row window
     static __device__ __forceinline__ void unit(float4 re, float4 im, float g, float4 &a, float4 &b)
     {
         float m0 = sqrtf(fmaf(im.x, im.x, re.x * re.x)), m1 = sqrtf(fmaf(im.y, im.y, re.y * re.y));
@@ -373,9 +415,9 @@ struct Scorer<KGE_ROTATE, NIT> {
             float4 sr = f4zero(), si = f4zero();
             Cs[it] = Sn[it] = Or_[it] = Oi[it] = f4zero();
             if (c < nch) {
-                sr = f4ld(s + 4 * c); si = f4ld(s + kp + 4 * c);
-                Cs[it] = f4ld(p + 4 * c); Sn[it] = f4ld(p + kp + 4 * c);
-                Or_[it] = f4ld(o + 4 * c); Oi[it] = f4ld(o + kp + 4 * c);
+                sr = f4ld(s + 4 * c); si = f4ld(s + hs + 4 * c);
+                Cs[it] = f4ld(p + 4 * c); Sn[it] = f4ld(p + hs + 4 * c);
+                Or_[it] = f4ld(o + 4 * c); Oi[it] = f4ld(o + hs + 4 * c);
             }
             Yr[it] = sr * Cs[it] - si * Sn[it];
             Yi[it] = f4fma(sr, Sn[it], si * Cs[it]);
@@ -392,8 +434,8 @@ struct Scorer<KGE_ROTATE, NIT> {
         for (int it = 0; it < NIT; ++it) {
             int c = lane + 32 * it;
             if (c < nch) {
-                float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + kp + 4 * c);
-                float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + kp + 4 * c);
+                float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + hs + 4 * c);
+                float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + hs + 4 * c);
                 if (SIDE) {
                     a -= f4mod_sum(Yr[it] - ar, Yi[it] - ai);
                     b -= f4mod_sum(Yr[it] - br, Yi[it] - bi);
@@ -409,19 +451,19 @@ struct Scorer<KGE_ROTATE, NIT> {
     template <int SIDE, class Sink>
     __device__ __forceinline__ void grad1(float *r, float *grow, float g, int it, int c, bool emit)
     {
-        float4 rr = f4ld(r + 4 * c), ri = f4ld(r + kp + 4 * c), a, b;
+        float4 rr = f4ld(r + 4 * c), ri = f4ld(r + hs + 4 * c), a, b;
         if (SIDE) {  // residual = y(s) - r ; df/dr = +(a,b)
             unit(Yr[it] - rr, Yi[it] - ri, g, a, b);
             Zor[it] = Zor[it] + a; Zoi[it] = Zoi[it] + b;
-            if (emit) { Sink::put(r, grow, 4 * c, a); Sink::put(r, grow, kp + 4 * c, b); }
+            if (emit) { Sink::put(r, grow, 4 * c, 4 * c, a); Sink::put(r, grow, hs + 4 * c, kp + 4 * c, b); }
         } else {  // residual = R(phi) r - o ; df/dr = -R(-phi)(a,b)
             float4 yr = rr * Cs[it] - ri * Sn[it], yi = f4fma(rr, Sn[it], ri * Cs[it]);
             unit(yr - Or_[it], yi - Oi[it], g, a, b);
             Zsr[it] = Zsr[it] + a; Zsi[it] = Zsi[it] + b;
             Aphi[it] = Aphi[it] + (a * yi - b * yr);
             if (emit) {
-                Sink::put(r, grow, 4 * c, f4neg(f4fma(a, Cs[it], b * Sn[it])));
-                Sink::put(r, grow, kp + 4 * c, a * Sn[it] - b * Cs[it]);
+                Sink::put(r, grow, 4 * c, 4 * c, f4neg(f4fma(a, Cs[it], b * Sn[it])));
+                Sink::put(r, grow, hs + 4 * c, kp + 4 * c, a * Sn[it] - b * Cs[it]);
             }
         }
     }
@@ -451,16 +493,25 @@ struct Scorer<KGE_ROTATE, NIT> {
                 float4 a, b;
                 unit(Yr[it] - Or_[it], Yi[it] - Oi[it], gP, a, b);
                 float4 Zr = a + Zor[it], Zi = b + Zoi[it];  // everything with y = R(phi) s
-                Sink::put(s, gs, 4 * c, f4neg(f4fma(Zr, Cs[it], Zi * Sn[it])));
-                Sink::put(s, gs, kp + 4 * c, Zr * Sn[it] - Zi * Cs[it]);
-                Sink::put(o, go, 4 * c, a + Zsr[it]);
-                Sink::put(o, go, kp + 4 * c, b + Zsi[it]);
-                Sink::put(p, gp, 4 * c, inv_div * (Aphi[it] + (Zr * Yi[it] - Zi * Yr[it])));
-                if (!Sink::kDirect) Sink::put(p, gp, kp + 4 * c, f4zero());
+                Sink::put(s, gs, 4 * c, 4 * c, f4neg(f4fma(Zr, Cs[it], Zi * Sn[it])));
+                Sink::put(s, gs, hs + 4 * c, kp + 4 * c, Zr * Sn[it] - Zi * Cs[it]);
+                Sink::put(o, go, 4 * c, 4 * c, a + Zsr[it]);
+                Sink::put(o, go, hs + 4 * c, kp + 4 * c, b + Zsi[it]);
+                Sink::put(p, gp, 4 * c, 4 * c, inv_div * (Aphi[it] + (Zr * Yi[it] - Zi * Yr[it])));
+                if (!Sink::kDirect) Sink::put(p, gp, hs + 4 * c, kp + 4 * c, f4zero());
             }
         }
     }
 };
+
+__device__ __forceinline__ void warp_sum2(float &a, float &b)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+}
 
 // --------------------------------------------------------------------------
 // per-positive loss and dL/dscore (warp-cooperative; lanes stride over j).
@@ -520,6 +571,24 @@ __device__ float loss_and_dscores(const TrainParams &p, float P, float *sc, int 
         break;
     }
     case KGE_LOSS_SELF_ADVERSARIAL: {  // loss_functions.py:563-572, softmax NOT detached
+        // with x = -N - margin, t = exp(-|x|):  log_sigmoid(x) = min(x,0) - log1p(t) and
+        // sigmoid(N + margin) = sigmoid(-x) = (x < 0 ? 1 : t) / (1 + t): one exp + one log1p per corruption
+        if (eta <= 32) {  // one corruption per lane: everything stays in registers
+            const bool on = lane < eta;
+            const float N = on ? sc[lane] : 0.f;
+            const float mx = warp_max(on ? p.alpha * N : -INFINITY);
+            const float e = on ? expf(p.alpha * N - mx) : 0.f;
+            const float x = -N - p.margin, t = expf(-fabsf(x));
+            const float lj = fminf(x, 0.f) - log1pf(t);
+            const float sg = ((x < 0.f) ? 1.f : t) / (1.f + t);
+            float z = e, sl = e * lj;
+            warp_sum2(z, sl);
+            const float S = sl / z, pj = e / z;
+            if (on) sc[lane] = w * (pj * sg - p.alpha * pj * (lj - S));
+            loss = -log_sigmoid(p.margin + P) - w * S;
+            dP = -sigmoidf(-(p.margin + P));
+            break;
+        }
         float mx = -INFINITY;
         for (int j = lane; j < eta; j += 32) mx = fmaxf(mx, p.alpha * sc[j]);
         mx = warp_max(mx);
@@ -565,14 +634,6 @@ __device__ float loss_and_dscores(const TrainParams &p, float P, float *sc, int 
 // --------------------------------------------------------------------------
 // the kernel
 // --------------------------------------------------------------------------
-__device__ __forceinline__ void warp_sum2(float &a, float &b)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-}
 
 // Visit the resident corruptions [0, gs) of one group, partitioned by side and two at a
 // time: f(side_tag, slot_a, slot_b, has_b).  nside[] holds keep_subj (1 = object replaced).
@@ -597,13 +658,21 @@ __device__ __forceinline__ void for_each_pair_by_side(const int *nside, int gs, 
     }
 }
 
-template <int MODEL, int NIT, class Sink>
-__global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kernel(const TrainParams p)
+// Shared-memory slot of one warp: (3+G) row WINDOWS.  A window is the [cb*wk, cb*wk+wk) column
+// slice of each half of a row (wk = min(kp, 128*NIT) floats), so one positive's working set is
+// bounded in registers (NIT float4 per lane per vector) and in shared memory whatever k and eta
+// are: columns are processed window by window (scores add up over windows), negatives group by
+// group.  With one window and one group (the common case: cfg2/cfg3) every row is gathered once
+// and stays resident for the gradient pass.
+// RESIDENT = one window and one group (decided on the host): the window/group machinery folds away.
+template <int MODEL, int NIT, class Sink, bool RESIDENT>
+__global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kernel(const TrainParams p)
 {
+    constexpr int HALVES = (MODEL == KGE_TRANSE || MODEL == KGE_DISTMULT) ? 1 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *region = smem_raw + (size_t)warp * p.region_bytes;
-    float *rows = reinterpret_cast<float *>(region);  // (3+G) rows of ld floats
+    float *rows = reinterpret_cast<float *>(region);  // (3+G) windows of lw floats
     float *sc = reinterpret_cast<float *>(region + p.rows_bytes);
     int *nid = reinterpret_cast<int *>(sc + p.eta_pad);
     int *nside = nid + p.eta_pad;
@@ -614,13 +683,44 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kern
     fence_proxy_async_smem();
     __syncthreads();
 
-    const int ld = p.ld, eta = p.eta, G = p.G;
-    const uint32_t row_bytes = (uint32_t)ld * 4u;
-    const int n_groups = (eta + G - 1) / G;
-    float *srow = rows, *prow = rows + ld, *orow = rows + 2 * ld, *nrows = rows + 3 * ld;
+    const int ld = p.ld, kp = p.kp, eta = p.eta, G = RESIDENT ? p.eta : p.G;
+    const int wk = RESIDENT ? p.kp : p.wk;     // window floats per half
+    const int lw = p.slot_floats;              // slot stride (>= HALVES*wk)
+    const int n_cb = RESIDENT ? 1 : p.n_cb;    // column windows per row
+    const int n_groups = RESIDENT ? 1 : (eta + G - 1) / G;
+    constexpr bool resident = RESIDENT;
+    float *srow = rows, *prow = rows + lw, *orow = rows + 2 * lw, *nrows = rows + 3 * lw;
     const float scale = p.score_scale;  // HolE 2/k, else 1
     uint32_t phase = 0;
     double loss_acc = 0.0;
+
+    // gather `cnt` row windows (rows given by src(r)) into consecutive slots starting at `dst`
+    auto gather = [&](float *dst, int cnt, int cb, auto src) {
+        const int wch_t = min(wk, kp - cb * wk);  // floats of this window per half
+        const uint32_t bytes = (n_cb == 1) ? (uint32_t)ld * 4u : (uint32_t)wch_t * 4u;
+        const int copies = (n_cb == 1) ? 1 : HALVES;
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * copies * bytes);
+        __syncwarp();
+        for (int r = lane; r < cnt * copies; r += 32) {
+            const int row = (copies == 1) ? r : r / HALVES, h = (copies == 1) ? 0 : r - row * HALVES;
+            bulk_load(dst + (size_t)row * lw + h * wk, src(row) + h * kp + cb * wk, bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+    };
+    // push `cnt` gradient row windows from shared memory into the gradient table (bulk scatter mode)
+    auto scatter = [&](float *srcw, int cnt, int cb, auto dst) {
+        const int wch_t = min(wk, kp - cb * wk);
+        const uint32_t bytes = (n_cb == 1) ? (uint32_t)ld * 4u : (uint32_t)wch_t * 4u;
+        const int copies = (n_cb == 1) ? 1 : HALVES;
+        fence_proxy_async_smem();
+        __syncwarp();
+        for (int r = lane; r < cnt * copies; r += 32) {
+            const int row = (copies == 1) ? r : r / HALVES, h = (copies == 1) ? 0 : r - row * HALVES;
+            bulk_reduce_add_f32(dst(row) + h * kp + cb * wk, srcw + (size_t)row * lw + h * wk, bytes);
+        }
+        bulk_commit();
+    };
 
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B; i += n_warps) {
@@ -633,53 +733,50 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kern
             else draw_corruption(p.seed, p.step, r, p.n_ent, &keep, &repl);
             nid[j] = repl;
             nside[j] = keep;  // keep_subj = 1 -> object replaced -> side 1
+            if (!resident) sc[j] = 0.f;
         }
         __syncwarp();
-        // ---- gather s, p, o and the first group of replaced rows (A2) ----
-        const int g0 = min(G, eta);
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(3 + g0) * row_bytes);
-        __syncwarp();
-        for (int r = lane; r < 3 + g0; r += 32) {
-            const float *src = (r == 0)   ? p.ent + (size_t)s_id * ld
-                               : (r == 1) ? p.rel + (size_t)p_id * ld
-                               : (r == 2) ? p.ent + (size_t)o_id * ld
-                                          : p.ent + (size_t)nid[r - 3] * ld;
-            bulk_load(rows + (size_t)r * ld, src, row_bytes, bar);
-        }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
+        auto spo_src = [&](int r) { return r == 0 ? p.ent + (size_t)s_id * ld : r == 1 ? p.rel + (size_t)p_id * ld : p.ent + (size_t)o_id * ld; };
+        float *const gs_row = p.grad_ent + (size_t)s_id * ld, *const gp_row = p.grad_rel + (size_t)p_id * ld,
+                     *const go_row = p.grad_ent + (size_t)o_id * ld;
 
         Scorer<MODEL, NIT> S;
-        S.nch = p.nch;
-        if constexpr (MODEL != KGE_TRANSE && MODEL != KGE_DISTMULT) S.kp = p.kp;
-        const float P = warp_sum(S.prep(srow, prow, orow, lane));
+        if constexpr (HALVES == 2) { S.kp = kp; S.hs = wk; }
+        float P = 0.f;
 
-        // ---- pass A: scores of all corruptions (A4) ----
-        for (int g = 0; g < n_groups; ++g) {
-            const int j0 = g * G, gs = min(G, eta - j0);
-            if (g > 0) {
+        // ---- pass A: scores, window by window, group by group (A2 + A4) ----
+        for (int cb = 0; cb < n_cb; ++cb) {
+            S.nch = min(wk, kp - cb * wk) / 4;
+            for (int g = 0; g < n_groups; ++g) {
+                const int j0 = g * G, gsz = min(G, eta - j0);
                 __syncwarp();
-                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)gs * row_bytes);
-                __syncwarp();
-                for (int r = lane; r < gs; r += 32)
-                    bulk_load(nrows + (size_t)r * ld, p.ent + (size_t)nid[j0 + r] * ld, row_bytes, bar);
-                mbar_wait(bar, phase);
-                phase ^= 1u;
+                if (g == 0) {  // s, p, o windows + first group in one transaction
+                    gather(rows, 3 + gsz, cb, [&](int r) { return r < 3 ? spo_src(r) : p.ent + (size_t)nid[r - 3] * ld; });
+                    P += warp_sum(S.prep(srow, prow, orow, lane));
+                } else {
+                    gather(nrows, gsz, cb, [&](int r) { return p.ent + (size_t)nid[j0 + r] * ld; });
+                }
+                auto store = [&](int a, int b, bool has_b, float pa, float pb) {
+                    if (lane == 0) {
+                        if (resident) { sc[j0 + a] = pa; if (has_b) sc[j0 + b] = pb; }
+                        else { sc[j0 + a] += pa; if (has_b) sc[j0 + b] += pb; }
+                    }
+                };
+                for_each_pair_by_side(
+                    nside + j0, gsz, lane,
+                    [&](int a, int b, bool has_b) {
+                        float pa, pb;
+                        S.template partial2<0>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
+                        warp_sum2(pa, pb);
+                        store(a, b, has_b, pa, pb);
+                    },
+                    [&](int a, int b, bool has_b) {
+                        float pa, pb;
+                        S.template partial2<1>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
+                        warp_sum2(pa, pb);
+                        store(a, b, has_b, pa, pb);
+                    });
             }
-            for_each_pair_by_side(
-                nside + j0, gs, lane,
-                [&](int a, int b, bool has_b) {
-                    float pa, pb;
-                    S.template partial2<0>(nrows + (size_t)a * ld, nrows + (size_t)b * ld, pa, pb);
-                    warp_sum2(pa, pb);
-                    if (lane == 0) { sc[j0 + a] = pa; if (has_b) sc[j0 + b] = pb; }
-                },
-                [&](int a, int b, bool has_b) {
-                    float pa, pb;
-                    S.template partial2<1>(nrows + (size_t)a * ld, nrows + (size_t)b * ld, pa, pb);
-                    warp_sum2(pa, pb);
-                    if (lane == 0) { sc[j0 + a] = pa; if (has_b) sc[j0 + b] = pb; }
-                });
         }
         __syncwarp();
 
@@ -701,51 +798,43 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS_FOR_NIT(NIT)) kge_train_kern
         }
         __syncwarp();
 
-        // ---- pass B: gradient rows, last group first (it is still resident) ----
-        for (int g = n_groups - 1; g >= 0; --g) {
-            const int j0 = g * G, gs = min(G, eta - j0);
-            if (g != n_groups - 1) {
-                if (!Sink::kDirect) bulk_wait_read_all();  // copy engine done reading the previous group's rows
-                __syncwarp();
-                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)gs * row_bytes);
-                __syncwarp();
-                for (int r = lane; r < gs; r += 32)
-                    bulk_load(nrows + (size_t)r * ld, p.ent + (size_t)nid[j0 + r] * ld, row_bytes, bar);
-                mbar_wait(bar, phase);
-                phase ^= 1u;
+        // ---- pass B: gradients, last window / last group first (they are still resident) ----
+        for (int cb = n_cb - 1; cb >= 0; --cb) {
+            S.nch = min(wk, kp - cb * wk) / 4;
+            const int gofs = cb * wk;  // column offset of this window inside a gradient row
+            for (int g = n_groups - 1; g >= 0; --g) {
+                const int j0 = g * G, gsz = min(G, eta - j0);
+                const bool still_there = (cb == n_cb - 1 && g == n_groups - 1);
+                if (!still_there) {
+                    if (!Sink::kDirect) bulk_wait_read_all();  // copy engine done reading what we overwrite
+                    __syncwarp();
+                    if (g == n_groups - 1) {  // first visit of this window: s, p, o come along and state is rebuilt
+                        gather(rows, 3 + gsz, cb, [&](int r) { return r < 3 ? spo_src(r) : p.ent + (size_t)nid[j0 + r - 3] * ld; });
+                        (void)S.prep(srow, prow, orow, lane);
+                    } else {
+                        gather(nrows, gsz, cb, [&](int r) { return p.ent + (size_t)nid[j0 + r] * ld; });
+                    }
+                }
+                for_each_pair_by_side(
+                    nside + j0, gsz, lane,
+                    [&](int a, int b, bool has_b) {
+                        S.template grad2<0, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw,
+                                                  p.grad_ent + (size_t)nid[j0 + a] * ld + gofs,
+                                                  p.grad_ent + (size_t)nid[j0 + b] * ld + gofs, scale * sc[j0 + a],
+                                                  has_b ? scale * sc[j0 + b] : 0.f, has_b);
+                    },
+                    [&](int a, int b, bool has_b) {
+                        S.template grad2<1, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw,
+                                                  p.grad_ent + (size_t)nid[j0 + a] * ld + gofs,
+                                                  p.grad_ent + (size_t)nid[j0 + b] * ld + gofs, scale * sc[j0 + a],
+                                                  has_b ? scale * sc[j0 + b] : 0.f, has_b);
+                    });
+                if (!Sink::kDirect) scatter(nrows, gsz, cb, [&](int r) { return p.grad_ent + (size_t)nid[j0 + r] * ld; });
             }
-            for_each_pair_by_side(
-                nside + j0, gs, lane,
-                [&](int a, int b, bool has_b) {
-                    S.template grad2<0, Sink>(nrows + (size_t)a * ld, nrows + (size_t)b * ld,
-                                              p.grad_ent + (size_t)nid[j0 + a] * ld, p.grad_ent + (size_t)nid[j0 + b] * ld,
-                                              scale * sc[j0 + a], has_b ? scale * sc[j0 + b] : 0.f, has_b);
-                },
-                [&](int a, int b, bool has_b) {
-                    S.template grad2<1, Sink>(nrows + (size_t)a * ld, nrows + (size_t)b * ld,
-                                              p.grad_ent + (size_t)nid[j0 + a] * ld, p.grad_ent + (size_t)nid[j0 + b] * ld,
-                                              scale * sc[j0 + a], has_b ? scale * sc[j0 + b] : 0.f, has_b);
-                });
-            if (!Sink::kDirect) {
-                fence_proxy_async_smem();
-                __syncwarp();
-                for (int r = lane; r < gs; r += 32)
-                    bulk_reduce_add_f32(p.grad_ent + (size_t)nid[j0 + r] * ld, nrows + (size_t)r * ld, row_bytes);
-                bulk_commit();
-            }
+            S.template finish<Sink>(srow, prow, orow, gs_row + gofs, gp_row + gofs, go_row + gofs, scale * dP, p.inv_div);
+            if (!Sink::kDirect) scatter(rows, 3, cb, [&](int r) { return r == 0 ? gs_row : r == 1 ? gp_row : go_row; });
         }
-        float *gs_row = p.grad_ent + (size_t)s_id * ld, *gp_row = p.grad_rel + (size_t)p_id * ld,
-              *go_row = p.grad_ent + (size_t)o_id * ld;
-        S.template finish<Sink>(srow, prow, orow, gs_row, gp_row, go_row, scale * dP, p.inv_div);
-        if (!Sink::kDirect) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) bulk_reduce_add_f32(gs_row, srow, row_bytes);
-            if (lane == 1) bulk_reduce_add_f32(gp_row, prow, row_bytes);
-            if (lane == 2) bulk_reduce_add_f32(go_row, orow, row_bytes);
-            bulk_commit();
-            bulk_wait_read_all();  // slot is reused by the next positive's gather
-        }
+        if (!Sink::kDirect) bulk_wait_read_all();  // slot is reused by the next positive's gather
         __syncwarp();
     }
     if (!Sink::kDirect) bulk_wait_all();
@@ -795,8 +884,10 @@ static cudaError_t launch_train_model(const TrainParams &p, int nit, int sm_coun
 {
 #define KGE_LAUNCH(N)                                                                                       \
     {                                                                                                       \
-        auto kern = p.scatter_mode == KGE_SCATTER_RED_V4 ? kge_train_kernel<MODEL, N, SinkRed>              \
-                                                         : kge_train_kernel<MODEL, N, SinkSmem>;            \
+        const bool res = p.n_cb == 1 && p.G >= p.eta;                                                       \
+        auto kern = p.scatter_mode == KGE_SCATTER_RED_V4                                                    \
+                        ? (res ? kge_train_kernel<MODEL, N, SinkRed, true> : kge_train_kernel<MODEL, N, SinkRed, false>)   \
+                        : (res ? kge_train_kernel<MODEL, N, SinkSmem, true> : kge_train_kernel<MODEL, N, SinkSmem, false>); \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                                     \
         int occ = 0;                                                                                        \

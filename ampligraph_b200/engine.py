@@ -23,7 +23,7 @@ def _ptr(t):
 class KGEEngine:
     def __init__(self, scoring_type, k, eta, n_ent, n_rel, loss="pairwise", loss_params=None,
                  optimizer="adam", optimizer_params=None, regularizer=None, device=0, neg_group=0,
-                 scatter=None):
+                 scatter=None, table_alloc=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("ampligraph_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -42,7 +42,8 @@ class KGEEngine:
         cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), _lib.SCORING[scoring_type], int(k), int(eta), int(n_ent),
                              int(n_rel), _lib.LOSSES[loss], _lib.REDUCTIONS[reduction],
                              float(lp.get("margin", default_margin)), float(lp.get("alpha", 0.5)), int(device),
-                             int(neg_group), _lib.SCATTER[scatter or os.environ.get("KGE_B200_SCATTER", "bulk")], 0)
+                             int(neg_group), _lib.SCATTER[scatter or os.environ.get("KGE_B200_SCATTER", "red_v4")],
+                             int(os.environ.get("KGE_B200_LAYOUT", "0")))
         h = C.c_void_p()
         _lib.check(self.lib.kge_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -51,8 +52,13 @@ class KGEEngine:
         self.ld = self.lib.kge_row_stride(h)
         with torch.cuda.device(self.device):
             z = lambda rows: torch.zeros((rows, self.ld), dtype=torch.float32, device=self.device)
-            self.ent, self.rel = z(self.n_ent), z(self.n_rel)
-            self.g_ent, self.g_rel = z(self.n_ent), z(self.n_rel)
+            if table_alloc is not None:  # e.g. symmetric (peer-mappable) memory for the multi-GPU path
+                self.ent, self.rel, self.g_ent, self.g_rel = table_alloc(self.n_ent, self.n_rel, self.ld, self.device)
+                for t_ in (self.ent, self.rel, self.g_ent, self.g_rel):
+                    assert t_.is_contiguous() and t_.dtype == torch.float32
+            else:
+                self.ent, self.rel = z(self.n_ent), z(self.n_rel)
+                self.g_ent, self.g_rel = z(self.n_ent), z(self.n_rel)
             self.loss_acc = torch.zeros(2, dtype=torch.float64, device=self.device)  # [batch loss, reg loss]
         self.set_optimizer(optimizer, optimizer_params, regularizer)
         self.launches = 0  # kernels launched by this engine (bench.py reports it)

@@ -58,41 +58,64 @@ def measured_hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML is polled from a thread
+    every ~2 ms (the nvidia-smi -lms loop of B200_PROFILING.md cannot deliver a sample inside a
+    timed region that lasts a few tens of milliseconds)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.samples, self._stop, self.th, self.err = index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            self.h = None
+            if uuid:
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+                except Exception:
+                    self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # NVML missing: report it, do not fail the benchmark
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))))
+            except Exception as e:
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()  # exact PID we started
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop = True
+        if self.th is not None:
+            self.th.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable: %s" % self.err],
+                    "samples": 0}
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(k for k, b in bits.items() if any(r & b for _, r in self.samples))
+        return {"sm_mhz": float(np.median([c for c, _ in self.samples])), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.samples)}
 
 
 # ---------------------------------------------------------------------------
@@ -101,8 +124,6 @@ class ClockSampler:
 def run_cpu_reference(steps, warmup, batch, threads=None):
     import torch
     from oracle import c_oracle, ref_step  # bench.py's cpu_baseline leg is allowed to execute oracle/
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
     rng = np.random.default_rng(0)
     K = 2 * CFG["k"]
     ent, rel = glorot(CFG["n_ent"], K, rng), glorot(CFG["n_rel"], K, rng)
@@ -118,6 +139,20 @@ def run_cpu_reference(steps, warmup, batch, threads=None):
         rs.train_step(t, c_oracle.corrupt(t, CFG["eta"], keep, repl))
         return len(t)
 
+    if threads is None:
+        # "all the host threads it can use": torch-CPU oversubscribes on many-core hosts (128 threads were 4x
+        # slower than 8 on the first B200 box), so time one step per candidate count and keep the fastest
+        best = None
+        for th in sorted({os.cpu_count(), 64, 32, 16, 8} & set(range(1, os.cpu_count() + 1)), reverse=True):
+            torch.set_num_threads(th)
+            one(0)
+            t0 = time.perf_counter()
+            one(1)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, th)
+        threads = best[1]
+    torch.set_num_threads(threads)
     for i in range(warmup):
         one(i)
     t0, pos = time.perf_counter(), 0
@@ -131,24 +166,26 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, dt, threads = run_cpu_reference(args.steps, args.warmup, CFG["batch"])
+    # bounded: the CPU step takes seconds, so cap the sample at 10 timed steps (3 warm-up)
+    steps, warmup = min(args.steps, 10), min(args.warmup, 3)
+    value, dt, threads = run_cpu_reference(steps, warmup, CFG["batch"])
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "triples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(1),
             "cpu_baseline": {"value": value, "unit": "triples/s", "cores": threads, "kind": "port",
                              "sample": "%d steps of %d positives (oracle/ref_step.py, torch-CPU fp32, op-for-op "
-                                       "restatement of the TF graph; TensorFlow is not installable here)" % (args.steps, CFG["batch"])},
+                                       "restatement of the TF graph; TensorFlow is not installable here)" % (steps, CFG["batch"])},
             "e2e": {"value": value, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, dp_mode=""):
     return {"workload": "cfg2: ComplEx k=200 eta=10 self_adversarial(margin 3, alpha 0.5), Adam lr 1e-3, "
                         "FB15K-237-shaped synthetic KG (14505 ent / 237 rel / 272115 triples, Zipf(1.0) entities), "
                         "batch 27212 positives per GPU",
             "global_batch": CFG["batch"] * n_gpus,
-            "parallelism": "dp%d (replicated tables, NCCL all-reduce of gradient tables)" % n_gpus if n_gpus > 1 else "single GPU",
+            "parallelism": ("dp%d, replicated tables, %s" % (n_gpus, dp_mode)) if n_gpus > 1 else "single GPU",
             "l2": "flushed between steps (256 MiB write outside the timed events); per-step CUDA events summed"}
 
 
@@ -170,9 +207,15 @@ def main_ours(args):
     rng = np.random.default_rng(0)
     K = 2 * CFG["k"]
     B, eta = CFG["batch"], CFG["eta"]
-    eng = KGEEngine(CFG["model"], CFG["k"], eta, CFG["n_ent"], CFG["n_rel"], loss=CFG["loss"],
-                    loss_params=CFG["loss_params"], optimizer=CFG["optimizer"],
-                    optimizer_params={"learning_rate": CFG["lr"]}, device=local)
+    from ampligraph_b200.parallel import DataParallelTrainer, batch_slot
+
+    def make_engine(alloc):
+        return KGEEngine(CFG["model"], CFG["k"], eta, CFG["n_ent"], CFG["n_rel"], loss=CFG["loss"],
+                         loss_params=CFG["loss_params"], optimizer=CFG["optimizer"],
+                         optimizer_params={"learning_rate": CFG["lr"]}, device=local, table_alloc=alloc)
+
+    dp = DataParallelTrainer(make_engine, mode=os.environ.get("KGE_B200_DP_MODE", "auto"))
+    eng = dp.eng
     eng.set_embeddings(glorot(CFG["n_ent"], K, rng), glorot(CFG["n_rel"], K, rng))  # same tables on every rank
     data_np = synthetic_kg(CFG["n_ent"], CFG["n_rel"], CFG["n_triples"])
     nb = len(data_np) // B  # full batches only, so every step does identical work
@@ -181,25 +224,30 @@ def main_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def batch_of(i):  # rank r takes batch (i*world + r) of the epoch, sequential like the reference
-        j = (i * world + rank) % nb
+        j = batch_slot(i, world, rank, nb)
         return data[j * B:(j + 1) * B]
 
     def step(i, ev=None):
         b = batch_of(i)
-        if ev: ev[0].record()
-        eng.forward_backward(b, None, seed=1234, step=i)
-        if ev: ev[1].record()
-        if world > 1:
-            dist.all_reduce(eng.g_ent)
-            dist.all_reduce(eng.g_rel)
-        eng.apply_gradients()
-        if ev: ev[2].record()
+        if world == 1:
+            if ev: ev[0].record()
+            eng.forward_backward(b, None, seed=1234, step=i)
+            if ev: ev[1].record()
+            eng.apply_gradients()
+            if ev: ev[2].record()
+        else:
+            if ev: ev[0].record()
+            dp.train_step(b, None, seed=1234, step=i, kernel_done=ev[1] if ev else None)
+            if ev: ev[2].record()
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # ---- warm-up ----
     for i in range(args.warmup):
         step(i)
@@ -207,11 +255,9 @@ def main_ours(args):
 
     # ---- timed: exactly K steps, per-step events, L2 flushed between steps ----
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launches
     sync_all()
+    sampler.samples = []  # keep only samples taken during the timed region
     for i in range(args.steps):
         flush.fill_(i & 0xff)  # evict L2 (126 MB) outside the timed events
         step(args.warmup + i, evs[i])
@@ -267,7 +313,7 @@ def main_ours(args):
         line = {"metric": METRIC, "value": value, "unit": "triples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_step / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(world), "clocks": clocks,
+                "config": workload_config(world, {"p2p": "gradient reduce-scatter + sharded Adam + parameter all-gather fused in one kernel over NVLink peer memory", "nccl": "NCCL all-reduce of gradient tables"}.get(dp.mode, dp.mode)), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": B * 3 * 4, "d2h_bytes_per_step": 8},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -287,8 +333,8 @@ def main_ours(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     a = ap.parse_args()

@@ -169,6 +169,23 @@ int kge_optimizer_step(kge_handle *h, const kge_optimizer_config *opt, int64_t t
                        float *grad_dev, float *slot0_dev, float *slot1_dev, int64_t rows,
                        double *reg_loss_dev, void *stream);
 
+/* Data-parallel variant of kge_optimizer_step FUSED with the gradient exchange over NVLink peer
+ * memory (the reference has no distributed path; SURVEY.md 8e asks for replicated tables + a
+ * gradient all-reduce).  Tables are replicated and every rank holds a full gradient table from its
+ * own batch.  Rank `rank` owns rows [row_begin, row_end): it reads that shard of EVERY rank's
+ * gradient table through peer pointers, sums in rank order, applies the optimizer (slots cover the
+ * shard only: [row_end-row_begin, ld]) and stores the updated rows into EVERY rank's table.
+ *   peer_tables / peer_grads  HOST arrays of `world` device pointers, indexed by rank; entry [rank]
+ *                             is the local buffer, the others are peer-mapped (cudaIpc / VMM /
+ *                             torch symmetric memory) addresses
+ * The caller must (1) order it after all ranks' kge_train_step (cross-rank barrier), (2) put a
+ * second barrier after it before any rank reads a table again, and (3) zero its own gradient
+ * table afterwards.  reg_loss_dev receives this rank's shard of the regulariser loss. */
+int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_config *opt, int64_t t, int32_t world,
+                               int32_t rank, float *const *peer_tables, float *const *peer_grads,
+                               float *slot0_shard_dev, float *slot1_shard_dev, int64_t row_begin,
+                               int64_t row_end, double *reg_loss_dev, void *stream);
+
 /* test_function / get_ranks (ScoringBasedEmbeddingModel.py:1387-1465,
  * layers/scoring/AbstractScoringLayer.py:156-422) for one corruption side.
  *   cand_ids_dev  NULL: candidates are entity rows [cand_begin, cand_begin+n_cand) of

@@ -16,6 +16,8 @@ CFGS = {
     "cfg2u": dict(model="ComplEx", k=200, eta=10, E=14505, R=237, B=27212, loss="self_adversarial", uniform=True),
     "cfg3": dict(model="DistMult", k=400, eta=20, E=40943, R=11, B=8684, loss="pairwise"),
     "cfg4": dict(model="RotatE", k=200, eta=30, E=123182, R=37, B=10791, loss="self_adversarial"),
+    "cfg4c": dict(model="ComplEx", k=200, eta=30, E=123182, R=37, B=10791, loss="self_adversarial"),
+    "cfg5w": dict(model="ComplEx", k=1000, eta=50, E=200000, R=1000, B=8192, loss="self_adversarial", uniform=True),
     "big": dict(model="ComplEx", k=200, eta=10, E=2000000, R=1000, B=65536, loss="self_adversarial", uniform=True),
 }
 
@@ -62,10 +64,17 @@ def run(name, scatter, neg_group=0, iters=20):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or ["cfg2", "cfg2u", "cfg3", "cfg4", "cfg1", "big"]
+    args = sys.argv[1:]
+    if args and args[0] == "one":  # one <cfg> <scatter> <G>   (for ncu)
+        run(args[1], args[2], int(args[3]), iters=5)
+        sys.exit(0)
+    if args and args[0] == "sweep":
+        for n, gs in (("cfg4", (0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3)), ("cfg4c", (0, 15, 13, 11, 10, 9, 8, 7, 6, 5)),
+                      ("cfg3", (0, 13, 11, 10, 9, 7, 5)), ("cfg5w", (0,))):
+            for g in gs:
+                run(n, "red_v4", neg_group=g)
+        sys.exit(0)
+    names = args or ["cfg2", "cfg2u", "cfg3", "cfg4", "cfg1", "big"]
     for n in names:
         for scatter in ("bulk", "red_v4"):
             run(n, scatter)
-        if n in ("cfg2", "cfg4"):
-            run(n, "red_v4", neg_group=5)
-            run(n, "bulk", neg_group=5)

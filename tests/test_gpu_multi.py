@@ -1,0 +1,80 @@
+"""2-GPU tests (run on a box with >= 2 B200s, e.g. `gpurun --gpus 2`): the data-parallel step --
+fused peer-memory optimizer ("p2p") and NCCL all-reduce ("nccl") -- equals the single-GPU step on
+the concatenated global batch; sharded ranking equals full ranking."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+mode = sys.argv[2]
+from ampligraph_b200.engine import KGEEngine
+from ampligraph_b200.parallel import DataParallelTrainer, allreduce_sum_, batch_slot, row_shard
+local = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(0)
+model, E, R, k, eta, B, steps = "ComplEx", 3000, 11, 64, 6, 512, 4
+K = 2 * k
+ent = rng.uniform(-.2, .2, (E, K)).astype(np.float32); rel = rng.uniform(-.2, .2, (R, K)).astype(np.float32)
+data = np.stack([rng.integers(0, E, steps*world*B), rng.integers(0, R, steps*world*B), rng.integers(0, E, steps*world*B)], 1).astype(np.int32)
+neg_ent = rng.integers(0, E, (steps*world, B*eta)).astype(np.int32); neg_keep = rng.integers(0, 2, (steps*world, B*eta)).astype(np.uint8)
+dev = lambda a: torch.as_tensor(a).cuda().contiguous()
+mk = lambda alloc: KGEEngine(model, k, eta, E, R, loss="self_adversarial", optimizer="adam",
+                             optimizer_params={"learning_rate": 1e-2}, device=local, table_alloc=alloc)
+dp = DataParallelTrainer(mk, mode=mode)
+assert dp.mode == mode, (dp.mode, getattr(dp, "p2p_error", None))
+dp.eng.set_embeddings(ent, rel)
+for i in range(steps):
+    j = batch_slot(i, world, rank, steps*world)
+    dp.train_step(dev(data[j*B:(j+1)*B]), (dev(neg_ent[j]), dev(neg_keep[j])))
+torch.cuda.synchronize()
+got_e, got_r = (x.cpu().numpy() for x in dp.eng.get_embeddings())
+# single-GPU run on the concatenated global batches (rank 0 only needs to check; all ranks do)
+ref = KGEEngine(model, k, eta, E, R, loss="self_adversarial", optimizer="adam", optimizer_params={"learning_rate": 1e-2}, device=local)
+ref.set_embeddings(ent, rel)
+for i in range(steps):
+    js = [batch_slot(i, world, r, steps*world) for r in range(world)]
+    t = np.concatenate([data[j*B:(j+1)*B] for j in js])
+    # tile order for the concatenated batch: row jj*Bg + i
+    ne = np.concatenate([neg_ent[j].reshape(eta, B) for j in js], axis=1).reshape(-1)
+    nk = np.concatenate([neg_keep[j].reshape(eta, B) for j in js], axis=1).reshape(-1)
+    ref.train_step(dev(t), (dev(ne), dev(nk)))
+ref_e, ref_r = (x.cpu().numpy() for x in ref.get_embeddings())
+assert np.allclose(got_e, ref_e, rtol=2e-4, atol=2e-6), np.abs(got_e - ref_e).max()
+assert np.allclose(got_r, ref_r, rtol=2e-4, atol=2e-6), np.abs(got_r - ref_r).max()
+# every replica holds the same table
+chk = torch.tensor([float(np.abs(got_e).sum())], device="cuda", dtype=torch.float64)
+lo = chk.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN); hi = chk.clone(); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+assert lo.item() == hi.item()
+# sharded ranking: each rank counts against its row shard, counts are summed
+q = dev(data[:64])
+lo_r, hi_r = row_shard(E, world, rank)
+cnt = ref.rank(q, "o", "worst", cand_begin=lo_r, n_cand=hi_r - lo_r)
+allreduce_sum_([cnt])
+full = ref.rank(q, "o", "worst")
+assert (cnt == full).all()
+dist.destroy_process_group()
+print("rank", rank, mode, "ok")
+'''
+
+
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_data_parallel_step_two_gpus(tmp_path, mode):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29621", str(script), ROOT, mode]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-4000:]
+    assert out.stdout.count(mode + " ok") >= 2

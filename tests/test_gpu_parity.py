@@ -180,6 +180,31 @@ def test_forward_backward_baseline_shapes(model, k, eta, B):
     eng.close()
 
 
+@pytest.mark.parametrize("model,k", [("TransE", 600), ("DistMult", 1100), ("ComplEx", 520), ("HolE", 1000), ("RotatE", 700)])
+@pytest.mark.parametrize("group", [0, 3])
+def test_wide_rows_column_windows(model, k, group):
+    """half-rows wider than 512 floats are processed in column windows (cfg5 has k=1000), with and
+    without negative groups; compared with the oracle."""
+    rng = np.random.default_rng(41)
+    E, R, eta, B = 60, 4, 7, 41
+    loss = "self_adversarial" if model in ("ComplEx", "RotatE") else "nll"
+    ent, rel = _tables(model, E, R, k, rng, scale=0.05)
+    t = _triples(E, R, B, rng)
+    neg_ent, neg_keep = _negatives(E, B, eta, rng)
+    eng = _engine(model, k, eta, E, R, loss=loss, neg_group=group)
+    eng.set_embeddings(ent, rel)
+    sp = torch.empty(B, device="cuda")
+    sn = torch.empty(B * eta, device="cuda")
+    eng.forward_backward(_dev(t), (_dev(neg_ent), _dev(neg_keep)), scores_pos=sp, scores_neg=sn)
+    rs = _ref(model, k, ent, rel, eta, loss, {})
+    rl, rsp, rsn, g_ent, g_rel = rs.loss_and_grads(t, _corruption_tensor(t, neg_ent, neg_keep, eta))
+    assert np.allclose(sp.cpu().numpy(), rsp.numpy(), rtol=RTOL, atol=1e-5)
+    assert np.allclose(sn.cpu().numpy(), rsn.numpy(), rtol=RTOL, atol=1e-5)
+    assert abs(eng.read_loss() - float(rl)) <= RTOL * abs(float(rl)) + 1e-5
+    assert _close(_dense(eng, eng.g_ent), g_ent.numpy()) and _close(_dense(eng, eng.g_rel), g_rel.numpy())
+    eng.close()
+
+
 @pytest.mark.parametrize("model", ["ComplEx", "TransE", "RotatE"])
 @pytest.mark.parametrize("group", [1, 3])
 def test_negative_groups_match_resident(model, group):
@@ -432,7 +457,7 @@ def test_error_convention():
     eng = _engine("TransE", 4, 1, 10, 2)
     with pytest.raises(ValueError):  # invalid corrupt side id
         _lib.check(eng.lib.kge_rank(eng.h, 7, 0, None, None, None, 0, None, 0, 0, None, None, 0, None, None))
-    with pytest.raises(NotImplementedError):  # half-row > 512 floats is not supported by the warp kernel yet
-        big = _engine("TransE", 600, 1, 10, 2)
-        big.forward_backward(_dev(np.zeros((1, 3), np.int32)))
+    with pytest.raises(ValueError):  # gradient buffers are mandatory outside FORWARD_ONLY
+        _lib.check(eng.lib.kge_train_step(eng.h, 0, eng.ent.data_ptr(), eng.rel.data_ptr(), None, None,
+                                          eng.ent.data_ptr(), 1, None, None, 0, 0, None, None, None, None, None, None))
     eng.close()
