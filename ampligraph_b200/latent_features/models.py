@@ -50,6 +50,11 @@ class ScoringBasedEmbeddingModel:
         self._loss_sum, self._loss_cnt = 0.0, 0  # never-reset running Mean metric (loss_functions.py:101,:224)
         self._initial_tables = None
         self._step = 0
+        # set True (under torchrun, after torch.distributed.init_process_group) to train data-parallel over
+        # all ranks -- every global batch is split across ranks -- and to rank against row shards
+        self.distributed = False
+        self._dp = None
+        self.use_focusE = False
 
     # ------------------------------------------------------------------ compile
     def compile(self, optimizer="adam", loss=None, entity_relation_initializer="glorot_uniform",
@@ -80,9 +85,17 @@ class ScoringBasedEmbeddingModel:
     def _build_engine(self):
         name, lp = self.compiled_loss.kernel_params()
         reg = self._regularizer.kernel_params() if self._regularizer is not None else None
-        self.engine = KGEEngine(self.scoring_type, self.k, self.eta, self.max_ent_size, self.max_rel_size,
-                                loss=name or "pairwise", loss_params=lp, optimizer=self.optimizer.name,
-                                optimizer_params=self.optimizer.hyperparams, regularizer=reg, device=self.device)
+        def make_engine(alloc=None):
+            return KGEEngine(self.scoring_type, self.k, self.eta, self.max_ent_size, self.max_rel_size,
+                             loss=name or "pairwise", loss_params=lp, optimizer=self.optimizer.name,
+                             optimizer_params=self.optimizer.hyperparams, regularizer=reg, device=self.device,
+                             table_alloc=alloc)
+        if self._world() > 1:
+            from ..parallel import DataParallelTrainer
+            self._dp = DataParallelTrainer(make_engine)
+            self.engine = self._dp.eng
+        else:
+            self.engine = make_engine()
         dense = [None, None]
         for n, (init, rows) in enumerate(zip(self._initializer, (self.max_ent_size, self.max_rel_size))):
             if isinstance(init, str):
@@ -95,6 +108,14 @@ class ScoringBasedEmbeddingModel:
         self.engine.init_glorot_uniform(self.seed)
         self.engine.set_embeddings(dense[0], dense[1])
         self._step = 0
+
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size() if (self.distributed and dist.is_available() and dist.is_initialized()) else 1
+
+    def _rank(self):
+        import torch.distributed as dist
+        return dist.get_rank() if self._world() > 1 else 0
 
     def _to_dev(self, a, dtype):
         return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).pin_memory().to(self.engine.device, non_blocking=True)
@@ -128,8 +149,19 @@ class ScoringBasedEmbeddingModel:
         self._assert_compile_was_called()
         if partitioning_k != 1:
             raise NotImplementedError("bucket partitioning is replaced by HBM-resident tables (DESIGN.md)")
-        if focusE:
-            raise NotImplementedError("FocusE is outside the hot-path scope of this round (SURVEY.md 8f)")
+        x = np.asarray(x)
+        # FocusE (:342-368, :396-406, :468-543): numeric edge values in columns 3.. re-weight the scores
+        self.use_focusE = bool(focusE) and x.shape[1] > 3
+        if x.shape[1] > 3 and not focusE:
+            print("Data shape is {}: not only triples were given, but focusE is not active!".format(x.shape[1]))
+        if self.use_focusE:
+            assert isinstance(focusE_params, dict), "focusE parameters need to be in a dict!"
+            from .torch_losses import focuse_non_linearity
+            self._focuse_nl = focuse_non_linearity(focusE_params.get("non_linearity", "linear"))
+            self._focuse_stop = focusE_params.get("stop_epoch", 251)
+            assert self._focuse_stop >= 0, "Invalid value for focusE stop_epoch: expected a value >=0 but got {}".format(self._focuse_stop)
+            self._focuse_sw = focusE_params.get("structural_wt", 0.001)
+            assert 0 <= self._focuse_sw <= 1, "Invalid focusE 'structural_wt' passed! It has to belong to [0,1]."
         triples = self._index(x, fit=True)
         if self.data_indexer is not False:
             self.max_ent_size = self.data_indexer.get_entities_count()
@@ -142,13 +174,29 @@ class ScoringBasedEmbeddingModel:
         eng = self.engine
         data = self._to_dev(triples, np.int32)  # uploaded once; batches are device-side slices
         n = data.shape[0]
+        weights = None
+        if self.use_focusE:
+            if len(triples) != len(x):
+                raise ValueError("focusE needs every input triple to be indexable")
+            weights = self._to_dev(np.asarray(x[:, 3:], dtype=np.float32), np.float32)
         batch_size = int(batch_size)
         history = History()
         user_loss = isinstance(self.compiled_loss, loss_functions.LossFunctionWrapper)
+        world, rank = self._world(), self._rank()
+        if world > 1 and (user_loss or self.use_focusE):
+            raise NotImplementedError("user-callable losses / focusE are single-GPU only")
         for epoch in range(initial_epoch, epochs):
+            if self.use_focusE and self._focuse_stop > 0:  # linear decay of the structural weight (:536-543)
+                self._focuse_sw = max(1 - epoch / self._focuse_stop, 0.001)
             for start in range(0, n, batch_size):
                 batch = data[start:start + batch_size]
-                if user_loss:
+                if self.use_focusE:
+                    self._two_phase_step(batch, weights[start:start + batch_size])
+                elif world > 1:  # this rank's slice of the global batch; the step is the global-batch step
+                    from ..parallel import row_shard
+                    lo, hi = row_shard(batch.shape[0], world, rank)
+                    self._dp.train_step(batch[lo:hi], None, seed=self.seed + 7919 * rank, step=self._step)
+                elif user_loss:
                     self._user_loss_step(batch)
                 else:
                     eng.forward_backward(batch, None, seed=self.seed, step=self._step)
@@ -157,6 +205,9 @@ class ScoringBasedEmbeddingModel:
                 self._loss_cnt += 1
             # per-batch losses accumulate on the device; one read-back per epoch (the logged value is
             # the reference's never-reset running mean of per-batch SUM losses)
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(eng.loss_acc)
             self._loss_sum += eng.read_loss()
             logs = {"loss": self._loss_sum / max(self._loss_cnt, 1)}
             validate = (epoch >= (validation_burn_in - 1) and validation_data is not None
@@ -204,7 +255,11 @@ class ScoringBasedEmbeddingModel:
         return loss
 
     def _user_loss_step(self, batch):
-        """LossFunctionWrapper path: scores from the kernel, dL/dscore from torch autograd."""
+        self._two_phase_step(batch, None)
+
+    def _two_phase_step(self, batch, weights):
+        """LossFunctionWrapper / FocusE path: scores from the kernel, dL/dscore from torch autograd
+        over a handful of elementwise ops, gradients from the kernel again."""
         eng, B = self.engine, batch.shape[0]
         neg = eng.generate_corruptions(batch, self.seed, self._step)
         tiled = batch.repeat(self.eta, 1)
@@ -214,7 +269,18 @@ class ScoringBasedEmbeddingModel:
         sn = torch.empty(B * self.eta, dtype=torch.float32, device=eng.device)
         eng.forward_backward(batch, (repl, keep), mode=_lib.STEP_FORWARD_ONLY, scores_pos=sp, scores_neg=sn)
         spg, sng = sp.requires_grad_(True), sn.requires_grad_(True)
-        loss = self.compiled_loss._user_losses(spg, sng.reshape(self.eta, -1)).sum()
+        fp, fn = spg, sng
+        if weights is not None:  # compute_focusE_weights (:342-368) + score re-weighting (:396-406)
+            w = weights.mean(1)
+            sw = self._focuse_sw
+            fp = self._focuse_nl(spg) * (sw + (1 - sw) * (1 - w))
+            fn = self._focuse_nl(sng) * (sw + (1 - sw) * w.repeat(self.eta))
+        if isinstance(self.compiled_loss, loss_functions.LossFunctionWrapper):
+            loss = self.compiled_loss._user_losses(fp, fn.reshape(self.eta, -1)).sum()
+        else:
+            from .torch_losses import per_positive_loss
+            name, lp = self.compiled_loss.kernel_params()
+            loss = per_positive_loss(name, fp, fn.reshape(self.eta, -1), lp).sum()
         loss.backward()
         eng.forward_backward(batch, (repl, keep), mode=_lib.STEP_BACKWARD_EXT, dpos=spg.grad.contiguous(),
                              dneg=sng.grad.contiguous())
@@ -267,7 +333,13 @@ class ScoringBasedEmbeddingModel:
                 if findex is not None:
                     o_np, i_np = findex.lookup(tb, side, position_of)
                     off, idx = self._to_dev(o_np, np.int64), self._to_dev(i_np, np.int32)
-                r = eng.rank(td, side, ranking_strategy, off, idx, cand_ids=cand_ids)
+                if self._world() > 1 and cand_ids is None:  # row-sharded candidates, counts summed over ranks
+                    from ..parallel import allreduce_sum_, row_shard
+                    lo, hi = row_shard(self.max_ent_size, self._world(), self._rank())
+                    r = eng.rank(td, side, ranking_strategy, off, idx, cand_begin=lo, n_cand=hi - lo)
+                    allreduce_sum_([r])
+                else:
+                    r = eng.rank(td, side, ranking_strategy, off, idx, cand_ids=cand_ids)
                 out[start:start + len(tb), j] = r.cpu().numpy()
         if corrupt_side == "s+o":  # :1459-1463 sum BEFORE the +1
             out = out.sum(1, keepdims=True)

@@ -127,3 +127,47 @@ def test_user_callable_loss_and_validation_and_weights(tmp_path):
     m2.load_weights(p)
     assert np.array_equal(m.predict(X[:50]), m2.predict(X[:50]))
     assert (m.evaluate(X[:20], verbose=False) == m2.evaluate(X[:20], verbose=False)).all()
+
+
+@pytest.mark.parametrize("non_linearity", ["linear", "tanh", "softplus"])
+def test_focuse_matches_oracle(non_linearity):
+    """FocusE (ScoringBasedEmbeddingModel.py:342-368, :396-406): numeric edge values re-weight the
+    scores before the loss; replayed with the oracle's scoring/loss restatements + autograd."""
+    from ampligraph_b200.latent_features import ScoringBasedEmbeddingModel, loss_functions
+    from ampligraph_b200.datasets import DataIndexer
+    from oracle import ref_step
+    rng = np.random.default_rng(9)
+    X = _kg(150, 4, 1200, seed=9)
+    vals = rng.uniform(0, 1, (len(X), 1)).round(3)
+    X4 = np.concatenate([X.astype(object), vals.astype(object)], axis=1)
+    ix = DataIndexer(X)
+    E, R, k, eta, bs = ix.get_entities_count(), ix.get_relations_count(), 10, 3, 500
+    ent0 = rng.uniform(-0.3, 0.3, (E, k)).astype(np.float32)
+    rel0 = rng.uniform(-0.3, 0.3, (R, k)).astype(np.float32)
+    m = ScoringBasedEmbeddingModel(eta=eta, k=k, scoring_type="DistMult", seed=3)
+    m.compile(optimizer="adam", loss=loss_functions.get("nll"), entity_relation_initializer=[ent0, rel0])
+    params = {"non_linearity": non_linearity, "stop_epoch": 3, "structural_wt": 0.001}
+    m.fit(X4, batch_size=bs, epochs=2, verbose=False, focusE=True, focusE_params=params)
+    # replay on the CPU
+    rs = ref_step.RefStep("DistMult", k, ent0, rel0, eta, loss="nll", optimizer="adam")
+    nl = {"linear": lambda x: x, "tanh": torch.tanh,
+          "softplus": lambda x: torch.log(1 + 9999 * torch.exp(x))}[non_linearity]
+    t = ix.get_indexes(X)
+    step = 0
+    for epoch in range(2):
+        sw = max(1 - epoch / 3, 0.001)
+        for s0 in range(0, len(t), bs):
+            b = np.ascontiguousarray(t[s0:s0 + bs])
+            w = torch.tensor(vals[s0:s0 + bs, 0], dtype=torch.float32)
+            corr = m.engine.generate_corruptions(torch.as_tensor(b).cuda(), seed=3, step=step).cpu().numpy()
+            for v in (rs.ent, rs.rel):
+                v.grad = None
+            sp, sn = rs.forward(b, corr)
+            fp = nl(sp) * (sw + (1 - sw) * (1 - w))
+            fn = nl(sn) * (sw + (1 - sw) * w.repeat(eta))
+            ref_step.total_loss("nll", fp, fn, eta).backward()
+            with torch.no_grad():
+                rs.opt.step({"ent": (rs.ent, rs.ent.grad), "rel": (rs.rel, rs.rel.grad)})
+            step += 1
+    ent = m.get_embeddings(ix.ent_labels, "e")
+    assert np.allclose(ent, rs.ent.detach().numpy(), rtol=2e-3, atol=5e-5), np.abs(ent - rs.ent.detach().numpy()).max()
