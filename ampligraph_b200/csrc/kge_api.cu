@@ -112,13 +112,20 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     if (cfg->reserved & 1) row_bytes = (row_bytes + 127) / 128 * 128;
     h->slot_floats = row_bytes / 4;
     const int max_warps = KGE_TRAIN_THREADS(cfg->scoring, h->nit) / 32;
-    // prefer everything resident (one gather per row) as long as >= KGE_MIN_RESIDENT_WARPS warps fit;
-    // otherwise shrink G until that many warps fit (the gradient pass then re-gathers the other groups)
+    // Residency policy, tuned on B200 (scripts/kbench.py sweep, profiles/): keep all eta corruptions resident
+    // (one gather per row) while >= KGE_MIN_RESIDENT_WARPS warps still fit; otherwise shrink G until
+    // min(max_warps, KGE_TARGET_WARPS) warps fit -- the gradient pass then re-gathers the other groups, which
+    // costs less than running with few warps.  RotatE is measurably (1.5x) faster with an odd group size.
     int G = cfg->eta;
     if (cfg->neg_group > 0) G = cfg->neg_group < cfg->eta ? cfg->neg_group : cfg->eta;
     else {
-        const int want = max_warps < KGE_MIN_RESIDENT_WARPS ? max_warps : KGE_MIN_RESIDENT_WARPS;
-        while (G > 1 && (long long)((3 + G) * (long long)row_bytes + aux) * want > h->max_smem) --G;
+        const long long full = (3 + (long long)cfg->eta) * row_bytes + aux;
+        const int min_res = max_warps < KGE_MIN_RESIDENT_WARPS ? max_warps : KGE_MIN_RESIDENT_WARPS;
+        if (full * min_res > h->max_smem) {
+            const int want = max_warps < KGE_TARGET_WARPS ? max_warps : KGE_TARGET_WARPS;
+            while (G > 1 && (long long)((3 + G) * (long long)row_bytes + aux) * want > h->max_smem) --G;
+            if (cfg->scoring == KGE_ROTATE && G > 1 && (G % 2) == 0) --G;
+        }
     }
     h->G = G;
     h->rows_bytes = (3 + G) * row_bytes;

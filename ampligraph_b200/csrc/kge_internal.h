@@ -8,6 +8,7 @@
 #define KGE_TRAIN_THREADS(model, nit) ((nit) <= 1 ? 512 : (nit) == 2 ? ((model) == KGE_ROTATE ? 256 : 384) : 256)
 #define KGE_MAX_SMEM_PER_CTA (227 * 1024)
 #define KGE_MIN_RESIDENT_WARPS 8  // tuned on B200: fewer warps/SM than this costs more than re-gathering
+#define KGE_TARGET_WARPS 10
 
 namespace kge {
 
