@@ -37,6 +37,11 @@ class KgeOptimizerConfig(C.Structure):
                 ("initial_accumulator_value", C.c_float), ("reg_p", C.c_int32), ("reg_lambda", C.c_float)]
 
 
+class KgeShardMap(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("world", C.c_int32), ("rows_per_shard", C.c_int64),
+                ("ent", C.c_void_p * 8), ("grad_ent", C.c_void_p * 8)]
+
+
 _P = C.c_void_p
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 PROTOTYPES = {
@@ -54,6 +59,10 @@ PROTOTYPES = {
     "kge_generate_corruptions": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, C.c_uint64, _P, _P]),
     "kge_train_step": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_uint64, C.c_uint64,
                                  _P, _P, _P, _P, _P, _P]),
+    "kge_train_step_sharded": (C.c_int, [_P, C.c_int32, C.POINTER(KgeShardMap), _P, _P, _P, C.c_int64, _P, _P,
+                                         C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P]),
+    "kge_rank_sharded": (C.c_int, [_P, C.POINTER(KgeShardMap), C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64,
+                                   _P, _P, C.c_int64, _P, _P]),
     "kge_optimizer_step": (C.c_int, [_P, C.POINTER(KgeOptimizerConfig), C.c_int64, _P, _P, _P, _P, C.c_int64,
                                      _P, _P]),
     "kge_optimizer_step_sharded": (C.c_int, [_P, C.POINTER(KgeOptimizerConfig), C.c_int64, C.c_int32, C.c_int32,

@@ -221,11 +221,25 @@ extern "C" int kge_generate_corruptions(kge_handle *h, const int32_t *triples_de
     return KGE_OK;
 }
 
-extern "C" int kge_train_step(kge_handle *h, int32_t mode, const float *ent_dev, const float *rel_dev,
-                              float *grad_ent_dev, float *grad_rel_dev, const int32_t *triples_dev, int64_t B,
-                              const int32_t *neg_ent_dev, const uint8_t *neg_keep_subj_dev, uint64_t seed,
-                              uint64_t step, double *loss_dev, float *scores_pos_dev, float *scores_neg_dev,
-                              const float *dpos_dev, const float *dneg_dev, void *stream)
+static int check_shard_map(const kge_handle *h, const kge_shard_map *map, const char *fn)
+{
+    if (!map || map->struct_size != (int32_t)sizeof(kge_shard_map))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "%s: bad kge_shard_map (ABI mismatch)", fn);
+    if (map->world < 1 || map->world > KGE_MAX_PEERS || map->rows_per_shard < 1)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "%s: world must be 1..%d, rows_per_shard >= 1", fn, KGE_MAX_PEERS);
+    if (map->rows_per_shard * (int64_t)map->world < h->cfg.n_ent)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "%s: world*rows_per_shard < n_ent", fn);
+    for (int q = 0; q < map->world; ++q)
+        if (!map->ent[q]) return fail(KGE_ERR_INVALID_ARGUMENT, "%s: null entity shard pointer for rank %d", fn, q);
+    return KGE_OK;
+}
+
+static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map, const float *ent_dev,
+                           const float *rel_dev, float *grad_ent_dev, float *grad_rel_dev,
+                           const int32_t *triples_dev, int64_t B, const int32_t *neg_ent_dev,
+                           const uint8_t *neg_keep_subj_dev, uint64_t seed, uint64_t step, double *loss_dev,
+                           float *scores_pos_dev, float *scores_neg_dev, const float *dpos_dev,
+                           const float *dneg_dev, void *stream)
 {
     KGE_CHECK_HANDLE(h, "kge_train_step");
     if (mode < KGE_STEP_FUSED || mode > KGE_STEP_BACKWARD_EXT)
@@ -285,9 +299,42 @@ extern "C" int kge_train_step(kge_handle *h, int32_t mode, const float *ent_dev,
     p.scores_neg = scores_neg_dev;
     p.dpos = dpos_dev;
     p.dneg = dneg_dev;
+    if (map && map->world > 1) {
+        p.shard_world = map->world;
+        p.rows_per_shard = (int)map->rows_per_shard;
+        for (int q = 0; q < map->world; ++q) { p.ent_shard[q] = map->ent[q]; p.grad_ent_shard[q] = map->grad_ent[q]; }
+    }
     KGE_CUDA(launch_train(p, h->nit, h->sm_count, h->warps * 32, (size_t)h->warps * h->region_bytes, st),
              "kge_train_step");
     return KGE_OK;
+}
+
+extern "C" int kge_train_step(kge_handle *h, int32_t mode, const float *ent_dev, const float *rel_dev,
+                              float *grad_ent_dev, float *grad_rel_dev, const int32_t *triples_dev, int64_t B,
+                              const int32_t *neg_ent_dev, const uint8_t *neg_keep_subj_dev, uint64_t seed,
+                              uint64_t step, double *loss_dev, float *scores_pos_dev, float *scores_neg_dev,
+                              const float *dpos_dev, const float *dneg_dev, void *stream)
+{
+    return train_step_impl(h, mode, nullptr, ent_dev, rel_dev, grad_ent_dev, grad_rel_dev, triples_dev, B, neg_ent_dev,
+                           neg_keep_subj_dev, seed, step, loss_dev, scores_pos_dev, scores_neg_dev, dpos_dev, dneg_dev,
+                           stream);
+}
+
+extern "C" int kge_train_step_sharded(kge_handle *h, int32_t mode, const kge_shard_map *map, const float *rel_dev,
+                                      float *grad_rel_dev, const int32_t *triples_dev, int64_t B,
+                                      const int32_t *neg_ent_dev, const uint8_t *neg_keep_subj_dev, uint64_t seed,
+                                      uint64_t step, double *loss_dev, float *scores_pos_dev,
+                                      float *scores_neg_dev, const float *dpos_dev, const float *dneg_dev,
+                                      void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_train_step_sharded");
+    if (int rc = check_shard_map(h, map, "kge_train_step_sharded")) return rc;
+    if (mode != KGE_STEP_FORWARD_ONLY)
+        for (int q = 0; q < map->world; ++q)
+            if (!map->grad_ent[q]) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_train_step_sharded: null gradient shard pointer for rank %d", q);
+    return train_step_impl(h, mode, map, map->ent[0], rel_dev, map->grad_ent[0], grad_rel_dev, triples_dev, B,
+                           neg_ent_dev, neg_keep_subj_dev, seed, step, loss_dev, scores_pos_dev, scores_neg_dev,
+                           dpos_dev, dneg_dev, stream);
 }
 
 extern "C" int kge_optimizer_step(kge_handle *h, const kge_optimizer_config *opt, int64_t t, float *table_dev,
@@ -376,10 +423,10 @@ extern "C" int64_t kge_rank_workspace_bytes(const kge_handle *h, int64_t b)
     return (int64_t)(3 * b * h->L.ld * sizeof(float) + 4 * b * sizeof(int32_t));
 }
 
-extern "C" int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const float *ent_dev, const float *rel_dev,
-                        const int32_t *triples_dev, int64_t b, const int32_t *cand_ids_dev, int64_t cand_begin,
-                        int64_t n_cand, const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
-                        int32_t *ranks_dev, void *stream)
+static int rank_impl(kge_handle *h, const kge_shard_map *map, int64_t filt_base, int32_t side, int32_t strategy,
+                     const float *ent_dev, const float *rel_dev, const int32_t *triples_dev, int64_t b,
+                     const int32_t *cand_ids_dev, int64_t cand_begin, int64_t n_cand, const int64_t *filt_off_dev,
+                     const int32_t *filt_idx_dev, int64_t n_filt, int32_t *ranks_dev, void *stream)
 {
     KGE_CHECK_HANDLE(h, "kge_rank");
     if (side != KGE_SIDE_S && side != KGE_SIDE_O) return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for corrupt_side");
@@ -389,7 +436,7 @@ extern "C" int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const flo
     if (b == 0) return KGE_OK;
     if (!ent_dev || !rel_dev || !triples_dev || !ranks_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: null pointer");
     if (cand_ids_dev && cand_begin != 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: cand_begin must be 0 with cand_ids_dev");
-    if (!cand_ids_dev && cand_begin + n_cand > h->cfg.n_ent)
+    if (!map && !cand_ids_dev && cand_begin + n_cand > h->cfg.n_ent)
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: candidate range [%lld,%lld) exceeds n_ent %lld",
                     (long long)cand_begin, (long long)(cand_begin + n_cand), (long long)h->cfg.n_ent);
     if ((filt_off_dev == nullptr) != (filt_idx_dev == nullptr) && n_filt > 0)
@@ -407,7 +454,14 @@ extern "C" int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const flo
     float *qs = h->ws_q, *qo = qs + (size_t)b * h->L.ld, *qaux = qo + (size_t)b * h->L.ld;
     int32_t *qpos = h->ws_i, *cnt = qpos + b;
     if (int rc = refresh_rotation(h, rel_dev, st)) return rc;
-    KGE_CUDA(launch_rank_prepare(h->L, ent_dev, rel_dev, h->rot, triples_dev, b, h->score_scale, qs, qo, qaux, qpos, st),
+    ShardView sv;
+    memset(&sv, 0, sizeof(sv));
+    if (map && map->world > 1) {
+        sv.world = map->world;
+        sv.rows_per_shard = (int)map->rows_per_shard;
+        for (int q = 0; q < map->world; ++q) sv.ent[q] = map->ent[q];
+    }
+    KGE_CUDA(launch_rank_prepare(h->L, sv, ent_dev, rel_dev, h->rot, triples_dev, b, h->score_scale, qs, qo, qaux, qpos, st),
              "kge_rank: prepare");
     KGE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)3 * b * sizeof(int32_t), st), "kge_rank: memset");
     RankParams p;
@@ -424,9 +478,35 @@ extern "C" int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const flo
     p.n_cand = n_cand;
     p.b = b;
     p.scale = h->score_scale;
+    p.filt_base = filt_base;
     KGE_CUDA(launch_rank_count(p, cnt, st), "kge_rank: count");
     if (filt_off_dev && n_filt > 0)
         KGE_CUDA(launch_rank_filter_n(p, (const long long *)filt_off_dev, filt_idx_dev, n_filt, cnt, st), "kge_rank: filter");
     KGE_CUDA(launch_rank_finalize(cnt, b, strategy, ranks_dev, st), "kge_rank: finalize");
     return KGE_OK;
+}
+
+extern "C" int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const float *ent_dev, const float *rel_dev,
+                        const int32_t *triples_dev, int64_t b, const int32_t *cand_ids_dev, int64_t cand_begin,
+                        int64_t n_cand, const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
+                        int32_t *ranks_dev, void *stream)
+{
+    return rank_impl(h, nullptr, 0, side, strategy, ent_dev, rel_dev, triples_dev, b, cand_ids_dev, cand_begin, n_cand,
+                     filt_off_dev, filt_idx_dev, n_filt, ranks_dev, stream);
+}
+
+extern "C" int kge_rank_sharded(kge_handle *h, const kge_shard_map *map, int32_t rank, int32_t side, int32_t strategy,
+                                const float *rel_dev, const int32_t *triples_dev, int64_t b,
+                                const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
+                                int32_t *ranks_dev, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_rank_sharded");
+    if (int rc = check_shard_map(h, map, "kge_rank_sharded")) return rc;
+    if (rank < 0 || rank >= map->world) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank_sharded: rank out of range");
+    const int64_t first = (int64_t)rank * map->rows_per_shard;
+    int64_t n_local = h->cfg.n_ent - first;
+    if (n_local > map->rows_per_shard) n_local = map->rows_per_shard;
+    if (n_local < 0) n_local = 0;
+    return rank_impl(h, map, first, side, strategy, map->ent[rank], rel_dev, triples_dev, b, nullptr, 0, n_local,
+                     filt_off_dev, filt_idx_dev, n_filt, ranks_dev, stream);
 }

@@ -7,6 +7,7 @@
 // (RotatE carries 11 float4 vectors of per-positive state per chunk: give it more registers)
 #define KGE_TRAIN_THREADS(model, nit) ((nit) <= 1 ? 512 : (nit) == 2 ? ((model) == KGE_ROTATE ? 256 : 384) : 256)
 #define KGE_MAX_SMEM_PER_CTA (227 * 1024)
+#define KGE_MAX_PEERS 8
 #define KGE_MIN_RESIDENT_WARPS 8  // tuned on B200: fewer warps/SM than this costs more than re-gathering
 #define KGE_TARGET_WARPS 10
 
@@ -35,6 +36,10 @@ struct TrainParams {
     double *loss_out;
     float *scores_pos, *scores_neg;
     const float *dpos, *dneg;
+    // row-sharded entity table (shard_world <= 1: single table at ent / grad_ent)
+    int shard_world, rows_per_shard;
+    const float *ent_shard[KGE_MAX_PEERS];
+    float *grad_ent_shard[KGE_MAX_PEERS];
 };
 
 // grid = min(occupancy * sm_count, ceil(B / warps))
@@ -61,13 +66,16 @@ struct OptimParams {
 cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
                              long long n_floats, double *reg_loss, int sm_count, cudaStream_t st);
 cudaError_t launch_fill(float *p, long long n, float v, cudaStream_t st);
-#define KGE_MAX_PEERS 8
 // tables/grads: HOST arrays of `world` device pointers (own rank first is NOT required; index = rank)
 cudaError_t launch_optimizer_sharded(const OptimParams &o, int world, int rank, float *const *tables, float *const *grads,
                                      float *slot0, float *slot1, long long off_floats, long long n_floats,
                                      double *reg_loss, int sm_count, cudaStream_t st);
 
 // kge_rank.cu
+struct ShardView {  // row-sharded entity table seen through peer pointers (world <= 1: not sharded)
+    int world, rows_per_shard;
+    const float *ent[KGE_MAX_PEERS];
+};
 struct RankParams {
     Layout L;
     int side, strategy;
@@ -77,9 +85,10 @@ struct RankParams {
     const int32_t *qpos;   // [b] quantised positive scores
     const int32_t *cand_ids;  // nullptr or [n_cand]
     long long cand_begin, n_cand, b;
+    long long filt_base;   // subtracted from filter ids (global id of the local shard's first row)
     float scale;           // HolE
 };
-cudaError_t launch_rank_prepare(const Layout &L, const float *ent, const float *rel, const float *rot,
+cudaError_t launch_rank_prepare(const Layout &L, const ShardView &sv, const float *ent, const float *rel, const float *rot,
                                 const int32_t *triples, long long b, float scale, float *qvec_s, float *qvec_o,
                                 float *qaux, int32_t *qpos, cudaStream_t st);
 // cnt = [b,3] int32 workspace: #(qpos < qc), #(qpos == qc), #filtered

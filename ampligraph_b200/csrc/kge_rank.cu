@@ -62,7 +62,14 @@ __device__ __forceinline__ float rank_finish(float acc, float scale)
 // --------------------------------------------------------------------------
 // prepare: per-query vectors for both sides + quantised positive score
 // --------------------------------------------------------------------------
-__global__ void kge_rank_qvec_kernel(int model, const float *__restrict__ ent, const float *__restrict__ rel,
+__device__ __forceinline__ const float *shard_row(const ShardView &v, const float *ent, int id, int ld)
+{
+    if (v.world <= 1) return ent + (size_t)id * ld;
+    const int q = id / v.rows_per_shard;
+    return v.ent[q] + (size_t)(id - q * v.rows_per_shard) * ld;
+}
+
+__global__ void kge_rank_qvec_kernel(int model, const ShardView sv, const float *__restrict__ ent, const float *__restrict__ rel,
                                      const float *__restrict__ rot, const int32_t *__restrict__ triples, long long b,
                                      int kp, int ld, float *__restrict__ qs, float *__restrict__ qo,
                                      float *__restrict__ qaux)
@@ -72,8 +79,8 @@ __global__ void kge_rank_qvec_kernel(int model, const float *__restrict__ ent, c
     if (idx >= b * kp) return;
     long long i = idx / kp;
     int d = (int)(idx - i * kp);
-    const float *s = ent + (size_t)triples[3 * i] * ld;
-    const float *o = ent + (size_t)triples[3 * i + 2] * ld;
+    const float *s = shard_row(sv, ent, triples[3 * i], ld);
+    const float *o = shard_row(sv, ent, triples[3 * i + 2], ld);
     const size_t prow = (size_t)triples[3 * i + 1] * ld;
     float *os = qs + i * ld, *oo = qo + i * ld;
     if (halves == 1) {
@@ -96,14 +103,14 @@ __global__ void kge_rank_qvec_kernel(int model, const float *__restrict__ ent, c
 }
 
 // positive score, canonical order (one thread per query; b is small)
-__global__ void kge_rank_qpos_kernel(int model, const float *__restrict__ ent, const float *__restrict__ rel,
+__global__ void kge_rank_qpos_kernel(int model, const ShardView sv, const float *__restrict__ ent, const float *__restrict__ rel,
                                      const float *__restrict__ rot, const int32_t *__restrict__ triples, long long b,
                                      int kp, int ld, float scale, int32_t *__restrict__ qpos)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b) return;
-    const float *s = ent + (size_t)triples[3 * i] * ld;
-    const float *o = ent + (size_t)triples[3 * i + 2] * ld;
+    const float *s = shard_row(sv, ent, triples[3 * i], ld);
+    const float *o = shard_row(sv, ent, triples[3 * i + 2], ld);
     const size_t prow = (size_t)triples[3 * i + 1] * ld;
     float acc = 0.f, score;
     if (model == KGE_TRANSE) {
@@ -129,15 +136,15 @@ __global__ void kge_rank_qpos_kernel(int model, const float *__restrict__ ent, c
     qpos[i] = quantise(score);
 }
 
-cudaError_t launch_rank_prepare(const Layout &L, const float *ent, const float *rel, const float *rot,
+cudaError_t launch_rank_prepare(const Layout &L, const ShardView &sv, const float *ent, const float *rel, const float *rot,
                                 const int32_t *triples, long long b, float scale, float *qvec_s, float *qvec_o,
                                 float *qaux, int32_t *qpos, cudaStream_t st)
 {
     if (b == 0) return cudaSuccess;
     long long n = b * L.kp;
-    kge_rank_qvec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.model, ent, rel, rot, triples, b, L.kp, L.ld,
+    kge_rank_qvec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.model, sv, ent, rel, rot, triples, b, L.kp, L.ld,
                                                                        qvec_s, qvec_o, qaux);
-    kge_rank_qpos_kernel<<<(unsigned)((b + 127) / 128), 128, 0, st>>>(L.model, ent, rel, rot, triples, b, L.kp, L.ld,
+    kge_rank_qpos_kernel<<<(unsigned)((b + 127) / 128), 128, 0, st>>>(L.model, sv, ent, rel, rot, triples, b, L.kp, L.ld,
                                                                       scale, qpos);
     return cudaGetLastError();
 }
@@ -343,7 +350,7 @@ __global__ void kge_rank_filter_kernel(const RankParams p, const long long *__re
         if (off[mid] <= f) lo = mid; else hi = mid;
     }
     const long long i = lo;
-    const long long pos = idx[f];
+    const long long pos = (long long)idx[f] - p.filt_base;  // filter ids are global; the shard's table is local
     if (pos < p.cand_begin || pos >= p.cand_begin + p.n_cand) return;  // :280-288
     const long long id = p.cand_ids ? (long long)p.cand_ids[pos] : pos;
     const float *e = p.ent + (size_t)id * p.L.ld;

@@ -664,6 +664,22 @@ __device__ __forceinline__ void for_each_pair_by_side(const int *nside, int gs, 
 // are: columns are processed window by window (scores add up over windows), negatives group by
 // group.  With one window and one group (the common case: cfg2/cfg3) every row is gathered once
 // and stays resident for the gradient pass.
+// Row-sharded tables: entity id e lives on rank e / rows_per_shard at local row
+// e % rows_per_shard; every shard is peer-mapped, so the SAME bulk gathers and red.v4 scatters reach
+// remote shards through NVLink -- the row all-to-all is fused into the kernel.
+__device__ __forceinline__ const float *ent_row(const TrainParams &p, int id)
+{
+    if (p.shard_world <= 1) return p.ent + (size_t)id * p.ld;
+    const int q = id / p.rows_per_shard;
+    return p.ent_shard[q] + (size_t)(id - q * p.rows_per_shard) * p.ld;
+}
+__device__ __forceinline__ float *gent_row(const TrainParams &p, int id)
+{
+    if (p.shard_world <= 1) return p.grad_ent + (size_t)id * p.ld;
+    const int q = id / p.rows_per_shard;
+    return p.grad_ent_shard[q] + (size_t)(id - q * p.rows_per_shard) * p.ld;
+}
+
 // RESIDENT = one window and one group (decided on the host): the window/group machinery folds away.
 template <int MODEL, int NIT, class Sink, bool RESIDENT>
 __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kernel(const TrainParams p)
@@ -736,9 +752,9 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
             if (!resident) sc[j] = 0.f;
         }
         __syncwarp();
-        auto spo_src = [&](int r) { return r == 0 ? p.ent + (size_t)s_id * ld : r == 1 ? p.rel + (size_t)p_id * ld : p.ent + (size_t)o_id * ld; };
-        float *const gs_row = p.grad_ent + (size_t)s_id * ld, *const gp_row = p.grad_rel + (size_t)p_id * ld,
-                     *const go_row = p.grad_ent + (size_t)o_id * ld;
+        auto spo_src = [&](int r) { return r == 0 ? ent_row(p, s_id) : r == 1 ? p.rel + (size_t)p_id * ld : ent_row(p, o_id); };
+        float *const gs_row = gent_row(p, s_id), *const gp_row = p.grad_rel + (size_t)p_id * ld,
+                     *const go_row = gent_row(p, o_id);
 
         Scorer<MODEL, NIT> S;
         if constexpr (HALVES == 2) { S.kp = kp; S.hs = wk; }
@@ -751,10 +767,10 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                 const int j0 = g * G, gsz = min(G, eta - j0);
                 __syncwarp();
                 if (g == 0) {  // s, p, o windows + first group in one transaction
-                    gather(rows, 3 + gsz, cb, [&](int r) { return r < 3 ? spo_src(r) : p.ent + (size_t)nid[r - 3] * ld; });
+                    gather(rows, 3 + gsz, cb, [&](int r) { return r < 3 ? spo_src(r) : ent_row(p, nid[r - 3]); });
                     P += warp_sum(S.prep(srow, prow, orow, lane));
                 } else {
-                    gather(nrows, gsz, cb, [&](int r) { return p.ent + (size_t)nid[j0 + r] * ld; });
+                    gather(nrows, gsz, cb, [&](int r) { return ent_row(p, nid[j0 + r]); });
                 }
                 auto store = [&](int a, int b, bool has_b, float pa, float pb) {
                     if (lane == 0) {
@@ -809,27 +825,27 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                     if (!Sink::kDirect) bulk_wait_read_all();  // copy engine done reading what we overwrite
                     __syncwarp();
                     if (g == n_groups - 1) {  // first visit of this window: s, p, o come along and state is rebuilt
-                        gather(rows, 3 + gsz, cb, [&](int r) { return r < 3 ? spo_src(r) : p.ent + (size_t)nid[j0 + r - 3] * ld; });
+                        gather(rows, 3 + gsz, cb, [&](int r) { return r < 3 ? spo_src(r) : ent_row(p, nid[j0 + r - 3]); });
                         (void)S.prep(srow, prow, orow, lane);
                     } else {
-                        gather(nrows, gsz, cb, [&](int r) { return p.ent + (size_t)nid[j0 + r] * ld; });
+                        gather(nrows, gsz, cb, [&](int r) { return ent_row(p, nid[j0 + r]); });
                     }
                 }
                 for_each_pair_by_side(
                     nside + j0, gsz, lane,
                     [&](int a, int b, bool has_b) {
                         S.template grad2<0, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw,
-                                                  p.grad_ent + (size_t)nid[j0 + a] * ld + gofs,
-                                                  p.grad_ent + (size_t)nid[j0 + b] * ld + gofs, scale * sc[j0 + a],
+                                                  gent_row(p, nid[j0 + a]) + gofs,
+                                                  gent_row(p, nid[j0 + b]) + gofs, scale * sc[j0 + a],
                                                   has_b ? scale * sc[j0 + b] : 0.f, has_b);
                     },
                     [&](int a, int b, bool has_b) {
                         S.template grad2<1, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw,
-                                                  p.grad_ent + (size_t)nid[j0 + a] * ld + gofs,
-                                                  p.grad_ent + (size_t)nid[j0 + b] * ld + gofs, scale * sc[j0 + a],
+                                                  gent_row(p, nid[j0 + a]) + gofs,
+                                                  gent_row(p, nid[j0 + b]) + gofs, scale * sc[j0 + a],
                                                   has_b ? scale * sc[j0 + b] : 0.f, has_b);
                     });
-                if (!Sink::kDirect) scatter(nrows, gsz, cb, [&](int r) { return p.grad_ent + (size_t)nid[j0 + r] * ld; });
+                if (!Sink::kDirect) scatter(nrows, gsz, cb, [&](int r) { return gent_row(p, nid[j0 + r]); });
             }
             S.template finish<Sink>(srow, prow, orow, gs_row + gofs, gp_row + gofs, go_row + gofs, scale * dP, p.inv_div);
             if (!Sink::kDirect) scatter(rows, 3, cb, [&](int r) { return r == 0 ? gs_row : r == 1 ? gp_row : go_row; });

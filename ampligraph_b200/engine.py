@@ -23,7 +23,7 @@ def _ptr(t):
 class KGEEngine:
     def __init__(self, scoring_type, k, eta, n_ent, n_rel, loss="pairwise", loss_params=None,
                  optimizer="adam", optimizer_params=None, regularizer=None, device=0, neg_group=0,
-                 scatter=None, table_alloc=None):
+                 scatter=None, table_alloc=None, ent_rows=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("ampligraph_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -38,6 +38,8 @@ class KGEEngine:
         default_margin = 3.0 if loss == "self_adversarial" else 1.0  # loss_functions.py:23,:29
         self.scoring_type, self.k, self.eta = scoring_type, int(k), int(eta)
         self.n_ent, self.n_rel = int(n_ent), int(n_rel)
+        # rows of the LOCAL entity table: n_ent, or one row shard of it (parallel.ShardedTrainer)
+        self.ent_rows = int(ent_rows) if ent_rows is not None else self.n_ent
         self.device = torch.device("cuda", device)
         cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), _lib.SCORING[scoring_type], int(k), int(eta), int(n_ent),
                              int(n_rel), _lib.LOSSES[loss], _lib.REDUCTIONS[reduction],
@@ -53,12 +55,12 @@ class KGEEngine:
         with torch.cuda.device(self.device):
             z = lambda rows: torch.zeros((rows, self.ld), dtype=torch.float32, device=self.device)
             if table_alloc is not None:  # e.g. symmetric (peer-mappable) memory for the multi-GPU path
-                self.ent, self.rel, self.g_ent, self.g_rel = table_alloc(self.n_ent, self.n_rel, self.ld, self.device)
+                self.ent, self.rel, self.g_ent, self.g_rel = table_alloc(self.ent_rows, self.n_rel, self.ld, self.device)
                 for t_ in (self.ent, self.rel, self.g_ent, self.g_rel):
                     assert t_.is_contiguous() and t_.dtype == torch.float32
             else:
-                self.ent, self.rel = z(self.n_ent), z(self.n_rel)
-                self.g_ent, self.g_rel = z(self.n_ent), z(self.n_rel)
+                self.ent, self.rel = z(self.ent_rows), z(self.n_rel)
+                self.g_ent, self.g_rel = z(self.ent_rows), z(self.n_rel)
             self.loss_acc = torch.zeros(2, dtype=torch.float64, device=self.device)  # [batch loss, reg loss]
         self.set_optimizer(optimizer, optimizer_params, regularizer)
         self.launches = 0  # kernels launched by this engine (bench.py reports it)
@@ -95,20 +97,20 @@ class KGEEngine:
         mk = lambda rows, v=0.0: torch.full((rows, self.ld), v, dtype=torch.float32, device=self.device)
         self.slots = {"ent": [None, None], "rel": [None, None]}
         if name == "adam":
-            for key, rows in (("ent", self.n_ent), ("rel", self.n_rel)):
+            for key, rows in (("ent", self.ent_rows), ("rel", self.n_rel)):
                 self.slots[key] = [mk(rows), mk(rows)]
         elif name == "adagrad":
-            for key, rows in (("ent", self.n_ent), ("rel", self.n_rel)):
+            for key, rows in (("ent", self.ent_rows), ("rel", self.n_rel)):
                 acc = mk(rows, self.opt_cfg.initial_accumulator_value)
                 self.slots[key] = [acc, None]
         elif self.opt_cfg.momentum != 0.0:
-            for key, rows in (("ent", self.n_ent), ("rel", self.n_rel)):
+            for key, rows in (("ent", self.ent_rows), ("rel", self.n_rel)):
                 self.slots[key] = [mk(rows), None]
 
     # -- tables ------------------------------------------------------------
     def set_embeddings(self, ent_dense=None, rel_dense=None):
         """dense [rows, internal_k] (numpy / torch) -> padded device layout."""
-        for dense, table, rows in ((ent_dense, self.ent, self.n_ent), (rel_dense, self.rel, self.n_rel)):
+        for dense, table, rows in ((ent_dense, self.ent, self.ent_rows), (rel_dense, self.rel, self.n_rel)):
             if dense is None:
                 continue
             d = torch.as_tensor(np.ascontiguousarray(dense, dtype=np.float32) if not torch.is_tensor(dense) else dense)
@@ -120,14 +122,14 @@ class KGEEngine:
 
     def get_embeddings(self):
         out = []
-        for table, rows in ((self.ent, self.n_ent), (self.rel, self.n_rel)):
+        for table, rows in ((self.ent, self.ent_rows), (self.rel, self.n_rel)):
             d = torch.empty((rows, self.internal_k), dtype=torch.float32, device=self.device)
             _lib.check(self.lib.kge_unpack_rows(self.h, _ptr(table), _ptr(d), rows, self._stream()))
             out.append(d)
         return out[0], out[1]
 
     def init_glorot_uniform(self, seed=0):
-        _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.ent), self.n_ent, int(seed) * 2 + 0, self._stream()))
+        _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.ent), self.ent_rows, int(seed) * 2 + 0, self._stream()))
         _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.rel), self.n_rel, int(seed) * 2 + 1, self._stream()))
 
     # -- training ------------------------------------------------------------
@@ -150,7 +152,7 @@ class KGEEngine:
     def apply_gradients(self):
         """optimizer.apply_gradients on both tables (dense semantics) + LP regulariser."""
         self.t += 1
-        for key, table, grad, rows in (("ent", self.ent, self.g_ent, self.n_ent),
+        for key, table, grad, rows in (("ent", self.ent, self.g_ent, self.ent_rows),
                                        ("rel", self.rel, self.g_rel, self.n_rel)):
             s0, s1 = self.slots[key]
             _lib.check(self.lib.kge_optimizer_step(

@@ -242,7 +242,9 @@ class ScoringBasedEmbeddingModel:
                 self.max_rel_size = self.data_indexer.get_relations_count()
             self._build_engine()
         batch = host.to(self.engine.device, non_blocking=True)
-        if isinstance(self.compiled_loss, loss_functions.LossFunctionWrapper):
+        if self._world() > 1:  # this rank's share of the global batch; gradients are exchanged inside the step
+            self._dp.train_step(batch, None, seed=self.seed + 7919 * self._rank(), step=self._step)
+        elif isinstance(self.compiled_loss, loss_functions.LossFunctionWrapper):
             self._user_loss_step(batch)
         else:
             self.engine.forward_backward(batch, None, seed=self.seed, step=self._step)

@@ -130,3 +130,117 @@ class DataParallelTrainer:
 
     def close(self):
         self.eng.close()
+
+
+class ShardedTrainer:
+    """Row-sharded entity table (BASELINE configs[3],[4]: tables too large for one GPU).
+
+    Rank r owns entity rows [r*rps, (r+1)*rps) -- table, gradient accumulator and optimizer slots --
+    in torch symmetric memory; relations are replicated.  One step of the reference's train_step on
+    the GLOBAL batch (each rank feeds its own slice):
+      1. kge_train_step_sharded: the fused kernel gathers the rows it needs from whichever rank owns
+         them and scatter-adds gradient rows back, all over NVLink peer memory (the forward row
+         all-to-all and backward gradient all-to-all of SURVEY.md 8e, fused into the kernel);
+      2. barrier; each rank runs the DENSE optimizer on its own shard (no exchange), and the
+         replicated relation table goes through kge_optimizer_step_sharded (peer reduce + all-gather);
+      3. barrier.
+    """
+
+    def __init__(self, scoring_type, k, eta, n_ent, n_rel, device, group=None, **engine_kw):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        from .engine import KGEEngine
+        self._C, self._lib = C, _lib
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_ent, self.n_rel = int(n_ent), int(n_rel)
+        self.rps = (self.n_ent + self.world - 1) // self.world
+        self.first = self.rank * self.rps
+        self.n_local = max(0, min(self.rps, self.n_ent - self.first))
+
+        def alloc(rows, n_rel_, ld, dev):
+            assert rows == self.rps
+            total = 2 * rows + 2 * n_rel_
+            self._buf = symm_mem.empty((total, ld), dtype=torch.float32, device=dev)
+            self._buf.zero_()
+            pg = group if group is not None else dist.group.WORLD
+            self.hdl = symm_mem.rendezvous(self._buf, pg.group_name)
+            self._off = {"ent": 0, "g_ent": rows, "rel": 2 * rows, "g_rel": 2 * rows + n_rel_}
+            b = self._buf
+            return b[0:rows], b[2 * rows:2 * rows + n_rel_], b[rows:2 * rows], b[2 * rows + n_rel_:total]
+
+        self.eng = KGEEngine(scoring_type, k, eta, n_ent, n_rel, device=device, table_alloc=alloc, ent_rows=self.rps,
+                             **engine_kw)
+        eng, ld = self.eng, self.eng.ld
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        ptr = lambda q, key: base[q] + self._off[key] * ld * 4
+        self.map = _lib.KgeShardMap(C.sizeof(_lib.KgeShardMap), self.world, self.rps)
+        for q in range(self.world):
+            self.map.ent[q] = ptr(q, "ent")
+            self.map.grad_ent[q] = ptr(q, "g_ent")
+        self._rel_ptrs = (C.c_void_p * self.world)(*[ptr(q, "rel") for q in range(self.world)])
+        self._grel_ptrs = (C.c_void_p * self.world)(*[ptr(q, "g_rel") for q in range(self.world)])
+        self.rel_shard = row_shard(self.n_rel, self.world, self.rank)
+        lo, hi = self.rel_shard
+        eng.slots["rel"] = [None if s is None else s[lo:hi].clone() for s in eng.slots["rel"]]
+        torch.cuda.synchronize()
+        self.hdl.barrier(channel=0)
+
+    def set_embeddings(self, ent_dense=None, rel_dense=None):
+        """dense GLOBAL tables (numpy, identical on every rank): each rank keeps its row slice."""
+        import numpy as np
+        if ent_dense is not None:
+            loc = np.zeros((self.rps, ent_dense.shape[1]), np.float32)
+            loc[:self.n_local] = ent_dense[self.first:self.first + self.n_local]
+            self.eng.set_embeddings(loc, None)
+        if rel_dense is not None:
+            self.eng.set_embeddings(None, rel_dense)
+        torch.cuda.synchronize()
+        self.hdl.barrier(channel=0)
+
+    def get_embeddings(self):
+        """-> (global entity table [n_ent, K] gathered from all shards, relation table), torch cpu."""
+        ent, rel = self.eng.get_embeddings()
+        parts = [torch.empty_like(ent) for _ in range(self.world)]
+        dist.all_gather(parts, ent.contiguous(), group=self.group)
+        return torch.cat(parts)[:self.n_ent].cpu(), rel.cpu()
+
+    def train_step(self, batch, negatives=None, seed=0, step=0):
+        C, _lib, eng = self._C, self._lib, self.eng
+        B = batch.shape[0]
+        neg_ent = neg_keep = None
+        if negatives is not None:
+            neg_ent, neg_keep = negatives
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        st = eng._stream()
+        _lib.check(eng.lib.kge_train_step_sharded(
+            eng.h, _lib.STEP_FUSED, C.byref(self.map), p(eng.rel), p(eng.g_rel), p(batch), B, p(neg_ent), p(neg_keep),
+            int(seed), int(step), p(eng.loss_acc), None, None, None, None, st))
+        self.hdl.barrier(channel=0)  # every rank's scatters (into my shard too) and relation gradients are complete
+        eng.t += 1
+        s0, s1 = eng.slots["ent"]
+        _lib.check(eng.lib.kge_optimizer_step(eng.h, C.byref(eng.opt_cfg), eng.t, p(eng.ent), p(eng.g_ent), p(s0), p(s1),
+                                              self.rps, C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
+        lo, hi = self.rel_shard
+        r0, r1 = eng.slots["rel"]
+        _lib.check(eng.lib.kge_optimizer_step_sharded(
+            eng.h, C.byref(eng.opt_cfg), eng.t, self.world, self.rank, self._rel_ptrs, self._grel_ptrs, p(r0), p(r1),
+            lo, hi, C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
+        self.hdl.barrier(channel=1)  # all shards updated, relation rows delivered, my relation gradients consumed
+        eng.g_rel.zero_()
+        eng.launches += 4
+
+    def rank(self, triples, side, strategy="worst", filt_off=None, filt_idx=None):
+        """full-table rank counts: each rank counts against its shard, int32 counts are summed."""
+        C, _lib, eng = self._C, self._lib, self.eng
+        b = triples.shape[0]
+        out = torch.zeros(b, dtype=torch.int32, device=eng.device)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        n_filt = int(filt_idx.numel()) if filt_idx is not None else 0
+        _lib.check(eng.lib.kge_rank_sharded(eng.h, C.byref(self.map), self.rank, _lib.SIDES[side], _lib.STRATEGIES[strategy],
+                                            p(eng.rel), p(triples), b, p(filt_off), p(filt_idx), n_filt, p(out), eng._stream()))
+        return allreduce_sum_([out], self.group)[0]
+
+    def close(self):
+        self.eng.close()

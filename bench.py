@@ -278,6 +278,7 @@ def main_ours(args):
     model = ScoringBasedEmbeddingModel(eta=eta, k=CFG["k"], scoring_type=CFG["model"], seed=0,
                                        max_ent_size=CFG["n_ent"], max_rel_size=CFG["n_rel"])
     model.device = local
+    model.distributed = world > 1  # N>1: the same data-parallel step (gradient exchange included) as above
     model.data_indexer = False  # synthetic ids are already indexed
     from ampligraph_b200.latent_features import loss_functions, optimizers
     model.compile(optimizer=optimizers.get("adam", {"learning_rate": CFG["lr"]}),

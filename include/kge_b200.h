@@ -158,6 +158,31 @@ int kge_train_step(kge_handle *h, int32_t mode, const float *ent_dev, const floa
                    uint64_t step, double *loss_dev, float *scores_pos_dev, float *scores_neg_dev,
                    const float *dpos_dev, const float *dneg_dev, void *stream);
 
+/* Row-sharded entity table (BASELINE configs[3],[4]: |E|*k too large for one GPU).
+ * Entity id e lives on rank e / rows_per_shard at local row e % rows_per_shard; every rank's shard
+ * [rows_per_shard, ld] and its gradient shard are peer-mapped (torch symmetric memory / cudaIpc /
+ * VMM), so ent[q] / grad_ent[q] are valid device pointers on THIS rank for every q. */
+typedef struct kge_shard_map {
+    int32_t struct_size;
+    int32_t world;          /* 1..8 */
+    int64_t rows_per_shard;
+    const float *ent[8];
+    float *grad_ent[8];
+} kge_shard_map;
+
+/* kge_train_step on a row-sharded entity table: the SAME fused kernel, its bulk row gathers and
+ * red.global.add.v4 gradient scatters simply address whichever rank owns the row -- the row
+ * all-to-all (forward) and gradient all-to-all (backward) SURVEY.md 8e describes happen inside the
+ * kernel over NVLink peer memory.  kge_config.n_ent is the GLOBAL entity count.  Relations are
+ * replicated (rel_dev / grad_rel_dev local; exchange them with kge_optimizer_step_sharded).
+ * The caller brackets it with cross-rank barriers: no rank may gather before every rank's
+ * optimizer finished, and no optimizer may start before every rank's scatters are complete. */
+int kge_train_step_sharded(kge_handle *h, int32_t mode, const kge_shard_map *map, const float *rel_dev,
+                           float *grad_rel_dev, const int32_t *triples_dev, int64_t B,
+                           const int32_t *neg_ent_dev, const uint8_t *neg_keep_subj_dev, uint64_t seed,
+                           uint64_t step, double *loss_dev, float *scores_pos_dev, float *scores_neg_dev,
+                           const float *dpos_dev, const float *dneg_dev, void *stream);
+
 /* OptimizerWrapper.minimize -> legacy apply_gradients (optimizers.py:136-168) for ONE
  * table, dense semantics, plus the LP regulariser's loss/gradient over the whole table
  * (regularizers.py:14-37; added to the loss at loss_functions.py:215-223).
@@ -203,6 +228,15 @@ int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const float *ent_dev
              const int32_t *cand_ids_dev, int64_t cand_begin, int64_t n_cand,
              const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
              int32_t *ranks_dev, void *stream);
+
+/* kge_rank against THIS rank's row shard of a sharded table: query rows are fetched from whichever
+ * rank owns them, candidates are the local shard's rows, filter ids are GLOBAL entity ids (those
+ * outside the shard are ignored, AbstractScoringLayer.py:280-288).  Sum ranks_dev over ranks
+ * (int32 all-reduce) for the full count (ScoringBasedEmbeddingModel.py:1449-1452). */
+int kge_rank_sharded(kge_handle *h, const kge_shard_map *map, int32_t rank, int32_t side, int32_t strategy,
+                     const float *rel_dev, const int32_t *triples_dev, int64_t b,
+                     const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
+                     int32_t *ranks_dev, void *stream);
 
 /* size in bytes of the device workspace kge_rank needs for b queries (allocated
  * internally and cached on the handle; exposed so callers can budget HBM). */
