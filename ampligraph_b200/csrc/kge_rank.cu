@@ -307,6 +307,142 @@ __global__ void __launch_bounds__(RK_THREADS) kge_rank_tile_kernel(const RankPar
     }
 }
 
+// --------------------------------------------------------------------------
+// DOT specialisation (DistMult / ComplEx / HolE): CTA = 256 candidates x 64 queries, thread tile =
+// 4 candidates (its own rows) x 16 queries, accumulators as 32 f32x2 pairs of adjacent queries.
+// The query tile is staged TRANSPOSED ([column][query]) so that one broadcast 128-bit read returns
+// four queries of one column, and each Blackwell packed FFMA2 (fma.rn.f32x2 with the candidate value
+// as the broadcast scalar operand) advances two canonical chains at once: same IEEE fma per chain,
+// same ascending column order, half the FP issue slots.
+// --------------------------------------------------------------------------
+constexpr int RD_TC = 256, RD_TQ = 64, RD_DK = 32, RD_ELDS = RD_DK + 4, RD_QLDS = RD_TQ + 4, RD_THREADS = 256;
+constexpr int RD_E_FLOATS = RD_TC * RD_ELDS, RD_Q_FLOATS = RD_DK * RD_QLDS;
+constexpr int RD_STAGE_FLOATS = RD_E_FLOATS + RD_Q_FLOATS;
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, bool valid)
+{
+    unsigned sz = valid ? 4u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned long long rk_pk2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long rk_fma2(float e, unsigned long long q, unsigned long long acc)
+{
+    unsigned long long d, ee = rk_pk2(e, e);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(ee), "l"(q), "l"(acc));
+    return d;
+}
+
+__global__ void __launch_bounds__(RD_THREADS, 2) kge_rank_dot_kernel(const RankParams p, int32_t *__restrict__ cnt)
+{
+    extern __shared__ __align__(128) float smem[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int cg = warp & 1, qg = warp >> 1;  // 2 candidate groups of 128, 4 query groups of 16
+    const long long c0 = (long long)blockIdx.x * RD_TC, q0 = (long long)blockIdx.y * RD_TQ;
+    const int ld = p.L.ld;
+    const int n_chunks = (ld + RD_DK - 1) / RD_DK;
+
+    // E staging: rows t/8 + 32n (n<8), column quad t%8 (16-byte copies)
+    const int lrow = t >> 3, c4 = t & 7;
+    const float *erow[8];
+    bool evalid[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        long long c = c0 + lrow + 32 * n;
+        evalid[n] = c < p.n_cand;
+        long long id = evalid[n] ? (p.cand_ids ? (long long)p.cand_ids[c] : p.cand_begin + c) : 0;
+        erow[n] = p.ent + (size_t)id * ld;
+    }
+    // Q staging (transposed): column t%32, queries t/32 + 8n (n<8), 4-byte copies
+    const int qd = t & 31, qq = t >> 5;
+
+    auto stage_load = [&](int chunk, int buf) {
+        float *Es = smem + buf * RD_STAGE_FLOATS, *Qs = Es + RD_E_FLOATS;
+        const int col = chunk * RD_DK + 4 * c4;
+        const bool cvalid = col < ld;
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+            cp_async16(Es + (lrow + 32 * n) * RD_ELDS + 4 * c4, erow[n] + (cvalid ? col : 0), cvalid && evalid[n]);
+        const int qcol = chunk * RD_DK + qd;
+        const bool qcvalid = qcol < ld;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const long long q = q0 + qq + 8 * n;
+            const bool ok = qcvalid && q < p.b;
+            cp_async4(Qs + qd * RD_QLDS + qq + 8 * n, p.qvec + (size_t)(ok ? q : 0) * ld + (ok ? qcol : 0), ok);
+        }
+        cp_async_commit();
+    };
+
+    unsigned long long acc[4][8];  // [candidate][query pair]
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[m][i] = 0ull;
+
+    stage_load(0, 0);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < n_chunks) { stage_load(ch + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const float *Es = smem + buf * RD_STAGE_FLOATS + (cg * 128 + lane) * RD_ELDS;
+        const float *Qs = smem + buf * RD_STAGE_FLOATS + RD_E_FLOATS + qg * 16;
+#pragma unroll
+        for (int d4 = 0; d4 < RD_DK / 4; ++d4) {
+            float4 e[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) e[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RD_ELDS + 4 * d4);
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+                const float *qrow = Qs + (4 * d4 + dd) * RD_QLDS;
+                unsigned long long q2[8];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(qrow + 4 * v);  // 4 queries
+                    q2[2 * v] = w.x;
+                    q2[2 * v + 1] = w.y;
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const float ev = dd == 0 ? e[m].x : dd == 1 ? e[m].y : dd == 2 ? e[m].z : e[m].w;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[m][i] = rk_fma2(ev, q2[i], acc[m][i]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // epilogue: quantise, compare with the positive, count over this warp's 128 candidates
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const long long q = q0 + qg * 16 + i;
+        const bool qok = q < p.b;
+        const int qp = qok ? p.qpos[q] : 0;
+        int gt = 0, eq = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[m][i >> 1]));
+            const float a = (i & 1) ? hi : lo;
+            const bool cok = (c0 + cg * 128 + lane + 32 * m) < p.n_cand;
+            const int qc = quantise(rank_finish<OP_DOT>(a, p.scale));
+            gt += __popc(__ballot_sync(0xffffffffu, cok && (qp < qc)));
+            eq += __popc(__ballot_sync(0xffffffffu, cok && (qp == qc)));
+        }
+        if (lane == 0 && qok) {
+            if (gt) atomicAdd(&cnt[3 * q + 0], gt);
+            if (eq) atomicAdd(&cnt[3 * q + 1], eq);
+        }
+    }
+}
+
 cudaError_t launch_rank_count(const RankParams &p, int32_t *cnt, cudaStream_t st)
 {
     if (p.b == 0 || p.n_cand == 0) return cudaSuccess;
@@ -321,7 +457,14 @@ cudaError_t launch_rank_count(const RankParams &p, int32_t *cnt, cudaStream_t st
         break;                                                                                               \
     }
     switch (rank_op(p.L.model, p.side)) {
-    case OP_DOT: KGE_RK(OP_DOT)
+    case OP_DOT: {
+        dim3 gd((unsigned)((p.n_cand + RD_TC - 1) / RD_TC), (unsigned)((p.b + RD_TQ - 1) / RD_TQ));
+        const size_t sm = 2 * RD_STAGE_FLOATS * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(kge_rank_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        kge_rank_dot_kernel<<<gd, RD_THREADS, sm, st>>>(p, cnt);
+        break;
+    }
     case OP_L1_ADD: KGE_RK(OP_L1_ADD)
     case OP_L1_SUB: KGE_RK(OP_L1_SUB)
     case OP_ROT_S: KGE_RK(OP_ROT_S)

@@ -6,7 +6,7 @@ from .loss_functions import LOSS_REGISTRY  # noqa: F401
 
 def __getattr__(name):
     # the model pulls in torch; keep `import ampligraph_b200.latent_features` light
-    if name == "ScoringBasedEmbeddingModel":
-        from .models import ScoringBasedEmbeddingModel
-        return ScoringBasedEmbeddingModel
+    if name in ("ScoringBasedEmbeddingModel", "EarlyStopping"):
+        from . import models
+        return getattr(models, name)
     raise AttributeError(name)

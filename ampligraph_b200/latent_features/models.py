@@ -30,6 +30,30 @@ class History:
             self.history.setdefault(k, []).append(v)
 
 
+class EarlyStopping:
+    """tf.keras.callbacks.EarlyStopping subset used with fit(validation_data=...): stop when `monitor`
+    (e.g. 'val_mrr') has not improved by `min_delta` for `patience` validations."""
+
+    def __init__(self, monitor="val_mrr", min_delta=0.0, patience=0, mode="auto", restore_best_weights=False):
+        self.monitor, self.min_delta, self.patience = monitor, abs(min_delta), patience
+        if mode == "auto":
+            mode = "min" if ("loss" in monitor or monitor.endswith("mr")) else "max"
+        self.sign = 1.0 if mode == "max" else -1.0
+        self.best, self.wait, self.stopped_epoch, self.model = None, 0, None, None
+
+    def on_epoch_end(self, epoch, logs):
+        if self.monitor not in logs:
+            return
+        v = self.sign * float(logs[self.monitor])
+        if self.best is None or v > self.best + self.min_delta:
+            self.best, self.wait = v, 0
+        else:
+            self.wait += 1
+            if self.wait >= self.patience and self.model is not None:
+                self.stopped_epoch = epoch
+                self.model.stop_training = True
+
+
 class ScoringBasedEmbeddingModel:
     """Same constructor as the reference (ScoringBasedEmbeddingModel.py:100-171)."""
 
@@ -181,6 +205,7 @@ class ScoringBasedEmbeddingModel:
             weights = self._to_dev(np.asarray(x[:, 3:], dtype=np.float32), np.float32)
         batch_size = int(batch_size)
         history = History()
+        self.stop_training = False
         user_loss = isinstance(self.compiled_loss, loss_functions.LossFunctionWrapper)
         world, rank = self._world(), self._rank()
         if world > 1 and (user_loss or self.use_focusE):
@@ -221,8 +246,18 @@ class ScoringBasedEmbeddingModel:
                              "val_hits@1": hits_at_n_score(ranks, 1), "val_hits@10": hits_at_n_score(ranks, 10),
                              "val_hits@100": hits_at_n_score(ranks, 100)})
             history._log(epoch, logs)
+            for cb in (callbacks or []):  # minimal Keras callback protocol: on_epoch_end + model.stop_training
+                if getattr(cb, "model", None) is None:
+                    try:
+                        cb.model = self
+                    except Exception:
+                        pass
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
             if verbose:
                 print("Epoch %d/%d - " % (epoch + 1, epochs) + " - ".join("%s: %.4f" % kv for kv in logs.items()))
+            if self.stop_training:
+                break
         self.is_fitted = True
         self.history = history
         return history
@@ -346,6 +381,63 @@ class ScoringBasedEmbeddingModel:
         if corrupt_side == "s+o":  # :1459-1463 sum BEFORE the +1
             out = out.sum(1, keepdims=True)
         return (out + 1).astype(np.int32)  # :1684
+
+    # ------------------------------------------------------------------ calibration
+    def calibrate(self, X_pos, X_neg=None, positive_base_rate=None, batch_size=32, epochs=50, verbose=0):
+        """calibrate (:1922-2122) with CalibrationLayer (layers/calibration/calibrate.py:11-129): Platt scaling,
+        two scalars (w, b) fitted with Adam on the kernel's scores of positives and negatives (given, or
+        generated corruptions when only positive_base_rate is given)."""
+        if not self.is_fitted:
+            raise RuntimeError("Model has not been fitted.")
+        self.is_calibrated = False
+        pos = self._to_dev(self._index(X_pos), np.int32)
+        pos_size = pos.shape[0]
+        with_corruption = X_neg is None
+        if with_corruption:
+            assert positive_base_rate is not None, "Please provide the negatives or positive base rate!"
+            neg, neg_size = None, pos_size
+        else:
+            neg = self._to_dev(self._index(X_neg), np.int32)
+            neg_size = neg.shape[0]
+            if positive_base_rate is None:
+                positive_base_rate = pos_size / (pos_size + neg_size)
+        if positive_base_rate is not None and (positive_base_rate <= 0 or positive_base_rate >= 1):
+            raise ValueError("positive_base_rate must be a value between 0 and 1.")
+        dev = self.engine.device
+        w = torch.zeros((), device=dev, requires_grad=True)  # calibrate.py:60-63
+        b = torch.tensor(float(np.log((neg_size + 1.0) / (pos_size + 1.0))), device=dev, requires_grad=True)
+        opt = torch.optim.Adam([w, b], lr=1e-3, eps=1e-7)
+        n_batches = int(np.ceil(pos_size / batch_size))
+        nb_size = int(np.ceil(neg_size / n_batches)) if not with_corruption else None
+        step = 0
+        for _ in range(epochs):
+            for i in range(n_batches):
+                pb = pos[i * batch_size:(i + 1) * batch_size].contiguous()
+                sp = self.engine.score(pb)
+                if with_corruption:
+                    sn = self.engine.score(self.engine.generate_corruptions(pb, self.seed, step))
+                else:
+                    sn = self.engine.score(neg[i * nb_size:(i + 1) * nb_size].contiguous())
+                step += 1
+                scores = torch.cat([sp, sn])
+                logits = -(w * scores + b)
+                labels = torch.cat([torch.full_like(sp, (pos_size + 1.0) / (pos_size + 2.0)),
+                                    torch.full_like(sn, 1.0 / (neg_size + 2.0))])
+                weights = torch.cat([torch.full_like(sp, sn.shape[0] / max(sp.shape[0], 1)),
+                                     torch.full_like(sn, (1.0 - positive_base_rate) / positive_base_rate)])
+                loss = (weights * torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="none")).mean()
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+        self.calib_w, self.calib_b = float(w.detach()), float(b.detach())
+        self.is_calibrated = True
+
+    def predict_proba(self, x, batch_size=32, verbose=0, callbacks=None):
+        """predict_proba (:2124-2212): sigmoid(-(w*score + b)) of the calibrated model."""
+        if not self.is_calibrated:
+            raise RuntimeError("Model has not been calibrated. Please call `model.calibrate(...)` before predicting probabilities.")
+        sc = self.predict(x, batch_size=batch_size)
+        return (1.0 / (1.0 + np.exp(self.calib_w * sc + self.calib_b))).astype(np.float32)
 
     # ------------------------------------------------------------------ embeddings / weights
     def get_embeddings(self, entities, embedding_type="e"):

@@ -171,3 +171,29 @@ def test_focuse_matches_oracle(non_linearity):
             step += 1
     ent = m.get_embeddings(ix.ent_labels, "e")
     assert np.allclose(ent, rs.ent.detach().numpy(), rtol=2e-3, atol=5e-5), np.abs(ent - rs.ent.detach().numpy()).max()
+
+
+def test_calibration_and_early_stopping():
+    """calibrate / predict_proba (ScoringBasedEmbeddingModel.py:1922-2212) and an EarlyStopping callback."""
+    from ampligraph_b200.latent_features import EarlyStopping, ScoringBasedEmbeddingModel
+    X = _kg(200, 5, 3000, seed=11)
+    m = ScoringBasedEmbeddingModel(eta=5, k=16, scoring_type="ComplEx", seed=2)
+    m.compile(optimizer="adam", loss="multiclass_nll")
+    es = EarlyStopping(monitor="val_mrr", patience=1)
+    h = m.fit(X[:2600], batch_size=650, epochs=60, validation_data=X[2600:], validation_freq=2, callbacks=[es], verbose=False)
+    assert es.stopped_epoch is not None and len(h.history["loss"]) < 60  # stopped early
+    with pytest.raises(RuntimeError):
+        m.predict_proba(X[:10])
+    rng = np.random.default_rng(0)
+    X_neg = X[2600:].copy()
+    X_neg[:, 2] = rng.permutation(X_neg[:, 2])  # corrupted objects
+    m.calibrate(X[2600:], X_neg=X_neg, batch_size=100, epochs=30)
+    p_pos, p_neg = m.predict_proba(X[2600:]), m.predict_proba(X_neg)
+    assert ((p_pos > 0) & (p_pos < 1)).all() and p_pos.mean() > p_neg.mean()
+    sc = m.predict(X[2600:])
+    order = np.argsort(sc)
+    assert (np.diff(p_pos[order]) >= -1e-7).all() or (np.diff(p_pos[order]) <= 1e-7).all()  # monotone in the score
+    m.calibrate(X[2600:], positive_base_rate=0.5, batch_size=100, epochs=5)  # corruption-based variant
+    assert m.is_calibrated and 0 < m.predict_proba(X[:5]).min()
+    with pytest.raises(ValueError):
+        m.calibrate(X[2600:], positive_base_rate=1.5)
