@@ -231,7 +231,7 @@ class ShardedTrainer:
         eng.g_rel.zero_()
         eng.launches += 4
 
-    def rank(self, triples, side, strategy="worst", filt_off=None, filt_idx=None):
+    def rank_counts(self, triples, side, strategy="worst", filt_off=None, filt_idx=None):
         """full-table rank counts: each rank counts against its shard, int32 counts are summed."""
         C, _lib, eng = self._C, self._lib, self.eng
         b = triples.shape[0]

@@ -120,7 +120,7 @@ for model, k in (("RotatE", 24), ("ComplEx", 40)):
     filt = [sorted(set(rng.integers(0, E, 6).tolist())) for _ in range(48)]
     off = dev(np.concatenate([[0], np.cumsum([len(f) for f in filt])]).astype(np.int64)); idx = dev(np.concatenate(filt).astype(np.int32))
     for side in ("s", "o"):
-        assert (tr.rank(q, side, "worst", off, idx) == ref.rank(q, side, "worst", off, idx)).all(), (model, side)
+        assert (tr.rank_counts(q, side, "worst", off, idx) == ref.rank(q, side, "worst", off, idx)).all(), (model, side)
     tr.close(); ref.close()
 dist.destroy_process_group()
 print("rank", rank, "sharded ok")
