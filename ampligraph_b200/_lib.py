@@ -39,7 +39,7 @@ class KgeOptimizerConfig(C.Structure):
 
 class KgeShardMap(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("world", C.c_int32), ("rows_per_shard", C.c_int64),
-                ("ent", C.c_void_p * 8), ("grad_ent", C.c_void_p * 8)]
+                ("ent", C.c_void_p * 8), ("grad_ent", C.c_void_p * 8), ("stamp_ent", C.c_void_p * 8)]
 
 
 _P = C.c_void_p
@@ -65,6 +65,10 @@ PROTOTYPES = {
                                    _P, _P, C.c_int64, _P, _P]),
     "kge_optimizer_step": (C.c_int, [_P, C.POINTER(KgeOptimizerConfig), C.c_int64, _P, _P, _P, _P, C.c_int64,
                                      _P, _P]),
+    "kge_set_row_stamps": (C.c_int, [_P, _P, _P]),
+    "kge_step_stamp": (C.c_int32, [C.c_uint64]),
+    "kge_optimizer_step_lazy": (C.c_int, [_P, C.POINTER(KgeOptimizerConfig), C.c_int64, _P, _P, _P, _P, C.c_int64, _P,
+                                          C.c_int32, _P, _P]),
     "kge_optimizer_step_sharded": (C.c_int, [_P, C.POINTER(KgeOptimizerConfig), C.c_int64, C.c_int32, C.c_int32,
                                              C.POINTER(_P), C.POINTER(_P), _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "kge_rank": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P,

@@ -20,6 +20,7 @@ struct kge_handle {
     // training launch geometry
     int nit, G, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats;
     // ranking workspace (grown on demand)
+    int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
     long long ws_b;
     float *ws_q;      // 3 * ws_b * ld floats: qvec_s | qvec_o | qaux
     int32_t *ws_i;    // 4 * ws_b ints: qpos | cnt[3]
@@ -299,10 +300,18 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
     p.scores_neg = scores_neg_dev;
     p.dpos = dpos_dev;
     p.dneg = dneg_dev;
+    p.stamp = (int)(step & 0x3fffffffu) + 1;
+    p.stamp_ent = h->stamp_ent;
+    p.stamp_rel = h->stamp_rel;
     if (map && map->world > 1) {
         p.shard_world = map->world;
         p.rows_per_shard = (int)map->rows_per_shard;
         for (int q = 0; q < map->world; ++q) { p.ent_shard[q] = map->ent[q]; p.grad_ent_shard[q] = map->grad_ent[q]; }
+        p.stamp_ent = map->stamp_ent[0];
+        for (int q = 0; q < map->world; ++q) {
+            p.stamp_ent_shard[q] = map->stamp_ent[q];
+            if (!map->stamp_ent[q]) p.stamp_ent = nullptr;  // all or nothing
+        }
     }
     KGE_CUDA(launch_train(p, h->nit, h->sm_count, h->warps * 32, (size_t)h->warps * h->region_bytes, st),
              "kge_train_step");
@@ -372,6 +381,16 @@ extern "C" int kge_optimizer_step(kge_handle *h, const kge_optimizer_config *opt
     return KGE_OK;
 }
 
+extern "C" int kge_set_row_stamps(kge_handle *h, int32_t *ent_stamps_dev, int32_t *rel_stamps_dev)
+{
+    KGE_CHECK_HANDLE(h, "kge_set_row_stamps");
+    h->stamp_ent = ent_stamps_dev;
+    h->stamp_rel = rel_stamps_dev;
+    return KGE_OK;
+}
+
+extern "C" int32_t kge_step_stamp(uint64_t step) { return (int32_t)(step & 0x3fffffffu) + 1; }
+
 static int fill_optim(const kge_optimizer_config *opt, int64_t t, OptimParams &o)
 {
     o.kind = opt->kind;
@@ -385,6 +404,30 @@ static int fill_optim(const kge_optimizer_config *opt, int64_t t, OptimParams &o
     o.lr_t = (float)((double)opt->learning_rate * sqrt(1.0 - pow((double)opt->beta_2, (double)t)) /
                      (1.0 - pow((double)opt->beta_1, (double)t)));
     return 0;
+}
+
+extern "C" int kge_optimizer_step_lazy(kge_handle *h, const kge_optimizer_config *opt, int64_t t, float *table_dev,
+                                       float *grad_dev, float *slot0_dev, float *slot1_dev, int64_t rows,
+                                       const int32_t *row_stamp_dev, int32_t stamp, double *reg_loss_dev, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_optimizer_step_lazy");
+    if (!opt || opt->struct_size != (int32_t)sizeof(kge_optimizer_config))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_lazy: bad kge_optimizer_config (ABI mismatch)");
+    if (opt->kind < KGE_OPT_SGD || opt->kind > KGE_OPT_ADAGRAD)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "Could not interpret optimizer identifier: %d", opt->kind);
+    if (rows < 0 || t < 1) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_lazy: rows >= 0 and t >= 1 required");
+    if (rows == 0) return KGE_OK;
+    if (!table_dev || !grad_dev || !row_stamp_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_lazy: null pointer");
+    const bool need0 = opt->kind != KGE_OPT_SGD || opt->momentum != 0.f;
+    const bool need1 = opt->kind == KGE_OPT_ADAM;
+    if ((need0 && !slot0_dev) || (need1 && !slot1_dev))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_lazy: optimizer slot buffer missing");
+    OptimParams o;
+    fill_optim(opt, t, o);
+    KGE_CUDA(launch_optimizer_lazy(o, table_dev, grad_dev, slot0_dev, slot1_dev, rows, h->L.ld, (const int *)row_stamp_dev,
+                                   stamp, reg_loss_dev, h->sm_count, (cudaStream_t)stream),
+             "kge_optimizer_step_lazy");
+    return KGE_OK;
 }
 
 extern "C" int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_config *opt, int64_t t, int32_t world,

@@ -40,6 +40,10 @@ struct TrainParams {
     int shard_world, rows_per_shard;
     const float *ent_shard[KGE_MAX_PEERS];
     float *grad_ent_shard[KGE_MAX_PEERS];
+    // lazy optimizer support: rows touched by this step get stamp written (nullptr: off)
+    int stamp;
+    int *stamp_ent, *stamp_rel;
+    int *stamp_ent_shard[KGE_MAX_PEERS];
 };
 
 // grid = min(occupancy * sm_count, ceil(B / warps))
@@ -66,6 +70,9 @@ struct OptimParams {
 cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
                              long long n_floats, double *reg_loss, int sm_count, cudaStream_t st);
 cudaError_t launch_fill(float *p, long long n, float v, cudaStream_t st);
+cudaError_t launch_optimizer_lazy(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
+                                  long long rows, int ld, const int *row_stamp, int stamp, double *reg_loss,
+                                  int sm_count, cudaStream_t st);
 // tables/grads: HOST arrays of `world` device pointers (own rank first is NOT required; index = rank)
 cudaError_t launch_optimizer_sharded(const OptimParams &o, int world, int rank, float *const *tables, float *const *grads,
                                      float *slot0, float *slot1, long long off_floats, long long n_floats,

@@ -174,6 +174,86 @@ cudaError_t launch_optimizer_sharded(const OptimParams &o, int world, int rank, 
     return cudaGetLastError();
 }
 
+// --------------------------------------------------------------------------
+// LAZY optimizer (extension for tables whose dense update is unaffordable, e.g. cfg5: 10 M entities x
+// k=1000 -> 80 GB table, 560 GB of dense-Adam traffic per step).  Only rows stamped by
+// this step's training kernel are read and updated: m, v of untouched rows do NOT decay and the rows do
+// not move (the semantics of TensorFlow-Addons' LazyAdam), bias correction uses the global step.  This
+// is NOT the reference's dense rule; it is opt-in ('lazy_adam' etc.).  A warp scans 32 row stamps with
+// one coalesced read, ballots the touched ones and updates each touched row cooperatively.
+// --------------------------------------------------------------------------
+template <int KIND, bool REG>
+__global__ void __launch_bounds__(256) kge_optim_lazy_kernel(float *__restrict__ var, float *__restrict__ grad,
+                                                             float *__restrict__ s0, float *__restrict__ s1,
+                                                             long long rows, int ld, const int *__restrict__ row_stamp,
+                                                             int stamp, OptimParams o, double *reg_loss)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float racc = 0.f;
+    for (long long base = warp0 * 32; base < rows; base += n_warps * 32) {
+        const long long r = base + lane;
+        unsigned m = __ballot_sync(0xffffffffu, r < rows && row_stamp[r] == stamp);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const size_t off = (size_t)(base + b) * ld;
+            for (int c = lane * 4; c < ld; c += 128) {
+                float4 x4 = *reinterpret_cast<float4 *>(var + off + c), g4 = *reinterpret_cast<float4 *>(grad + off + c);
+                float x[4] = {x4.x, x4.y, x4.z, x4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w}, a[4], bb[4];
+                if (KIND != KGE_OPT_SGD || o.momentum != 0.f) { float4 t = *reinterpret_cast<float4 *>(s0 + off + c); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+                if (KIND == KGE_OPT_ADAM) { float4 t = *reinterpret_cast<float4 *>(s1 + off + c); bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float gg = g[e];
+                    if (REG) { float pw; gg += reg_grad(x[e], o.reg_p, o.reg_lambda, &pw); racc += pw; }
+                    if (KIND == KGE_OPT_ADAM) {
+                        a[e] = fmaf(gg - a[e], 1.f - o.beta1, a[e]);
+                        bb[e] = fmaf(gg * gg - bb[e], 1.f - o.beta2, bb[e]);
+                        x[e] -= (a[e] * o.lr_t) / (sqrtf(bb[e]) + o.eps);
+                    } else if (KIND == KGE_OPT_ADAGRAD) {
+                        a[e] = fmaf(gg, gg, a[e]);
+                        x[e] -= o.lr * gg / (sqrtf(a[e]) + o.eps);
+                    } else {
+                        if (o.momentum != 0.f) { a[e] = o.momentum * a[e] - o.lr * gg; x[e] += a[e]; }
+                        else x[e] -= o.lr * gg;
+                    }
+                }
+                *reinterpret_cast<float4 *>(var + off + c) = make_float4(x[0], x[1], x[2], x[3]);
+                if (KIND != KGE_OPT_SGD || o.momentum != 0.f) *reinterpret_cast<float4 *>(s0 + off + c) = make_float4(a[0], a[1], a[2], a[3]);
+                if (KIND == KGE_OPT_ADAM) *reinterpret_cast<float4 *>(s1 + off + c) = make_float4(bb[0], bb[1], bb[2], bb[3]);
+                *reinterpret_cast<float4 *>(grad + off + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    if (REG && reg_loss) {
+        racc = warp_sum(racc);
+        if (lane == 0 && racc != 0.f) atomicAdd(reg_loss, (double)o.reg_lambda * (double)racc);
+    }
+}
+
+cudaError_t launch_optimizer_lazy(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
+                                  long long rows, int ld, const int *row_stamp, int stamp, double *reg_loss,
+                                  int sm_count, cudaStream_t st)
+{
+    if (rows == 0) return cudaSuccess;
+    long long want = (rows + 255) / 256;  // 8 warps x 32 rows per block
+    int grid = (int)(want < (long long)sm_count * 8 ? want : (long long)sm_count * 8);
+    const bool reg = o.reg_p > 0;
+#define KGE_OPTL(K)                                                                                                      \
+    if (reg) kge_optim_lazy_kernel<K, true><<<grid, 256, 0, st>>>(table, grad, slot0, slot1, rows, ld, row_stamp, stamp, o, reg_loss); \
+    else kge_optim_lazy_kernel<K, false><<<grid, 256, 0, st>>>(table, grad, slot0, slot1, rows, ld, row_stamp, stamp, o, reg_loss);
+    switch (o.kind) {
+    case KGE_OPT_SGD: KGE_OPTL(KGE_OPT_SGD) break;
+    case KGE_OPT_ADAM: KGE_OPTL(KGE_OPT_ADAM) break;
+    case KGE_OPT_ADAGRAD: KGE_OPTL(KGE_OPT_ADAGRAD) break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef KGE_OPTL
+    return cudaGetLastError();
+}
+
 __global__ void kge_fill_kernel(float *p, long long n, float v)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -673,6 +673,12 @@ __device__ __forceinline__ const float *ent_row(const TrainParams &p, int id)
     const int q = id / p.rows_per_shard;
     return p.ent_shard[q] + (size_t)(id - q * p.rows_per_shard) * p.ld;
 }
+__device__ __forceinline__ void stamp_ent_row(const TrainParams &p, int id)
+{
+    if (p.shard_world <= 1) { p.stamp_ent[id] = p.stamp; return; }
+    const int q = id / p.rows_per_shard;
+    p.stamp_ent_shard[q][id - q * p.rows_per_shard] = p.stamp;
+}
 __device__ __forceinline__ float *gent_row(const TrainParams &p, int id)
 {
     if (p.shard_world <= 1) return p.grad_ent + (size_t)id * p.ld;
@@ -750,6 +756,12 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
             nid[j] = repl;
             nside[j] = keep;  // keep_subj = 1 -> object replaced -> side 1
             if (!resident) sc[j] = 0.f;
+            if (p.stamp_ent && p.mode != KGE_STEP_FORWARD_ONLY) stamp_ent_row(p, repl);  // lazy optimizer: row touched
+        }
+        if (p.stamp_ent && p.mode != KGE_STEP_FORWARD_ONLY) {
+            if (lane == 0) stamp_ent_row(p, s_id);
+            if (lane == 1) stamp_ent_row(p, o_id);
+            if (lane == 2 && p.stamp_rel) p.stamp_rel[p_id] = p.stamp;
         }
         __syncwarp();
         auto spo_src = [&](int r) { return r == 0 ? ent_row(p, s_id) : r == 1 ? p.rel + (size_t)p_id * ld : ent_row(p, o_id); };

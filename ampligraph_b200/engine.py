@@ -83,6 +83,10 @@ class KGEEngine:
     # -- optimizer state (optimizers.py:255-291) ---------------------------
     def set_optimizer(self, name="adam", params=None, regularizer=None):
         name = name.lower()
+        # 'lazy_<name>' (extension): update only the rows touched by the step (kge_optimizer_step_lazy)
+        self.lazy = name.startswith("lazy_")
+        if self.lazy:
+            name = name[len("lazy_"):]
         if name not in _lib.OPTIMIZERS:
             raise ValueError("Could not interpret optimizer identifier: %r" % (name,))
         p = dict(params or {})
@@ -106,6 +110,12 @@ class KGEEngine:
         elif self.opt_cfg.momentum != 0.0:
             for key, rows in (("ent", self.ent_rows), ("rel", self.n_rel)):
                 self.slots[key] = [mk(rows), None]
+        self.stamps = {"ent": None, "rel": None}
+        if self.lazy:
+            self.stamps = {"ent": torch.zeros(self.ent_rows, dtype=torch.int32, device=self.device),
+                           "rel": torch.zeros(self.n_rel, dtype=torch.int32, device=self.device)}
+        _lib.check(self.lib.kge_set_row_stamps(self.h, _ptr(self.stamps["ent"]), _ptr(self.stamps["rel"])))
+        self._last_step = 0
 
     # -- tables ------------------------------------------------------------
     def set_embeddings(self, ent_dense=None, rel_dense=None):
@@ -147,6 +157,7 @@ class KGEEngine:
             self.h, mode, _ptr(self.ent), _ptr(self.rel), _ptr(self.g_ent), _ptr(self.g_rel), _ptr(triples), B,
             _ptr(neg_ent), _ptr(neg_keep), int(seed), int(step), _ptr(self.loss_acc), _ptr(scores_pos),
             _ptr(scores_neg), _ptr(dpos), _ptr(dneg), self._stream()))
+        self._last_step = int(step)
         self.launches += 2 if self.scoring_type == "RotatE" else 1
 
     def apply_gradients(self):
@@ -155,6 +166,12 @@ class KGEEngine:
         for key, table, grad, rows in (("ent", self.ent, self.g_ent, self.ent_rows),
                                        ("rel", self.rel, self.g_rel, self.n_rel)):
             s0, s1 = self.slots[key]
+            if self.lazy:
+                _lib.check(self.lib.kge_optimizer_step_lazy(
+                    self.h, C.byref(self.opt_cfg), self.t, _ptr(table), _ptr(grad), _ptr(s0), _ptr(s1), rows,
+                    _ptr(self.stamps[key]), self.lib.kge_step_stamp(self._last_step),
+                    C.c_void_p(self.loss_acc.data_ptr() + 8), self._stream()))
+                continue
             _lib.check(self.lib.kge_optimizer_step(
                 self.h, C.byref(self.opt_cfg), self.t, _ptr(table), _ptr(grad), _ptr(s0), _ptr(s1), rows,
                 C.c_void_p(self.loss_acc.data_ptr() + 8), self._stream()))

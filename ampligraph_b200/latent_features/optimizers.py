@@ -4,7 +4,9 @@ The reference wraps tf.keras.optimizers.legacy.* (optimizers.py:255-291); here t
 update itself is csrc/kge_optim.cu and this wrapper only carries name +
 hyper-parameters.  Supported: 'sgd' (optional momentum), 'adam', 'adagrad'.
 """
-SUPPORTED = ("sgd", "adam", "adagrad")
+SUPPORTED = ("sgd", "adam", "adagrad",
+             # extension (not in the reference): touched-rows-only updates for tables too large for the dense rule
+             "lazy_sgd", "lazy_adam", "lazy_adagrad")
 
 
 class OptimizerWrapper:
@@ -16,7 +18,7 @@ class OptimizerWrapper:
         self.hyperparams = dict(hyperparams or {})
         self.hyperparams.setdefault("learning_rate", 0.001)  # optimizers.py:284
         # adam has beta_1/beta_2 slots (optimizers.py:119-120)
-        self.number_hyperparams = 2 if name == "adam" else 1
+        self.number_hyperparams = 2 if name.endswith("adam") else 1
 
     def get_hyperparam_count(self):
         return self.number_hyperparams

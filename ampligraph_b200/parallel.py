@@ -146,7 +146,10 @@ class ShardedTrainer:
       3. barrier.
     """
 
-    def __init__(self, scoring_type, k, eta, n_ent, n_rel, device, group=None, **engine_kw):
+    def __init__(self, scoring_type, k, eta, n_ent, n_rel, device, group=None, lazy=False, **engine_kw):
+        """lazy=True: each rank updates only the rows of its shard that the step touched
+        (kge_optimizer_step_lazy; opt-in, not the reference's dense rule) -- what makes a 10 M-entity
+        table trainable: the dense pass would stream the whole 10 GB shard 8 times per step."""
         import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
@@ -159,16 +162,20 @@ class ShardedTrainer:
         self.first = self.rank * self.rps
         self.n_local = max(0, min(self.rps, self.n_ent - self.first))
 
+        self.lazy = bool(lazy)
+
         def alloc(rows, n_rel_, ld, dev):
             assert rows == self.rps
-            total = 2 * rows + 2 * n_rel_
+            self._stamp_rows = (rows + ld - 1) // ld  # int32 row stamps live in the same symmetric buffer
+            total = 2 * rows + 2 * n_rel_ + self._stamp_rows
             self._buf = symm_mem.empty((total, ld), dtype=torch.float32, device=dev)
             self._buf.zero_()
             pg = group if group is not None else dist.group.WORLD
             self.hdl = symm_mem.rendezvous(self._buf, pg.group_name)
-            self._off = {"ent": 0, "g_ent": rows, "rel": 2 * rows, "g_rel": 2 * rows + n_rel_}
+            self._off = {"ent": 0, "g_ent": rows, "rel": 2 * rows, "g_rel": 2 * rows + n_rel_,
+                         "stamp": 2 * rows + 2 * n_rel_}
             b = self._buf
-            return b[0:rows], b[2 * rows:2 * rows + n_rel_], b[rows:2 * rows], b[2 * rows + n_rel_:total]
+            return b[0:rows], b[2 * rows:2 * rows + n_rel_], b[rows:2 * rows], b[2 * rows + n_rel_:2 * rows + 2 * n_rel_]
 
         self.eng = KGEEngine(scoring_type, k, eta, n_ent, n_rel, device=device, table_alloc=alloc, ent_rows=self.rps,
                              **engine_kw)
@@ -179,6 +186,9 @@ class ShardedTrainer:
         for q in range(self.world):
             self.map.ent[q] = ptr(q, "ent")
             self.map.grad_ent[q] = ptr(q, "g_ent")
+            self.map.stamp_ent[q] = ptr(q, "stamp") if self.lazy else None
+        so = self._off["stamp"]
+        self._stamps = self._buf[so:so + self._stamp_rows].view(torch.int32).reshape(-1)[:self.rps]
         self._rel_ptrs = (C.c_void_p * self.world)(*[ptr(q, "rel") for q in range(self.world)])
         self._grel_ptrs = (C.c_void_p * self.world)(*[ptr(q, "g_rel") for q in range(self.world)])
         self.rel_shard = row_shard(self.n_rel, self.world, self.rank)
@@ -220,8 +230,13 @@ class ShardedTrainer:
         self.hdl.barrier(channel=0)  # every rank's scatters (into my shard too) and relation gradients are complete
         eng.t += 1
         s0, s1 = eng.slots["ent"]
-        _lib.check(eng.lib.kge_optimizer_step(eng.h, C.byref(eng.opt_cfg), eng.t, p(eng.ent), p(eng.g_ent), p(s0), p(s1),
-                                              self.rps, C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
+        if self.lazy:
+            _lib.check(eng.lib.kge_optimizer_step_lazy(eng.h, C.byref(eng.opt_cfg), eng.t, p(eng.ent), p(eng.g_ent), p(s0), p(s1),
+                                                       self.rps, p(self._stamps), eng.lib.kge_step_stamp(int(step)),
+                                                       C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
+        else:
+            _lib.check(eng.lib.kge_optimizer_step(eng.h, C.byref(eng.opt_cfg), eng.t, p(eng.ent), p(eng.g_ent), p(s0), p(s1),
+                                                  self.rps, C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
         lo, hi = self.rel_shard
         r0, r1 = eng.slots["rel"]
         _lib.check(eng.lib.kge_optimizer_step_sharded(

@@ -168,6 +168,7 @@ typedef struct kge_shard_map {
     int64_t rows_per_shard;
     const float *ent[8];
     float *grad_ent[8];
+    int32_t *stamp_ent[8]; /* optional lazy-optimizer row stamps of every shard (all NULL = off) */
 } kge_shard_map;
 
 /* kge_train_step on a row-sharded entity table: the SAME fused kernel, its bulk row gathers and
@@ -193,6 +194,19 @@ int kge_train_step_sharded(kge_handle *h, int32_t mode, const kge_shard_map *map
 int kge_optimizer_step(kge_handle *h, const kge_optimizer_config *opt, int64_t t, float *table_dev,
                        float *grad_dev, float *slot0_dev, float *slot1_dev, int64_t rows,
                        double *reg_loss_dev, void *stream);
+
+/* LAZY optimizer (opt-in extension, NOT the reference's dense rule): only rows touched by the
+ * step are read and updated; m, v of untouched rows do not decay and the rows do not move (the
+ * semantics of TensorFlow-Addons' LazyAdam).  Needed when the dense pass is unaffordable
+ * (BASELINE configs[4]: 80 GB table).  kge_set_row_stamps registers caller-owned int32 [rows]
+ * buffers; from then on kge_train_step writes kge_step_stamp(step) into the stamp of every row it
+ * scatters a gradient to, and kge_optimizer_step_lazy(..., row_stamp_dev, kge_step_stamp(step))
+ * updates exactly those rows (and zeroes their gradient rows). */
+int kge_set_row_stamps(kge_handle *h, int32_t *ent_stamps_dev, int32_t *rel_stamps_dev);
+int32_t kge_step_stamp(uint64_t step);
+int kge_optimizer_step_lazy(kge_handle *h, const kge_optimizer_config *opt, int64_t t, float *table_dev,
+                            float *grad_dev, float *slot0_dev, float *slot1_dev, int64_t rows,
+                            const int32_t *row_stamp_dev, int32_t stamp, double *reg_loss_dev, void *stream);
 
 /* Data-parallel variant of kge_optimizer_step FUSED with the gradient exchange over NVLink peer
  * memory (the reference has no distributed path; SURVEY.md 8e asks for replicated tables + a

@@ -176,6 +176,10 @@ class LegacyOptimizer:
     rows first, then Adam decays m/v for EVERY row and moves every row."""
 
     def __init__(self, name="adam", learning_rate=0.001, **hp):
+        # 'lazy_<name>': update only rows with a gradient contribution this step (the documented
+        # semantics of TensorFlow-Addons LazyAdam; NOT the reference's rule -- an extension of the product)
+        self.lazy = name.lower().startswith("lazy_")
+        name = name.lower()[5:] if self.lazy else name
         self.name = name.lower()
         self.lr = float(learning_rate)
         self.hp = hp
@@ -210,10 +214,37 @@ class LegacyOptimizer:
         else:
             raise ValueError("Could not interpret optimizer identifier: %s" % self.name)
 
-    def step(self, named_vars_grads):
+    def step(self, named_vars_grads, touched=None):
+        """touched: {key: LongTensor of row ids} -- required in lazy mode."""
         self.t += 1
         for key, (var, grad) in named_vars_grads.items():
-            self.apply(var, grad, key)
+            if not self.lazy:
+                self.apply(var, grad, key)
+                continue
+            rows = torch.unique(touched[key])
+            full = self.slots.get(key)
+            sub_var = var[rows].clone()
+            saved = self.slots.get(key)
+            # run the dense rule on the touched rows only, with row-sliced slots
+            if saved is not None:
+                self.slots[key] = tuple(s[rows].clone() for s in saved) if isinstance(saved, tuple) else saved[rows].clone()
+            elif self.name == "adam":
+                self.slots[key] = (torch.zeros_like(sub_var), torch.zeros_like(sub_var))
+                saved = (torch.zeros_like(var), torch.zeros_like(var))
+            elif self.name == "adagrad":
+                init = float(self.hp.get("initial_accumulator_value", 0.1))
+                self.slots[key] = torch.full_like(sub_var, init)
+                saved = torch.full_like(var, init)
+            self.apply(sub_var, grad[rows], key)
+            var[rows] = sub_var
+            new = self.slots.get(key)
+            if new is not None:
+                if isinstance(new, tuple):
+                    for s_full, s_new in zip(saved, new):
+                        s_full[rows] = s_new
+                else:
+                    saved[rows] = new
+                self.slots[key] = saved
 
 
 # --------------------------------------------------------------------------
@@ -260,5 +291,10 @@ class RefStep:
     def train_step(self, triples, corruptions):
         loss, sp, sn, g_ent, g_rel = self.loss_and_grads(triples, corruptions)
         with torch.no_grad():  # optimizers.py:168 apply_gradients
-            self.opt.step({"ent": (self.ent, g_ent), "rel": (self.rel, g_rel)})
+            touched = None
+            if self.opt.lazy:
+                t = torch.as_tensor(triples, dtype=torch.long)
+                c = torch.as_tensor(corruptions, dtype=torch.long)
+                touched = {"ent": torch.cat([t[:, 0], t[:, 2], c[:, 0], c[:, 2]]), "rel": t[:, 1]}
+            self.opt.step({"ent": (self.ent, g_ent), "rel": (self.rel, g_rel)}, touched)
         return float(loss)

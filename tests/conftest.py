@@ -9,6 +9,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+try:  # the oracle's torch-CPU ops oversubscribe badly on many-core shared hosts (seen on the B200 boxes)
+    import torch
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+except Exception:
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -281,6 +281,30 @@ def test_train_steps_vs_oracle(opt, params, reg):
     eng.close()
 
 
+@pytest.mark.parametrize("opt", ["lazy_adam", "lazy_adagrad", "lazy_sgd"])
+def test_lazy_optimizer_matches_restatement(opt):
+    """opt-in lazy optimizer (rows touched by the step only) vs the oracle's lazy restatement; untouched
+    rows must not move at all."""
+    rng = np.random.default_rng(43)
+    model, E, R, k, eta, B = "DistMult", 400, 6, 12, 3, 25   # few positives: most rows stay untouched
+    ent, rel = _tables(model, E, R, k, rng, scale=0.5)
+    eng = _engine(model, k, eta, E, R, loss="nll", optimizer=opt, optimizer_params={"learning_rate": 0.01})
+    eng.set_embeddings(ent, rel)
+    rs = _ref(model, k, ent, rel, eta, "nll", {}, optimizer=opt, optimizer_params={"learning_rate": 0.01})
+    touched = np.zeros(E, bool)
+    for step in range(4):
+        t = _triples(E, R, B, rng)
+        neg_ent, neg_keep = _negatives(E, B, eta, rng)
+        eng.train_step(_dev(t), (_dev(neg_ent), _dev(neg_keep)), step=step)
+        rs.train_step(t, _corruption_tensor(t, neg_ent, neg_keep, eta))
+        touched[t[:, 0]] = touched[t[:, 2]] = touched[neg_ent] = True
+        assert (eng.g_ent == 0).all()
+    got = _dense(eng, eng.ent)
+    assert _close(got, rs.ent.detach().numpy(), rtol=5e-4) and _close(_dense(eng, eng.rel), rs.rel.detach().numpy(), rtol=5e-4)
+    assert (~touched).sum() > 50 and (got[~touched] == ent[~touched]).all()
+    eng.close()
+
+
 def test_external_loss_two_phase():
     """LossFunctionWrapper path (loss_functions.py:657): scores out, dL/dscore back in."""
     rng = np.random.default_rng(19)
