@@ -46,6 +46,7 @@ def test_config_struct_matches_header():
     import ctypes as C
     from ampligraph_b200 import _lib
     assert C.sizeof(_lib.KgeConfig) == 64 and C.sizeof(_lib.KgeOptimizerConfig) == 40
+    assert C.sizeof(_lib.KgeShardMap) == 16 + 3 * 8 * 8  # kge_shard_map: header + ent[8] + grad_ent[8] + stamp_ent[8]
     bad = _lib.KgeConfig(12, 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0, 0, 0)
     h = C.c_void_p()
     assert _lib.load().kge_create(C.byref(bad), C.byref(h)) == _lib.KGE_ERR_INVALID_ARGUMENT  # ABI guard first
