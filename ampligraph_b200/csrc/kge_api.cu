@@ -18,7 +18,7 @@ struct kge_handle {
     float rot_div;      // RotatE range/pi
     float *rot;         // [n_rel, ld] rotation table workspace (RotatE)
     // training launch geometry
-    int nit, G, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats;
+    int nit, G, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats, resident;
     // ranking workspace (grown on demand)
     int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
     long long ws_b;
@@ -117,19 +117,25 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     // (one gather per row) while >= KGE_MIN_RESIDENT_WARPS warps still fit; otherwise shrink G until
     // min(max_warps, KGE_TARGET_WARPS) warps fit -- the gradient pass then re-gathers the other groups, which
     // costs less than running with few warps.  RotatE is measurably (1.5x) faster with an odd group size.
+    // non-resident slots hold TWO group buffers (the next group is prefetched while the current one is processed)
     int G = cfg->eta;
-    if (cfg->neg_group > 0) G = cfg->neg_group < cfg->eta ? cfg->neg_group : cfg->eta;
-    else {
+    bool res = h->n_cb == 1;
+    if (cfg->neg_group > 0) {
+        G = cfg->neg_group < cfg->eta ? cfg->neg_group : cfg->eta;
+        res = res && G >= cfg->eta;
+    } else {
         const long long full = (3 + (long long)cfg->eta) * row_bytes + aux;
         const int min_res = max_warps < KGE_MIN_RESIDENT_WARPS ? max_warps : KGE_MIN_RESIDENT_WARPS;
-        if (full * min_res > h->max_smem) {
+        if (!res || full * min_res > h->max_smem) {
+            res = false;
             const int want = max_warps < KGE_TARGET_WARPS ? max_warps : KGE_TARGET_WARPS;
-            while (G > 1 && (long long)((3 + G) * (long long)row_bytes + aux) * want > h->max_smem) --G;
+            while (G > 1 && (long long)((3 + 2 * G) * (long long)row_bytes + aux) * want > h->max_smem) --G;
             if (cfg->scoring == KGE_ROTATE && G > 1 && (G % 2) == 0) --G;
         }
     }
+    h->resident = res ? 1 : 0;
     h->G = G;
-    h->rows_bytes = (3 + G) * row_bytes;
+    h->rows_bytes = (res ? 3 + G : 3 + 2 * G) * row_bytes;
     h->region_bytes = h->rows_bytes + aux;
     if (cfg->reserved & 2) h->region_bytes = (h->region_bytes + 127) / 128 * 128;
     int warps = h->max_smem / h->region_bytes;
@@ -284,6 +290,7 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
     p.wk = h->wk;
     p.n_cb = h->n_cb;
     p.slot_floats = h->slot_floats;
+    p.resident = h->resident;
     p.eta_pad = h->eta_pad;
     p.rows_bytes = h->rows_bytes;
     p.region_bytes = h->region_bytes;

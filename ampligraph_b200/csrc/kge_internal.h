@@ -28,6 +28,7 @@ struct TrainParams {
     int G;                        // replaced rows resident per pass
     int wk, n_cb;                 // column window (floats per half) and number of windows per row
     int slot_floats;              // stride between row windows in the shared-memory slot
+    int resident;                 // 1: one window, one group, rows stay in place between the passes
     int eta_pad;                  // round_up(eta,4)
     int rows_bytes, region_bytes; // per-warp shared-memory carve-up
     int loss, reduction, mode;

@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
     int *nside = nid + p.eta_pad;
     uint64_t *bar = reinterpret_cast<uint64_t *>(nside + p.eta_pad);
 
-    if (lane == 0) mbar_init(bar, 1);
+    if (lane == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
     fence_mbar_init();
     fence_proxy_async_smem();
     __syncthreads();
@@ -711,38 +711,14 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
     const int n_cb = RESIDENT ? 1 : p.n_cb;    // column windows per row
     const int n_groups = RESIDENT ? 1 : (eta + G - 1) / G;
     constexpr bool resident = RESIDENT;
-    float *srow = rows, *prow = rows + lw, *orow = rows + 2 * lw, *nrows = rows + 3 * lw;
+    // slot: s, p, o windows, then group buffer 0 and (non-resident only) group buffer 1: the next group is
+    // gathered while the current one is being processed, which hides the gather latency (NVLink latency
+    // when the table is row-sharded over GPUs)
+    float *srow = rows, *prow = rows + lw, *orow = rows + 2 * lw;
+    auto nbuf = [&](int b) { return rows + (size_t)(3 + b * G) * lw; };
     const float scale = p.score_scale;  // HolE 2/k, else 1
-    uint32_t phase = 0;
+    uint32_t phase0 = 0u, phase1 = 0u;
     double loss_acc = 0.0;
-
-    // gather `cnt` row windows (rows given by src(r)) into consecutive slots starting at `dst`
-    auto gather = [&](float *dst, int cnt, int cb, auto src) {
-        const int wch_t = min(wk, kp - cb * wk);  // floats of this window per half
-        const uint32_t bytes = (n_cb == 1) ? (uint32_t)ld * 4u : (uint32_t)wch_t * 4u;
-        const int copies = (n_cb == 1) ? 1 : HALVES;
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * copies * bytes);
-        __syncwarp();
-        for (int r = lane; r < cnt * copies; r += 32) {
-            const int row = (copies == 1) ? r : r / HALVES, h = (copies == 1) ? 0 : r - row * HALVES;
-            bulk_load(dst + (size_t)row * lw + h * wk, src(row) + h * kp + cb * wk, bytes, bar);
-        }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-    };
-    // push `cnt` gradient row windows from shared memory into the gradient table (bulk scatter mode)
-    auto scatter = [&](float *srcw, int cnt, int cb, auto dst) {
-        const int wch_t = min(wk, kp - cb * wk);
-        const uint32_t bytes = (n_cb == 1) ? (uint32_t)ld * 4u : (uint32_t)wch_t * 4u;
-        const int copies = (n_cb == 1) ? 1 : HALVES;
-        fence_proxy_async_smem();
-        __syncwarp();
-        for (int r = lane; r < cnt * copies; r += 32) {
-            const int row = (copies == 1) ? r : r / HALVES, h = (copies == 1) ? 0 : r - row * HALVES;
-            bulk_reduce_add_f32(dst(row) + h * kp + cb * wk, srcw + (size_t)row * lw + h * wk, bytes);
-        }
-        bulk_commit();
-    };
 
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B; i += n_warps) {
@@ -764,26 +740,65 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
             if (lane == 2 && p.stamp_rel) p.stamp_rel[p_id] = p.stamp;
         }
         __syncwarp();
-        auto spo_src = [&](int r) { return r == 0 ? ent_row(p, s_id) : r == 1 ? p.rel + (size_t)p_id * ld : ent_row(p, o_id); };
-        float *const gs_row = gent_row(p, s_id), *const gp_row = p.grad_rel + (size_t)p_id * ld,
-                     *const go_row = gent_row(p, o_id);
+        float *const gs_row = gent_row(p, s_id), *const gp_row = p.grad_rel + (size_t)p_id * ld, *const go_row = gent_row(p, o_id);
+
+        // issue the gather of (optionally) the s,p,o windows and of group [j0, j0+gsz) into buffer `buf`:
+        // one 1-D bulk copy per row window, completion counted on the buffer's mbarrier
+        auto issue = [&](int buf, int cb, bool with_spo, int j0, int gsz) {
+            const int wch_t = min(wk, kp - cb * wk);  // floats of this window per half
+            const uint32_t bytes = (n_cb == 1) ? (uint32_t)ld * 4u : (uint32_t)wch_t * 4u;
+            const int copies = (n_cb == 1) ? 1 : HALVES;
+            const int nspo = with_spo ? 3 : 0, total = (nspo + gsz) * copies;
+            if (lane == 0) mbar_arrive_expect_tx(bar + buf, (uint32_t)total * bytes);
+            __syncwarp();
+            float *const gb = nbuf(buf);
+            for (int r = lane; r < total; r += 32) {
+                const int row = (copies == 1) ? r : r / HALVES, h = (copies == 1) ? 0 : r - row * HALVES;
+                const float *src;
+                float *dst;
+                if (row < nspo) {
+                    src = row == 0 ? ent_row(p, s_id) : row == 1 ? p.rel + (size_t)p_id * ld : ent_row(p, o_id);
+                    dst = rows + (size_t)row * lw;
+                } else {
+                    src = ent_row(p, nid[j0 + row - nspo]);
+                    dst = gb + (size_t)(row - nspo) * lw;
+                }
+                bulk_load(dst + h * wk, src + h * kp + cb * wk, bytes, bar + buf);
+            }
+        };
+        auto wait = [&](int buf) {
+            if (buf) { mbar_wait(bar + 1, phase1); phase1 ^= 1u; }
+            else { mbar_wait(bar, phase0); phase0 ^= 1u; }
+        };
+        // push `cnt` gradient row windows from shared memory into the gradient table (bulk scatter mode)
+        auto scatter = [&](float *srcw, int cnt, int cb, auto dst) {
+            const int wch_t = min(wk, kp - cb * wk);
+            const uint32_t bytes = (n_cb == 1) ? (uint32_t)ld * 4u : (uint32_t)wch_t * 4u;
+            const int copies = (n_cb == 1) ? 1 : HALVES;
+            fence_proxy_async_smem();
+            __syncwarp();
+            for (int r = lane; r < cnt * copies; r += 32) {
+                const int row = (copies == 1) ? r : r / HALVES, h = (copies == 1) ? 0 : r - row * HALVES;
+                bulk_reduce_add_f32(dst(row) + h * kp + cb * wk, srcw + (size_t)row * lw + h * wk, bytes);
+            }
+            bulk_commit();
+        };
 
         Scorer<MODEL, NIT> S;
         if constexpr (HALVES == 2) { S.kp = kp; S.hs = wk; }
         float P = 0.f;
 
-        // ---- pass A: scores, window by window, group by group (A2 + A4) ----
+        // ---- pass A: scores, window by window, group by group, next group prefetched (A2 + A4) ----
         for (int cb = 0; cb < n_cb; ++cb) {
             S.nch = min(wk, kp - cb * wk) / 4;
+            __syncwarp();
+            issue(0, cb, true, 0, min(G, eta));
             for (int g = 0; g < n_groups; ++g) {
-                const int j0 = g * G, gsz = min(G, eta - j0);
-                __syncwarp();
-                if (g == 0) {  // s, p, o windows + first group in one transaction
-                    gather(rows, 3 + gsz, cb, [&](int r) { return r < 3 ? spo_src(r) : ent_row(p, nid[r - 3]); });
-                    P += warp_sum(S.prep(srow, prow, orow, lane));
-                } else {
-                    gather(nrows, gsz, cb, [&](int r) { return ent_row(p, nid[j0 + r]); });
-                }
+                const int buf = g & 1, j0 = g * G, gsz = min(G, eta - j0);
+                if (g + 1 < n_groups) issue(buf ^ 1, cb, false, j0 + G, min(G, eta - j0 - G));
+                wait(buf);
+                if (g == 0) P += warp_sum(S.prep(srow, prow, orow, lane));
+                float *const nrows = nbuf(buf);
                 auto store = [&](int a, int b, bool has_b, float pa, float pb) {
                     if (lane == 0) {
                         if (resident) { sc[j0 + a] = pa; if (has_b) sc[j0 + b] = pb; }
@@ -804,9 +819,9 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                         warp_sum2(pa, pb);
                         store(a, b, has_b, pa, pb);
                     });
+                __syncwarp();
             }
         }
-        __syncwarp();
 
         // ---- loss and dL/dscore (A5) ----
         float dP;
@@ -831,33 +846,36 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
             S.nch = min(wk, kp - cb * wk) / 4;
             const int gofs = cb * wk;  // column offset of this window inside a gradient row
             for (int g = n_groups - 1; g >= 0; --g) {
-                const int j0 = g * G, gsz = min(G, eta - j0);
-                const bool still_there = (cb == n_cb - 1 && g == n_groups - 1);
-                if (!still_there) {
+                const int buf = g & 1, j0 = g * G, gsz = min(G, eta - j0);
+                const bool top = (g == n_groups - 1);
+                const bool still_there = (cb == n_cb - 1 && top);  // left in place by pass A
+                if (top && !still_there) {  // first visit of this window: s, p, o come along, state is rebuilt
                     if (!Sink::kDirect) bulk_wait_read_all();  // copy engine done reading what we overwrite
                     __syncwarp();
-                    if (g == n_groups - 1) {  // first visit of this window: s, p, o come along and state is rebuilt
-                        gather(rows, 3 + gsz, cb, [&](int r) { return r < 3 ? spo_src(r) : ent_row(p, nid[j0 + r - 3]); });
-                        (void)S.prep(srow, prow, orow, lane);
-                    } else {
-                        gather(nrows, gsz, cb, [&](int r) { return ent_row(p, nid[j0 + r]); });
-                    }
+                    issue(buf, cb, true, j0, gsz);
                 }
+                if (g > 0) {  // prefetch the next (lower) group into the other buffer
+                    if (!Sink::kDirect) bulk_wait_read_all();
+                    __syncwarp();
+                    issue(buf ^ 1, cb, false, j0 - G, G);
+                }
+                if (!still_there) wait(buf);
+                if (top && !still_there) (void)S.prep(srow, prow, orow, lane);
+                float *const nrows = nbuf(buf);
                 for_each_pair_by_side(
                     nside + j0, gsz, lane,
                     [&](int a, int b, bool has_b) {
                         S.template grad2<0, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw,
-                                                  gent_row(p, nid[j0 + a]) + gofs,
-                                                  gent_row(p, nid[j0 + b]) + gofs, scale * sc[j0 + a],
-                                                  has_b ? scale * sc[j0 + b] : 0.f, has_b);
+                                                  gent_row(p, nid[j0 + a]) + gofs, gent_row(p, nid[j0 + b]) + gofs,
+                                                  scale * sc[j0 + a], has_b ? scale * sc[j0 + b] : 0.f, has_b);
                     },
                     [&](int a, int b, bool has_b) {
                         S.template grad2<1, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw,
-                                                  gent_row(p, nid[j0 + a]) + gofs,
-                                                  gent_row(p, nid[j0 + b]) + gofs, scale * sc[j0 + a],
-                                                  has_b ? scale * sc[j0 + b] : 0.f, has_b);
+                                                  gent_row(p, nid[j0 + a]) + gofs, gent_row(p, nid[j0 + b]) + gofs,
+                                                  scale * sc[j0 + a], has_b ? scale * sc[j0 + b] : 0.f, has_b);
                     });
                 if (!Sink::kDirect) scatter(nrows, gsz, cb, [&](int r) { return gent_row(p, nid[j0 + r]); });
+                __syncwarp();
             }
             S.template finish<Sink>(srow, prow, orow, gs_row + gofs, gp_row + gofs, go_row + gofs, scale * dP, p.inv_div);
             if (!Sink::kDirect) scatter(rows, 3, cb, [&](int r) { return r == 0 ? gs_row : r == 1 ? gp_row : go_row; });
@@ -912,7 +930,7 @@ static cudaError_t launch_train_model(const TrainParams &p, int nit, int sm_coun
 {
 #define KGE_LAUNCH(N)                                                                                       \
     {                                                                                                       \
-        const bool res = p.n_cb == 1 && p.G >= p.eta;                                                       \
+        const bool res = p.resident != 0;                                                                   \
         auto kern = p.scatter_mode == KGE_SCATTER_RED_V4                                                    \
                         ? (res ? kge_train_kernel<MODEL, N, SinkRed, true> : kge_train_kernel<MODEL, N, SinkRed, false>)   \
                         : (res ? kge_train_kernel<MODEL, N, SinkSmem, true> : kge_train_kernel<MODEL, N, SinkSmem, false>); \

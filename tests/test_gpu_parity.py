@@ -180,6 +180,35 @@ def test_forward_backward_baseline_shapes(model, k, eta, B):
     eng.close()
 
 
+@pytest.mark.parametrize("model,loss,eta,B", [("ComplEx", "self_adversarial", 40, 37), ("TransE", "multiclass_nll", 70, 9),
+                                              ("RotatE", "self_adversarial", 33, 21), ("DistMult", "nll", 1, 1),
+                                              ("HolE", "pairwise", 1, 300)])
+def test_edge_shapes_eta_over_32_and_tiny_batches(model, loss, eta, B):
+    """eta > 32 (several corruptions per lane in the loss, more than one ballot word), eta = 1, B = 1."""
+    rng = np.random.default_rng(47)
+    E, R, k = 90, 3, 10
+    ent, rel = _tables(model, E, R, k, rng, scale=0.4)
+    t = _triples(E, R, B, rng)
+    neg_ent, neg_keep = _negatives(E, B, eta, rng)
+    eng = _engine(model, k, eta, E, R, loss=loss)
+    eng.set_embeddings(ent, rel)
+    sn = torch.empty(B * eta, device="cuda")
+    sp = torch.empty(B, device="cuda")
+    eng.forward_backward(_dev(t), (_dev(neg_ent), _dev(neg_keep)), scores_pos=sp, scores_neg=sn)
+    rs = _ref(model, k, ent, rel, eta, loss, {})
+    rl, rsp, rsn, g_ent, g_rel = rs.loss_and_grads(t, _corruption_tensor(t, neg_ent, neg_keep, eta))
+    assert np.allclose(sn.cpu().numpy(), rsn.numpy(), rtol=RTOL, atol=1e-5)
+    assert abs(eng.read_loss() - float(rl)) <= RTOL * abs(float(rl)) + 1e-5
+    assert _close(_dense(eng, eng.g_ent), g_ent.numpy()) and _close(_dense(eng, eng.g_rel), g_rel.numpy())
+    # an empty batch is a no-op
+    eng.g_ent.zero_(); eng.g_rel.zero_()
+    eng.forward_backward(torch.empty((0, 3), dtype=torch.int32, device="cuda"), None)
+    assert eng.read_loss() == 0 and (eng.g_ent == 0).all()
+    assert eng.score(torch.empty((0, 3), dtype=torch.int32, device="cuda")).numel() == 0
+    assert eng.rank(torch.empty((0, 3), dtype=torch.int32, device="cuda"), "s").numel() == 0
+    eng.close()
+
+
 @pytest.mark.parametrize("model,k", [("TransE", 600), ("DistMult", 1100), ("ComplEx", 520), ("HolE", 1000), ("RotatE", 700)])
 @pytest.mark.parametrize("group", [0, 3])
 def test_wide_rows_column_windows(model, k, group):
