@@ -216,9 +216,17 @@ class ShardedTrainer:
         dist.all_gather(parts, ent.contiguous(), group=self.group)
         return torch.cat(parts)[:self.n_ent].cpu(), rel.cpu()
 
-    def train_step(self, batch, negatives=None, seed=0, step=0):
+    def train_step(self, batch, negatives=None, seed=0, step=0, events=None):
+        """events: optional list; receives 5 CUDA events (start, kernel done, barrier 0 done, optimizers done,
+        barrier 1 done) so a benchmark can attribute the step time."""
         C, _lib, eng = self._C, self._lib, self.eng
         B = batch.shape[0]
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append(e)
+        mark()
         neg_ent = neg_keep = None
         if negatives is not None:
             neg_ent, neg_keep = negatives
@@ -227,7 +235,9 @@ class ShardedTrainer:
         _lib.check(eng.lib.kge_train_step_sharded(
             eng.h, _lib.STEP_FUSED, C.byref(self.map), p(eng.rel), p(eng.g_rel), p(batch), B, p(neg_ent), p(neg_keep),
             int(seed), int(step), p(eng.loss_acc), None, None, None, None, st))
+        mark()
         self.hdl.barrier(channel=0)  # every rank's scatters (into my shard too) and relation gradients are complete
+        mark()
         eng.t += 1
         s0, s1 = eng.slots["ent"]
         if self.lazy:
@@ -242,8 +252,10 @@ class ShardedTrainer:
         _lib.check(eng.lib.kge_optimizer_step_sharded(
             eng.h, C.byref(eng.opt_cfg), eng.t, self.world, self.rank, self._rel_ptrs, self._grel_ptrs, p(r0), p(r1),
             lo, hi, C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
+        mark()
         self.hdl.barrier(channel=1)  # all shards updated, relation rows delivered, my relation gradients consumed
         eng.g_rel.zero_()
+        mark()
         eng.launches += 4
 
     def rank_counts(self, triples, side, strategy="worst", filt_off=None, filt_idx=None):

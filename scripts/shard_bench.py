@@ -53,6 +53,13 @@ torch.cuda.synchronize(); dist.barrier()
 t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 ms = t.item() / a.steps
+# attribution of one step (separate pass, events between the phases)
+evs = []
+for i in range(3):
+    evs = []
+    tr.train_step(batches[i % nb], None, seed=7 + rank, step=1000 + i, events=evs)
+torch.cuda.synchronize()
+phases = [round(evs[j].elapsed_time(evs[j + 1]), 3) for j in range(4)]
 ld = tr.eng.ld
 alg = 2 * (3 + eta) * ld * 4 * B  # per rank per step
 # ranking: 1024 test triples, both sides, against ALL entities (each rank its shard, counts summed)
@@ -73,6 +80,7 @@ if rank == 0:
            "triples_per_s": round(world * B * (1 + eta) / (ms / 1e3)), "alg_GBps_per_gpu": round(alg / (ms / 1e3) / 1e9, 1),
            "nvlink_rows_GB_per_gpu_per_step_each_way": round((3 + eta) * B * ld * 4 * (world - 1) / world / 1e9, 3),
            "rank_1024x2sides_ms": round(tr_ms.item(), 2), "rank_Gscores_per_s": round(2 * 1024 * E / (tr_ms.item() / 1e3) / 1e9, 1),
+           "rank0_phase_ms[kernel,barrier0,optimizers,barrier1]": phases, "G": None,
            "loss": tr.eng.read_loss()}, flush=True)
 tr.close()
 dist.destroy_process_group()
