@@ -19,6 +19,7 @@ struct kge_handle {
     float *rot;         // [n_rel, ld] rotation table workspace (RotatE)
     // training launch geometry
     int nit, G, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats, resident;
+    int team, team_nit, team_region, team_count;
     // ranking workspace (grown on demand)
     int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
     long long ws_b;
@@ -134,6 +135,22 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
         }
     }
     h->resident = res ? 1 : 0;
+    // team mode (kge_config.reserved bit 2, experiment): two warps per positive share one slot
+    h->team = 0;
+    if ((cfg->reserved & 4) && res && cfg->scatter_mode == KGE_SCATTER_RED_V4 && cfg->scoring != KGE_ROTATE &&
+        (nch + 63) / 64 <= 2) {
+        const int tnit_raw = (nch + 63) / 64;
+        const int tnit = tnit_raw <= 1 ? 1 : tnit_raw <= 2 ? 2 : 4;
+        const int tregion = (3 + cfg->eta) * row_bytes + 2 * (3 * h->eta_pad * 4) + 2 * (h->eta_pad + 4) * 4 + 16;
+        int teams = h->max_smem / tregion;
+        if (teams > KGE_TEAM_THREADS / 64) teams = KGE_TEAM_THREADS / 64;
+        if (teams >= 2) {
+            h->team = 1;
+            h->team_nit = tnit;
+            h->team_region = tregion;
+            h->team_count = teams;
+        }
+    }
     h->G = G;
     h->rows_bytes = (res ? 3 + G : 3 + 2 * G) * row_bytes;
     h->region_bytes = h->rows_bytes + aux;
@@ -319,6 +336,13 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
             p.stamp_ent_shard[q] = map->stamp_ent[q];
             if (!map->stamp_ent[q]) p.stamp_ent = nullptr;  // all or nothing
         }
+    }
+    if (h->team && !(map && map->world > 1)) {
+        p.team = 1;
+        p.region_bytes = h->team_region;
+        KGE_CUDA(launch_train(p, h->team_nit, h->sm_count, h->team_count * 64, (size_t)h->team_count * h->team_region, st),
+                 "kge_train_step(team)");
+        return KGE_OK;
     }
     KGE_CUDA(launch_train(p, h->nit, h->sm_count, h->warps * 32, (size_t)h->warps * h->region_bytes, st),
              "kge_train_step");

@@ -10,6 +10,7 @@
 #define KGE_MAX_PEERS 8
 #define KGE_MIN_RESIDENT_WARPS 8  // tuned on B200: fewer warps/SM than this costs more than re-gathering
 #define KGE_TARGET_WARPS 10
+#define KGE_TEAM_THREADS 640  // team kernel: up to 10 teams of 2 warps (register cap 96/thread)
 
 namespace kge {
 
@@ -29,6 +30,7 @@ struct TrainParams {
     int wk, n_cb;                 // column window (floats per half) and number of windows per row
     int slot_floats;              // stride between row windows in the shared-memory slot
     int resident;                 // 1: one window, one group, rows stay in place between the passes
+    int team;                     // 1: two warps per positive (kge_train_team_kernel), resident + red.v4 only
     int eta_pad;                  // round_up(eta,4)
     int rows_bytes, region_bytes; // per-warp shared-memory carve-up
     int loss, reduction, mode;

@@ -138,14 +138,14 @@ struct Scorer;
 template <int NIT>
 struct Scorer<KGE_DISTMULT, NIT> {
     float4 A[NIT], C[NIT], Ws[NIT], Wo[NIT];
-    int lane, nch;
+    int lane, nch, cs = 32;  // cs: chunk stride = lanes cooperating on one positive
     __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
         float4 acc = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             float4 vs = f4zero(), vp = f4zero(), vo = f4zero();
             if (c < nch) { vs = f4ld(s + 4 * c); vp = f4ld(p + 4 * c); vo = f4ld(o + 4 * c); }
             A[it] = vp * vo;
@@ -162,7 +162,7 @@ struct Scorer<KGE_DISTMULT, NIT> {
         float4 a = f4zero(), b = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 const float4 q = SIDE ? C[it] : A[it];
                 a = f4fma(f4ld(ra + 4 * c), q, a);
@@ -178,7 +178,7 @@ struct Scorer<KGE_DISTMULT, NIT> {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 float4 va = f4ld(ra + 4 * c), vb = f4ld(rb + 4 * c);
                 const float4 q = SIDE ? C[it] : A[it];
@@ -196,7 +196,7 @@ struct Scorer<KGE_DISTMULT, NIT> {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 float4 vs = f4ld(s + 4 * c), vp = f4ld(p + 4 * c), vo = f4ld(o + 4 * c);
                 float4 U = f4fma(gP, vs, Ws[it]);  // everything that sat in the subject slot
@@ -216,14 +216,14 @@ template <int NIT>
 struct ComplexScorer {
     float4 A[NIT], Bv[NIT], C[NIT], D[NIT];          // subject-side / object-side query vectors
     float4 Wsr[NIT], Wsi[NIT], Wor[NIT], Woi[NIT];   // sum_j g_j r_j per side (re, im)
-    int lane, nch, kp, hs;  // kp: half stride in HBM rows, hs: half stride of the staged row window
+    int lane, nch, cs = 32, kp, hs;  // cs: chunk stride = lanes on one positive; kp: half stride in HBM rows, hs: half stride of the staged row window
     __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
         float4 acc = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             float4 sr = f4zero(), si = f4zero(), pr = f4zero(), pi = f4zero(), orr = f4zero(), oi = f4zero();
             if (c < nch) {
                 sr = f4ld(s + 4 * c); si = f4ld(s + hs + 4 * c);
@@ -246,7 +246,7 @@ struct ComplexScorer {
         float4 a = f4zero(), b = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
                 a = f4fma(f4ld(ra + 4 * c), qr, a);
@@ -264,7 +264,7 @@ struct ComplexScorer {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + hs + 4 * c);
                 float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + hs + 4 * c);
@@ -288,7 +288,7 @@ struct ComplexScorer {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 float4 sr = f4ld(s + 4 * c), si = f4ld(s + hs + 4 * c);
                 float4 pr = f4ld(p + 4 * c), pi = f4ld(p + hs + 4 * c);
@@ -315,14 +315,14 @@ template <int NIT> struct Scorer<KGE_HOLE, NIT> : ComplexScorer<NIT> {};
 template <int NIT>
 struct Scorer<KGE_TRANSE, NIT> {
     float4 Qs[NIT], Qo[NIT], Vs[NIT], Vo[NIT];  // p-o, s+p, sum g*sign per side
-    int lane, nch;
+    int lane, nch, cs = 32;  // cs: chunk stride = lanes cooperating on one positive
     __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
         float acc = 0.f;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             float4 vs = f4zero(), vp = f4zero(), vo = f4zero();
             if (c < nch) { vs = f4ld(s + 4 * c); vp = f4ld(p + 4 * c); vo = f4ld(o + 4 * c); }
             Qs[it] = vp - vo;
@@ -338,7 +338,7 @@ struct Scorer<KGE_TRANSE, NIT> {
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 float4 va = f4ld(ra + 4 * c), vb = f4ld(rb + 4 * c);
                 a -= f4abssum(SIDE ? (Qo[it] - va) : (va + Qs[it]));
@@ -354,7 +354,7 @@ struct Scorer<KGE_TRANSE, NIT> {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 float4 va = f4ld(ra + 4 * c), vb = f4ld(rb + 4 * c);
                 // SIDE 1: t = (s+p) - r, df/dr = +sign(t);  SIDE 0: t = r + (p-o), df/dr = -sign(t)
@@ -373,7 +373,7 @@ struct Scorer<KGE_TRANSE, NIT> {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 float4 vo = f4ld(o + 4 * c);
                 float4 Vp = gP * f4sgn(Qo[it] - vo);
@@ -395,7 +395,7 @@ template <int NIT>
 struct Scorer<KGE_ROTATE, NIT> {
     float4 Cs[NIT], Sn[NIT], Yr[NIT], Yi[NIT], Or_[NIT], Oi[NIT];
     float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], Aphi[NIT];
-    int lane, nch, kp, hs;  // kp: half stride in HBM rows, hs: half stride of the staged row window
+    int lane, nch, cs = 32, kp, hs;  // cs: chunk stride = lanes on one positive; kp: half stride in HBM rows, hs: half stride of the staged row window
     static __device__ __forceinline__ void unit(float4 re, float4 im, float g, float4 &a, float4 &b)
     {
         float m0 = sqrtf(fmaf(im.x, im.x, re.x * re.x)), m1 = sqrtf(fmaf(im.y, im.y, re.y * re.y));
@@ -411,7 +411,7 @@ struct Scorer<KGE_ROTATE, NIT> {
         float acc = 0.f;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             float4 sr = f4zero(), si = f4zero();
             Cs[it] = Sn[it] = Or_[it] = Oi[it] = f4zero();
             if (c < nch) {
@@ -432,7 +432,7 @@ struct Scorer<KGE_ROTATE, NIT> {
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + hs + 4 * c);
                 float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + hs + 4 * c);
@@ -473,7 +473,7 @@ struct Scorer<KGE_ROTATE, NIT> {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 grad1<SIDE, Sink>(ra, ga_row, ga, it, c, true);
                 grad1<SIDE, Sink>(rb, gb_row, gb, it, c, has_b);  // gb == 0 when !has_b: contributes nothing
@@ -488,7 +488,7 @@ struct Scorer<KGE_ROTATE, NIT> {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + 32 * it;
+            int c = lane + cs * it;
             if (c < nch) {
                 float4 a, b;
                 unit(Yr[it] - Or_[it], Yi[it] - Oi[it], gP, a, b);
@@ -888,6 +888,142 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
 }
 
 // --------------------------------------------------------------------------
+// Team variant of the resident kernel: TWO warps own one positive and split its columns (chunk
+// stride 64), sharing one shared-memory slot.  Shared memory (13 rows per positive for cfg2) is what
+// limits residency, so two warps per slot double the warps per SM at the same footprint (20 instead
+// of 11 for cfg2) and halve the per-lane register state.  Cost: partial scores are exchanged through
+// shared memory (one 64-thread named barrier) and the per-positive prologue / loss is executed by both
+// warps.  red.v4 scatter only.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void team_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int MODEL, int NIT>
+__global__ void __launch_bounds__(KGE_TEAM_THREADS) kge_train_team_kernel(const TrainParams p)
+{
+    constexpr int WPP = 2;
+    using Sink = SinkRed;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int team = warp / WPP, tw = warp % WPP, tlane = tw * 32 + lane;
+    const int n_teams = (blockDim.x >> 5) / WPP;
+    unsigned char *region = smem_raw + (size_t)team * p.region_bytes;
+    float *rows = reinterpret_cast<float *>(region);                          // (3+eta) rows, shared by the team
+    unsigned char *aux = region + p.rows_bytes + (size_t)tw * (3 * p.eta_pad * 4);
+    float *sc = reinterpret_cast<float *>(aux);                               // per warp: scores / dL/dscore
+    int *nid = reinterpret_cast<int *>(sc + p.eta_pad);
+    int *nside = nid + p.eta_pad;
+    float *part = reinterpret_cast<float *>(region + p.rows_bytes + (size_t)WPP * (3 * p.eta_pad * 4));  // [WPP][eta_pad+4]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(part + WPP * (p.eta_pad + 4));
+    const int pstride = p.eta_pad + 4;
+
+    if (tw == 0 && lane == 0) mbar_init(bar, 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    const int ld = p.ld, eta = p.eta, lw = p.slot_floats;
+    const uint32_t row_bytes = (uint32_t)ld * 4u;
+    float *srow = rows, *prow = rows + lw, *orow = rows + 2 * lw, *nrows = rows + 3 * lw;
+    const float scale = p.score_scale;
+    uint32_t phase = 0;
+    double loss_acc = 0.0;
+
+    const long long stride = (long long)gridDim.x * n_teams;
+    for (long long i = (long long)blockIdx.x * n_teams + team; i < p.B; i += stride) {
+        const int s_id = p.triples[3 * i], p_id = p.triples[3 * i + 1], o_id = p.triples[3 * i + 2];
+        for (int j = lane; j < eta; j += 32) {  // both warps draw the same corruptions into their own copies
+            int keep, repl;
+            const unsigned long long r = (unsigned long long)j * (unsigned long long)p.B + (unsigned long long)i;
+            if (p.neg_ent) { repl = p.neg_ent[r]; keep = p.neg_keep[r] ? 1 : 0; }
+            else draw_corruption(p.seed, p.step, r, p.n_ent, &keep, &repl);
+            nid[j] = repl;
+            nside[j] = keep;
+            if (tw == 0 && p.stamp_ent && p.mode != KGE_STEP_FORWARD_ONLY) stamp_ent_row(p, repl);
+        }
+        if (tw == 0 && p.stamp_ent && p.mode != KGE_STEP_FORWARD_ONLY) {
+            if (lane == 0) stamp_ent_row(p, s_id);
+            if (lane == 1) stamp_ent_row(p, o_id);
+            if (lane == 2 && p.stamp_rel) p.stamp_rel[p_id] = p.stamp;
+        }
+        __syncwarp();
+        team_sync(team + 1, WPP * 32);  // the whole team is done with the previous positive's rows
+        if (tw == 0) {
+            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(3 + eta) * row_bytes);
+            __syncwarp();
+            for (int r = lane; r < 3 + eta; r += 32) {
+                const float *src = r == 0 ? ent_row(p, s_id) : r == 1 ? p.rel + (size_t)p_id * ld : r == 2 ? ent_row(p, o_id)
+                                                                                                        : ent_row(p, nid[r - 3]);
+                bulk_load(rows + (size_t)r * lw, src, row_bytes, bar);
+            }
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+
+        Scorer<MODEL, NIT> S;
+        S.nch = p.nch;
+        S.cs = 32 * WPP;
+        if constexpr (MODEL != KGE_TRANSE && MODEL != KGE_DISTMULT) { S.kp = p.kp; S.hs = p.kp; }
+        float *mine = part + tw * pstride;
+        {
+            const float pp = warp_sum(S.prep(srow, prow, orow, tlane));
+            if (lane == 0) mine[eta] = pp;
+        }
+        for_each_pair_by_side(
+            nside, eta, lane,
+            [&](int a, int b, bool has_b) {
+                float pa, pb;
+                S.template partial2<0>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
+                warp_sum2(pa, pb);
+                if (lane == 0) { mine[a] = pa; if (has_b) mine[b] = pb; }
+            },
+            [&](int a, int b, bool has_b) {
+                float pa, pb;
+                S.template partial2<1>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
+                warp_sum2(pa, pb);
+                if (lane == 0) { mine[a] = pa; if (has_b) mine[b] = pb; }
+            });
+        team_sync(team + 1, WPP * 32);  // partial scores of both column halves are in shared memory
+        const float P = part[eta] + part[pstride + eta];
+        for (int j = lane; j < eta; j += 32) sc[j] = scale * (part[j] + part[pstride + j]);
+        __syncwarp();
+
+        float dP;
+        if (p.mode != KGE_STEP_BACKWARD_EXT) {
+            if (tw == 0) {
+                if (p.scores_neg)
+                    for (int j = lane; j < eta; j += 32) p.scores_neg[(size_t)j * p.B + i] = sc[j];
+                if (p.scores_pos && lane == 0) p.scores_pos[i] = scale * P;
+            }
+            if (p.mode == KGE_STEP_FORWARD_ONLY) { __syncwarp(); continue; }
+            float li = loss_and_dscores(p, scale * P, sc, lane, &dP);
+            if (tw == 0 && lane == 0) loss_acc += (double)li;
+        } else {
+            for (int j = lane; j < eta; j += 32) sc[j] = p.dneg[(size_t)j * p.B + i];
+            dP = p.dpos[i];
+        }
+        __syncwarp();
+
+        for_each_pair_by_side(
+            nside, eta, lane,
+            [&](int a, int b, bool has_b) {
+                S.template grad2<0, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, gent_row(p, nid[a]), gent_row(p, nid[b]),
+                                          scale * sc[a], has_b ? scale * sc[b] : 0.f, has_b);
+            },
+            [&](int a, int b, bool has_b) {
+                S.template grad2<1, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, gent_row(p, nid[a]), gent_row(p, nid[b]),
+                                          scale * sc[a], has_b ? scale * sc[b] : 0.f, has_b);
+            });
+        S.template finish<Sink>(srow, prow, orow, gent_row(p, s_id), p.grad_rel + (size_t)p_id * ld, gent_row(p, o_id),
+                                scale * dP, p.inv_div);
+        __syncwarp();
+    }
+    if (p.loss_out && p.mode == KGE_STEP_FUSED && tw == 0 && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_out, loss_acc);
+}
+
+// --------------------------------------------------------------------------
 // RotatE rotation table: rot[r] = [cos(theta/div) | sin(theta/div)] (RotatE.py:96-98),
 // canonical sin/cos so that training, predict and ranking agree bit for bit.
 // --------------------------------------------------------------------------
@@ -930,6 +1066,15 @@ static cudaError_t launch_train_model(const TrainParams &p, int nit, int sm_coun
 {
 #define KGE_LAUNCH(N)                                                                                       \
     {                                                                                                       \
+        if (p.team) {                                                                                       \
+            auto tk = kge_train_team_kernel<MODEL, N>;                                                      \
+            cudaError_t e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                 \
+            long long want = (p.B + (threads / 64) - 1) / (threads / 64);                                   \
+            int grid = (int)(want < (long long)sm_count ? want : (long long)sm_count);                       \
+            tk<<<grid, threads, smem, st>>>(p);                                                             \
+            return cudaGetLastError();                                                                      \
+        }                                                                                                   \
         const bool res = p.resident != 0;                                                                   \
         auto kern = p.scatter_mode == KGE_SCATTER_RED_V4                                                    \
                         ? (res ? kge_train_kernel<MODEL, N, SinkRed, true> : kge_train_kernel<MODEL, N, SinkRed, false>)   \
