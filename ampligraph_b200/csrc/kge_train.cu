@@ -107,9 +107,14 @@ struct SinkSmem {
     static constexpr bool kDirect = false;
     static __device__ __forceinline__ void put(float *slot, float *, int soff, int, float4 v) { f4st(slot + soff, v); }
 };
+__device__ __constant__ int g_debug_noscatter = 0;  // profiling aid (kge_config.reserved bit 3): drop the gradient scatter
 struct SinkRed {
     static constexpr bool kDirect = true;
-    static __device__ __forceinline__ void put(float *, float *grow, int, int goff, float4 v) { red_add_v4(grow + goff, v); }
+    static __device__ __forceinline__ void put(float *, float *grow, int, int goff, float4 v)
+    {
+        if (g_debug_noscatter) { if (v.x == 1.2345e38f) red_add_v4(grow + goff, v); return; }  // keeps v live
+        red_add_v4(grow + goff, v);
+    }
 };
 
 __device__ __forceinline__ float f4mod_sum(float4 re, float4 im)
@@ -1099,6 +1104,8 @@ static cudaError_t launch_train_model(const TrainParams &p, int nit, int sm_coun
     }
 #undef KGE_LAUNCH
 }
+
+cudaError_t set_debug_noscatter(int v) { return cudaMemcpyToSymbol(g_debug_noscatter, &v, sizeof(int)); }
 
 cudaError_t launch_train(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st)
 {
