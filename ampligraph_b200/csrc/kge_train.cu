@@ -117,10 +117,17 @@ struct SinkRed {
     }
 };
 
+// |z| = x * rsqrt(x), x = re^2 + im^2: one MUFU.RSQ instead of an IEEE sqrt (and, in the gradient, instead of
+// sqrt + divide).  rsqrtf is accurate to 2 ulp, far inside the 1e-4 training tolerance; the RANKING kernels keep
+// the correctly rounded sqrt because their scores must be bit-identical to the oracle.
+__device__ __forceinline__ float fast_mod(float re, float im)
+{
+    const float x = fmaf(im, im, re * re);
+    return x > 0.f ? x * rsqrtf(x) : 0.f;
+}
 __device__ __forceinline__ float f4mod_sum(float4 re, float4 im)
 {
-    return (sqrtf(fmaf(im.x, im.x, re.x * re.x)) + sqrtf(fmaf(im.y, im.y, re.y * re.y))) +
-           (sqrtf(fmaf(im.z, im.z, re.z * re.z)) + sqrtf(fmaf(im.w, im.w, re.w * re.w)));
+    return (fast_mod(re.x, im.x) + fast_mod(re.y, im.y)) + (fast_mod(re.z, im.z) + fast_mod(re.w, im.w));
 }
 
 // --------------------------------------------------------------------------
@@ -401,12 +408,13 @@ struct Scorer<KGE_ROTATE, NIT> {
     float4 Cs[NIT], Sn[NIT], Yr[NIT], Yi[NIT], Or_[NIT], Oi[NIT];
     float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], Aphi[NIT];
     int lane, nch, cs = 32, kp, hs;  // cs: chunk stride = lanes on one positive; kp: half stride in HBM rows, hs: half stride of the staged row window
+    // (a, b) = g * residual / |residual|, zero where the residual is exactly zero
     static __device__ __forceinline__ void unit(float4 re, float4 im, float g, float4 &a, float4 &b)
     {
-        float m0 = sqrtf(fmaf(im.x, im.x, re.x * re.x)), m1 = sqrtf(fmaf(im.y, im.y, re.y * re.y));
-        float m2 = sqrtf(fmaf(im.z, im.z, re.z * re.z)), m3 = sqrtf(fmaf(im.w, im.w, re.w * re.w));
-        float i0 = m0 > 0.f ? g / m0 : 0.f, i1 = m1 > 0.f ? g / m1 : 0.f;
-        float i2 = m2 > 0.f ? g / m2 : 0.f, i3 = m3 > 0.f ? g / m3 : 0.f;
+        const float x0 = fmaf(im.x, im.x, re.x * re.x), x1 = fmaf(im.y, im.y, re.y * re.y);
+        const float x2 = fmaf(im.z, im.z, re.z * re.z), x3 = fmaf(im.w, im.w, re.w * re.w);
+        const float i0 = x0 > 0.f ? g * rsqrtf(x0) : 0.f, i1 = x1 > 0.f ? g * rsqrtf(x1) : 0.f;
+        const float i2 = x2 > 0.f ? g * rsqrtf(x2) : 0.f, i3 = x3 > 0.f ? g * rsqrtf(x3) : 0.f;
         a = make_float4(re.x * i0, re.y * i1, re.z * i2, re.w * i3);
         b = make_float4(im.x * i0, im.y * i1, im.z * i2, im.w * i3);
     }
