@@ -22,6 +22,8 @@ struct kge_handle {
     int team, team_nit, team_region, team_count;
     // ranking workspace (grown on demand)
     int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
+    float *stash;                // caller-owned row stash for sharded runs (kge_set_row_stash) or nullptr
+    long long stash_rows;
     long long ws_b;
     float *ws_q;      // 3 * ws_b * ld floats: qvec_s | qvec_o | qaux
     int32_t *ws_i;    // 4 * ws_b ints: qpos | cnt[3]
@@ -328,6 +330,7 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
     p.stamp = (int)(step & 0x3fffffffu) + 1;
     p.stamp_ent = h->stamp_ent;
     p.stamp_rel = h->stamp_rel;
+    p.stash = (h->stash && h->stash_rows >= B * (int64_t)h->cfg.eta) ? h->stash : nullptr;
     if (map && map->world > 1) {
         p.shard_world = map->world;
         p.rows_per_shard = (int)map->rows_per_shard;
@@ -418,6 +421,17 @@ extern "C" int kge_set_row_stamps(kge_handle *h, int32_t *ent_stamps_dev, int32_
     KGE_CHECK_HANDLE(h, "kge_set_row_stamps");
     h->stamp_ent = ent_stamps_dev;
     h->stamp_rel = rel_stamps_dev;
+    return KGE_OK;
+}
+
+extern "C" int kge_rows_resident(const kge_handle *h) { return h ? (h->resident ? 1 : 0) : -1; }
+
+extern "C" int kge_set_row_stash(kge_handle *h, float *stash_dev, int64_t rows)
+{
+    KGE_CHECK_HANDLE(h, "kge_set_row_stash");
+    if (rows < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_set_row_stash: rows < 0");
+    h->stash = stash_dev;
+    h->stash_rows = stash_dev ? rows : 0;
     return KGE_OK;
 }
 

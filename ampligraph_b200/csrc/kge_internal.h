@@ -2,11 +2,9 @@
 #pragma once
 #include "kge_common.cuh"
 
-#define KGE_TRAIN_MAX_THREADS 512
 // per-lane register state grows with NIT (float4 chunks per lane): trade threads for registers
 // (RotatE carries 11 float4 vectors of per-positive state per chunk: give it more registers)
 #define KGE_TRAIN_THREADS(model, nit) ((nit) <= 1 ? 512 : (nit) == 2 ? ((model) == KGE_ROTATE ? 256 : 384) : 256)
-#define KGE_MAX_SMEM_PER_CTA (227 * 1024)
 #define KGE_MAX_PEERS 8
 #define KGE_MIN_RESIDENT_WARPS 8  // tuned on B200: fewer warps/SM than this costs more than re-gathering
 #define KGE_TARGET_WARPS 10
@@ -47,6 +45,7 @@ struct TrainParams {
     int stamp;
     int *stamp_ent, *stamp_rel;
     int *stamp_ent_shard[KGE_MAX_PEERS];
+    float *stash;  // [B, eta, ld] local copy of the replaced rows gathered by the score pass (sharded runs) or nullptr
 };
 
 // grid = min(occupancy * sm_count, ceil(B / warps))
@@ -73,7 +72,6 @@ struct OptimParams {
 };
 cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
                              long long n_floats, double *reg_loss, int sm_count, cudaStream_t st);
-cudaError_t launch_fill(float *p, long long n, float v, cudaStream_t st);
 cudaError_t launch_optimizer_lazy(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
                                   long long rows, int ld, const int *row_stamp, int stamp, double *reg_loss,
                                   int sm_count, cudaStream_t st);

@@ -254,19 +254,6 @@ cudaError_t launch_optimizer_lazy(const OptimParams &o, float *table, float *gra
     return cudaGetLastError();
 }
 
-__global__ void kge_fill_kernel(float *p, long long n, float v)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
-cudaError_t launch_fill(float *p, long long n, float v, cudaStream_t st)
-{
-    if (n == 0) return cudaSuccess;
-    kge_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
                              long long n_floats, double *reg_loss, int sm_count, cudaStream_t st)
 {

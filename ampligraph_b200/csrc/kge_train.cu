@@ -87,7 +87,6 @@ __device__ __forceinline__ float4 f4fma(float a, float4 b, float4 c)
     return f4from(fma2(aa, KGE_LO(b), KGE_LO(c)), fma2(aa, KGE_HI(b), KGE_HI(c)));
 }
 __device__ __forceinline__ float f4hsum(float4 a) { return (a.x + a.y) + (a.z + a.w); }
-__device__ __forceinline__ float f4dot(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }  // TF abs grad
 __device__ __forceinline__ float4 f4sgn(float4 a) { return make_float4(sgnf(a.x), sgnf(a.y), sgnf(a.z), sgnf(a.w)); }
 __device__ __forceinline__ float f4abssum(float4 a) { return (fabsf(a.x) + fabsf(a.y)) + (fabsf(a.z) + fabsf(a.w)); }
@@ -757,7 +756,9 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
 
         // issue the gather of (optionally) the s,p,o windows and of group [j0, j0+gsz) into buffer `buf`:
         // one 1-D bulk copy per row window, completion counted on the buffer's mbarrier
-        auto issue = [&](int buf, int cb, bool with_spo, int j0, int gsz) {
+        // from_stash: the gradient pass of a row-sharded run re-reads the replaced rows from the LOCAL stash the score
+        // pass filled, instead of pulling them through NVLink a second time
+        auto issue = [&](int buf, int cb, bool with_spo, int j0, int gsz, bool from_stash = false) {
             const int wch_t = min(wk, kp - cb * wk);  // floats of this window per half
             const uint32_t bytes = (n_cb == 1) ? (uint32_t)ld * 4u : (uint32_t)wch_t * 4u;
             const int copies = (n_cb == 1) ? 1 : HALVES;
@@ -773,7 +774,7 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                     src = row == 0 ? ent_row(p, s_id) : row == 1 ? p.rel + (size_t)p_id * ld : ent_row(p, o_id);
                     dst = rows + (size_t)row * lw;
                 } else {
-                    src = ent_row(p, nid[j0 + row - nspo]);
+                    src = from_stash ? p.stash + ((size_t)i * eta + (j0 + row - nspo)) * ld : ent_row(p, nid[j0 + row - nspo]);
                     dst = gb + (size_t)(row - nspo) * lw;
                 }
                 bulk_load(dst + h * wk, src + h * kp + cb * wk, bytes, bar + buf);
@@ -783,6 +784,19 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
             if (buf) { mbar_wait(bar + 1, phase1); phase1 ^= 1u; }
             else { mbar_wait(bar, phase0); phase0 ^= 1u; }
         };
+        // copy the group rows just gathered (possibly from a peer GPU) into this rank's stash
+        auto stash_rows = [&](int buf, int cb, int j0, int gsz) {
+            const int wch_t = min(wk, kp - cb * wk);
+            const uint32_t bytes = (n_cb == 1) ? (uint32_t)ld * 4u : (uint32_t)wch_t * 4u;
+            const int copies = (n_cb == 1) ? 1 : HALVES;
+            float *const gb = nbuf(buf);
+            for (int r = lane; r < gsz * copies; r += 32) {
+                const int row = (copies == 1) ? r : r / HALVES, h = (copies == 1) ? 0 : r - row * HALVES;
+                bulk_store(p.stash + ((size_t)i * eta + (j0 + row)) * ld + h * kp + cb * wk, gb + (size_t)row * lw + h * wk, bytes);
+            }
+            bulk_commit();
+        };
+        const bool use_stash = !RESIDENT && p.stash != nullptr;
         // push `cnt` gradient row windows from shared memory into the gradient table (bulk scatter mode)
         auto scatter = [&](float *srcw, int cnt, int cb, auto dst) {
             const int wch_t = min(wk, kp - cb * wk);
@@ -804,12 +818,17 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
         // ---- pass A: scores, window by window, group by group, next group prefetched (A2 + A4) ----
         for (int cb = 0; cb < n_cb; ++cb) {
             S.nch = min(wk, kp - cb * wk) / 4;
+            if (use_stash) bulk_wait_read_all();
             __syncwarp();
             issue(0, cb, true, 0, min(G, eta));
             for (int g = 0; g < n_groups; ++g) {
                 const int buf = g & 1, j0 = g * G, gsz = min(G, eta - j0);
-                if (g + 1 < n_groups) issue(buf ^ 1, cb, false, j0 + G, min(G, eta - j0 - G));
+                if (g + 1 < n_groups) {
+                    if (use_stash) { bulk_wait_read_all(); __syncwarp(); }  // the stash store of group g-1 has read buf^1
+                    issue(buf ^ 1, cb, false, j0 + G, min(G, eta - j0 - G));
+                }
                 wait(buf);
+                if (use_stash) stash_rows(buf, cb, j0, gsz);
                 if (g == 0) P += warp_sum(S.prep(srow, prow, orow, lane));
                 float *const nrows = nbuf(buf);
                 auto store = [&](int a, int b, bool has_b, float pa, float pb) {
@@ -854,6 +873,8 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
         }
         __syncwarp();
 
+        if (use_stash) { bulk_wait_all(); __syncwarp(); }  // stash rows are in HBM before the gradient pass reads them
+
         // ---- pass B: gradients, last window / last group first (they are still resident) ----
         for (int cb = n_cb - 1; cb >= 0; --cb) {
             S.nch = min(wk, kp - cb * wk) / 4;
@@ -865,12 +886,12 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                 if (top && !still_there) {  // first visit of this window: s, p, o come along, state is rebuilt
                     if (!Sink::kDirect) bulk_wait_read_all();  // copy engine done reading what we overwrite
                     __syncwarp();
-                    issue(buf, cb, true, j0, gsz);
+                    issue(buf, cb, true, j0, gsz, use_stash);
                 }
                 if (g > 0) {  // prefetch the next (lower) group into the other buffer
                     if (!Sink::kDirect) bulk_wait_read_all();
                     __syncwarp();
-                    issue(buf ^ 1, cb, false, j0 - G, G);
+                    issue(buf ^ 1, cb, false, j0 - G, G, use_stash);
                 }
                 if (!still_there) wait(buf);
                 if (top && !still_there) (void)S.prep(srow, prow, orow, lane);

@@ -118,6 +118,17 @@ class KGEEngine:
         self._last_step = 0
 
     # -- tables ------------------------------------------------------------
+    def ensure_row_stash(self, B):
+        """Local [B*eta, ld] stash the gradient pass re-reads instead of gathering the replaced rows a second time
+        (kge_set_row_stash); a no-op when the kernel keeps every row window resident."""
+        if self.lib.kge_rows_resident(self.h) != 0:
+            return None
+        need = int(B) * self.eta
+        if getattr(self, "row_stash", None) is None or self.row_stash.shape[0] < need:
+            self.row_stash = torch.empty((need, self.ld), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.kge_set_row_stash(self.h, _ptr(self.row_stash), need))
+        return self.row_stash
+
     def set_embeddings(self, ent_dense=None, rel_dense=None):
         """dense [rows, internal_k] (numpy / torch) -> padded device layout."""
         for dense, table, rows in ((ent_dense, self.ent, self.ent_rows), (rel_dense, self.rel, self.n_rel)):

@@ -3,7 +3,6 @@
 KGEEngine.  Only the loops and the host-side data plumbing live here; every number is
 produced by libkge_b200.so.
 """
-import os
 import pickle
 
 import numpy as np

@@ -8,6 +8,8 @@ the identical dense optimizer step to its replica.  Ranking shards over entity r
 counts against its row range and the int32 counts are summed (rank counts are additive over
 entity partitions, ScoringBasedEmbeddingModel.py:1449-1452).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -163,6 +165,7 @@ class ShardedTrainer:
         self.n_local = max(0, min(self.rps, self.n_ent - self.first))
 
         self.lazy = bool(lazy)
+        self.use_stash = os.environ.get("KGE_B200_STASH", "1") != "0"
 
         def alloc(rows, n_rel_, ld, dev):
             assert rows == self.rps
@@ -221,6 +224,8 @@ class ShardedTrainer:
         barrier 1 done) so a benchmark can attribute the step time."""
         C, _lib, eng = self._C, self._lib, self.eng
         B = batch.shape[0]
+        if self.use_stash:
+            eng.ensure_row_stash(B)
         def mark():
             if events is not None:
                 e = torch.cuda.Event(enable_timing=True)

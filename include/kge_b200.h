@@ -178,6 +178,16 @@ typedef struct kge_shard_map {
  * replicated (rel_dev / grad_rel_dev local; exchange them with kge_optimizer_step_sharded).
  * The caller brackets it with cross-rank barriers: no rank may gather before every rank's
  * optimizer finished, and no optimizer may start before every rank's scatters are complete. */
+/* Optional for kge_train_step_sharded: a caller-owned LOCAL buffer of `rows` table rows ([rows, ld]
+ * fp32, rows >= B*eta).  When the corruptions of a positive do not all fit in shared memory the
+ * gradient pass needs their rows a second time; with a stash the score pass copies every gathered
+ * row into it (cp.async.bulk shared->global) and the gradient pass re-reads the LOCAL copy instead
+ * of pulling the row through NVLink again, halving the peer traffic. */
+int kge_set_row_stash(kge_handle *h, float *stash_dev, int64_t rows);
+/* 1 when all 3+eta row windows of a positive stay in shared memory (single gather, the stash is never
+ * used), 0 when the kernel works in negative groups / column windows, -1 for a NULL handle. */
+int kge_rows_resident(const kge_handle *h);
+
 int kge_train_step_sharded(kge_handle *h, int32_t mode, const kge_shard_map *map, const float *rel_dev,
                            float *grad_rel_dev, const int32_t *triples_dev, int64_t B,
                            const int32_t *neg_ent_dev, const uint8_t *neg_keep_subj_dev, uint64_t seed,

@@ -78,7 +78,8 @@ dist.all_reduce(tr_ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     print({"cfg": a.cfg, "n_gpus": world, "entities": E, "table_GB": round(E * ld * 4 / 1e9, 2), "ms_per_step": round(ms, 3),
            "triples_per_s": round(world * B * (1 + eta) / (ms / 1e3)), "alg_GBps_per_gpu": round(alg / (ms / 1e3) / 1e9, 1),
-           "nvlink_rows_GB_per_gpu_per_step_each_way": round((3 + eta) * B * ld * 4 * (world - 1) / world / 1e9, 3),
+           "nvlink_rows_GB_per_gpu_per_step_each_way(one gather)": round((3 + eta) * B * ld * 4 * (world - 1) / world / 1e9, 3),
+           "stash": os.environ.get("KGE_B200_STASH", "1"),
            "rank_1024x2sides_ms": round(tr_ms.item(), 2), "rank_Gscores_per_s": round(2 * 1024 * E / (tr_ms.item() / 1e3) / 1e9, 1),
            "rank0_phase_ms[kernel,barrier0,optimizers,barrier1]": phases, "G": None,
            "loss": tr.eng.read_loss()}, flush=True)

@@ -254,6 +254,35 @@ def test_negative_groups_match_resident(model, group):
     assert abs(outs[1][2] - outs[0][2]) <= RTOL * abs(outs[0][2])
 
 
+@pytest.mark.parametrize("model,k,group", [("ComplEx", 20, 3), ("RotatE", 24, 2), ("TransE", 600, 3), ("ComplEx", 520, 0),
+                                           ("DistMult", 1100, 1)])
+def test_row_stash_matches_second_gather(model, k, group):
+    """kge_set_row_stash: the gradient pass re-reads the replaced rows from the stash the score pass filled; same
+    gradients as gathering them twice, and the stash holds exactly the gathered table rows."""
+    rng = np.random.default_rng(23)
+    E, R, eta, B = 90, 4, 7, 70
+    ent, rel = _tables(model, E, R, k, rng, scale=0.3 if k < 100 else 0.05)
+    t = _triples(E, R, B, rng)
+    neg = _negatives(E, B, eta, rng)
+    outs = []
+    for stash in (False, True):
+        eng = _engine(model, k, eta, E, R, loss="self_adversarial", neg_group=group)
+        eng.set_embeddings(ent, rel)
+        if stash:
+            st = eng.ensure_row_stash(B)
+            assert st is not None, "expected a non-resident geometry"
+            st.fill_(float("nan"))
+        eng.forward_backward(_dev(t), (_dev(neg[0]), _dev(neg[1])))
+        outs.append((_dense(eng, eng.g_ent), _dense(eng, eng.g_rel), eng.read_loss()))
+        if stash:
+            torch.cuda.synchronize()
+            want = eng.ent[_dev(neg[0]).long().view(eta, B).t().reshape(-1)]  # stash row i*eta+j <- tile row j*B+i
+            assert torch.equal(st[:B * eta], want)
+        eng.close()
+    assert _close(outs[1][0], outs[0][0]) and _close(outs[1][1], outs[0][1])
+    assert abs(outs[1][2] - outs[0][2]) <= RTOL * abs(outs[0][2])
+
+
 def test_philox_corruptions_structure_and_parity():
     """In-kernel Philox negatives: structure of A3 + the fused kernel really uses that stream."""
     rng = np.random.default_rng(13)
