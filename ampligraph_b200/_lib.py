@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libkge_b200.so")
+SO_PATH = os.environ.get("KGE_B200_LIB") or os.path.join(_HERE, "libkge_b200.so")  # override: kernel A/B experiments
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "kge_b200.h")
 

@@ -161,7 +161,6 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     if (warps > max_warps) warps = max_warps;
     h->warps = warps;  // 0 => even (3+1) windows do not fit (reported by kge_train_step)
 
-    set_debug_noscatter((cfg->reserved & 8) ? 1 : 0);
     if (cfg->scoring == KGE_ROTATE) {
         cudaError_t e2 = cudaMalloc(&h->rot, (size_t)cfg->n_rel * L.ld * sizeof(float));
         if (e2 != cudaSuccess) { delete h; return cuda_fail(e2, "cudaMalloc(rotation table)"); }

@@ -50,7 +50,6 @@ struct TrainParams {
 
 // grid = min(occupancy * sm_count, ceil(B / warps))
 cudaError_t launch_train(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st);
-cudaError_t set_debug_noscatter(int v);
 cudaError_t launch_rotation_table(const float *rel, float *rot, long long n_rel, int kp, int ld, float div,
                                   cudaStream_t st);
 cudaError_t launch_corruptions(const int32_t *triples, long long B, int eta, unsigned long long seed,
