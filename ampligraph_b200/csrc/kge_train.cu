@@ -154,6 +154,10 @@ template <int NIT>
 struct Scorer<KGE_DISTMULT, NIT> {
     float4 A[NIT], C[NIT], Ws[NIT], Wo[NIT];
     int lane, nch, cs = 32;  // cs: chunk stride = lanes cooperating on one positive
+    // Lanes past the end of the window (c >= nch) carry ZERO query vectors (prep) and read the window's last chunk
+    // instead of branching: their products are exact zeros, their W accumulators are never read, only their stores
+    // are predicated.  The row loops are then branch-free, so the loads of all NIT iterations issue back to back.
+    __device__ __forceinline__ int chunk(int it) const { return min(lane + cs * it, nch - 1); }
     __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
@@ -177,12 +181,10 @@ struct Scorer<KGE_DISTMULT, NIT> {
         float4 a = f4zero(), b = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + cs * it;
-            if (c < nch) {
-                const float4 q = SIDE ? C[it] : A[it];
-                a = f4fma(f4ld(ra + 4 * c), q, a);
-                b = f4fma(f4ld(rb + 4 * c), q, b);
-            }
+            const int c = chunk(it);
+            const float4 q = SIDE ? C[it] : A[it];
+            a = f4fma(f4ld(ra + 4 * c), q, a);
+            b = f4fma(f4ld(rb + 4 * c), q, b);
         }
         pa = f4hsum(a);
         pb = f4hsum(b);
@@ -193,16 +195,15 @@ struct Scorer<KGE_DISTMULT, NIT> {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + cs * it;
-            if (c < nch) {
-                float4 va = f4ld(ra + 4 * c), vb = f4ld(rb + 4 * c);
-                const float4 q = SIDE ? C[it] : A[it];
-                float4 &W = SIDE ? Wo[it] : Ws[it];
-                W = f4fma(ga, va, W);
-                W = f4fma(gb, vb, W);
-                Sink::put(ra, ga_row, 4 * c, 4 * c, ga * q);
-                if (has_b) Sink::put(rb, gb_row, 4 * c, 4 * c, gb * q);
-            }
+            const int c = chunk(it);
+            const bool live = lane + cs * it < nch;
+            float4 va = f4ld(ra + 4 * c), vb = f4ld(rb + 4 * c);
+            const float4 q = SIDE ? C[it] : A[it];
+            float4 &W = SIDE ? Wo[it] : Ws[it];
+            W = f4fma(ga, va, W);
+            W = f4fma(gb, vb, W);
+            if (live) Sink::put(ra, ga_row, 4 * c, 4 * c, ga * q);
+            if (live && has_b) Sink::put(rb, gb_row, 4 * c, 4 * c, gb * q);
         }
     }
     template <class Sink>
@@ -232,6 +233,7 @@ struct ComplexScorer {
     float4 A[NIT], Bv[NIT], C[NIT], D[NIT];          // subject-side / object-side query vectors
     float4 Wsr[NIT], Wsi[NIT], Wor[NIT], Woi[NIT];   // sum_j g_j r_j per side (re, im)
     int lane, nch, cs = 32, kp, hs;  // cs: chunk stride = lanes on one positive; kp: half stride in HBM rows, hs: half stride of the staged row window
+    __device__ __forceinline__ int chunk(int it) const { return min(lane + cs * it, nch - 1); }  // see Scorer<KGE_DISTMULT>
     __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
         lane = ln;
@@ -261,14 +263,12 @@ struct ComplexScorer {
         float4 a = f4zero(), b = f4zero();
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + cs * it;
-            if (c < nch) {
-                const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
-                a = f4fma(f4ld(ra + 4 * c), qr, a);
-                b = f4fma(f4ld(rb + 4 * c), qr, b);
-                a = f4fma(f4ld(ra + hs + 4 * c), qi, a);
-                b = f4fma(f4ld(rb + hs + 4 * c), qi, b);
-            }
+            const int c = chunk(it);
+            const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
+            a = f4fma(f4ld(ra + 4 * c), qr, a);
+            b = f4fma(f4ld(rb + 4 * c), qr, b);
+            a = f4fma(f4ld(ra + hs + 4 * c), qi, a);
+            b = f4fma(f4ld(rb + hs + 4 * c), qi, b);
         }
         pa = f4hsum(a);
         pb = f4hsum(b);
@@ -279,21 +279,22 @@ struct ComplexScorer {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + cs * it;
-            if (c < nch) {
-                float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + hs + 4 * c);
-                float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + hs + 4 * c);
-                const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
-                float4 &Wr = SIDE ? Wor[it] : Wsr[it];
-                float4 &Wi = SIDE ? Woi[it] : Wsi[it];
-                Wr = f4fma(ga, ar, Wr); Wi = f4fma(ga, ai, Wi);
-                Wr = f4fma(gb, br, Wr); Wi = f4fma(gb, bi, Wi);
+            const int c = chunk(it);
+            const bool live = lane + cs * it < nch;
+            float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + hs + 4 * c);
+            float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + hs + 4 * c);
+            const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
+            float4 &Wr = SIDE ? Wor[it] : Wsr[it];
+            float4 &Wi = SIDE ? Woi[it] : Wsi[it];
+            Wr = f4fma(ga, ar, Wr); Wi = f4fma(ga, ai, Wi);
+            Wr = f4fma(gb, br, Wr); Wi = f4fma(gb, bi, Wi);
+            if (live) {
                 Sink::put(ra, ga_row, 4 * c, 4 * c, ga * qr);
                 Sink::put(ra, ga_row, hs + 4 * c, kp + 4 * c, ga * qi);
-                if (has_b) {
-                    Sink::put(rb, gb_row, 4 * c, 4 * c, gb * qr);
-                    Sink::put(rb, gb_row, hs + 4 * c, kp + 4 * c, gb * qi);
-                }
+            }
+            if (live && has_b) {
+                Sink::put(rb, gb_row, 4 * c, 4 * c, gb * qr);
+                Sink::put(rb, gb_row, hs + 4 * c, kp + 4 * c, gb * qi);
             }
         }
     }
