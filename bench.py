@@ -172,7 +172,8 @@ def main_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "triples/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1),
+            "config": dict(workload_config(1), parallelism="host CPU, %d torch threads, rank 0 only" % threads,
+                           l2="n/a (CPU wall clock around a bounded sample of the same per-step batch)"),
             "cpu_baseline": {"value": value, "unit": "triples/s", "cores": threads, "kind": "port",
                              "sample": "%d steps of %d positives (oracle/ref_step.py, torch-CPU fp32, op-for-op "
                                        "restatement of the TF graph; TensorFlow is not installable here)" % (steps, CFG["batch"])},
