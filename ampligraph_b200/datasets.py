@@ -11,6 +11,20 @@ import numpy as np
 import pandas as pd
 
 
+def as_triple_array(x, sep="\t"):
+    """Accept what the reference's DataSourceIdentifier accepts for an in-memory run
+    (ampligraph/datasets/source_identifier.py:25-50, :134-136): a numpy array / nested list, a pandas
+    DataFrame, or the path of a csv / txt / gz file with one `sep`-separated triple per line and no header."""
+    if isinstance(x, str):
+        ext = x.rsplit(".", 1)[-1].lower() if "." in x else ""
+        if ext not in ("csv", "txt", "gz"):
+            raise ValueError("Unsupported data source file type: %r (expected csv, txt or gz)" % x)
+        return pd.read_csv(x, sep=sep, header=None).values
+    if isinstance(x, pd.DataFrame):
+        return x.values
+    return np.asarray(x)
+
+
 class DataIndexer:
     def __init__(self, X=None):
         self.ent_labels = np.empty(0, dtype=object)

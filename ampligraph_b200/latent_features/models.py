@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..datasets import DataIndexer, FilterIndex
+from ..datasets import DataIndexer, FilterIndex, as_triple_array
 from ..engine import KGEEngine
 from ..evaluation import hits_at_n_score, mr_score, mrr_score
 from . import loss_functions, optimizers, regularizers
@@ -145,7 +145,7 @@ class ScoringBasedEmbeddingModel:
 
     # ------------------------------------------------------------------ indexing
     def _index(self, x, fit=False):
-        x = np.asarray(x)
+        x = as_triple_array(x)
         if self.data_indexer is False:  # use_indexer=False: data is already int ids
             return np.ascontiguousarray(x[:, :3], dtype=np.int32)
         if fit and not isinstance(self.data_indexer, DataIndexer):
@@ -172,7 +172,7 @@ class ScoringBasedEmbeddingModel:
         self._assert_compile_was_called()
         if partitioning_k != 1:
             raise NotImplementedError("bucket partitioning is replaced by HBM-resident tables (DESIGN.md)")
-        x = np.asarray(x)
+        x = as_triple_array(x)
         # FocusE (:342-368, :396-406, :468-543): numeric edge values in columns 3.. re-weight the scores
         self.use_focusE = bool(focusE) and x.shape[1] > 3
         if x.shape[1] > 3 and not focusE:

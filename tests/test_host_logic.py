@@ -185,3 +185,17 @@ def test_data_parallel_host_path_gloo_world2(tmp_path):
     out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-3000:]
     assert out.stdout.count("ok") >= 2
+
+
+def test_as_triple_array_sources(tmp_path):
+    """numpy / DataFrame / csv path inputs (source_identifier.py:25-50, :134-136)."""
+    import pandas as pd
+    from ampligraph_b200.datasets import as_triple_array
+    X = np.array([["a", "r1", "b"], ["b", "r2", "c"]], dtype=object)
+    p = tmp_path / "triples.csv"
+    pd.DataFrame(X).to_csv(p, sep="\t", header=False, index=False)
+    for src in (X, X.tolist(), pd.DataFrame(X), str(p)):
+        got = as_triple_array(src)
+        assert got.shape == (2, 3) and (got == X).all()
+    with pytest.raises(ValueError):
+        as_triple_array(str(tmp_path / "triples.parquet"))
