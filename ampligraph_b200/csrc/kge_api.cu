@@ -119,7 +119,7 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     // Residency policy, tuned on B200 (scripts/kbench.py sweep, profiles/): keep all eta corruptions resident
     // (one gather per row) while >= KGE_MIN_RESIDENT_WARPS warps still fit; otherwise shrink G until
     // min(max_warps, KGE_TARGET_WARPS) warps fit -- the gradient pass then re-gathers the other groups, which
-    // costs less than running with few warps.  RotatE is measurably (1.5x) faster with an odd group size.
+    // costs less than running with few warps.
     // non-resident slots hold TWO group buffers (the next group is prefetched while the current one is processed)
     int G = cfg->eta;
     bool res = h->n_cb == 1;
@@ -133,7 +133,6 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
             res = false;
             const int want = max_warps < KGE_TARGET_WARPS ? max_warps : KGE_TARGET_WARPS;
             while (G > 1 && (long long)((3 + 2 * G) * (long long)row_bytes + aux) * want > h->max_smem) --G;
-            if (cfg->scoring == KGE_ROTATE && G > 1 && (G % 2) == 0) --G;
         }
     }
     h->resident = res ? 1 : 0;
