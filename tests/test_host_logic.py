@@ -124,6 +124,12 @@ def test_metrics():
     r = np.array([[1, 2], [4, 10]])
     assert mr_score(r) == 4.25 and abs(mrr_score(r) - (1 + .5 + .25 + .1) / 4) < 1e-12
     assert hits_at_n_score(r, 3) == 0.5
+    # the reference's own docstring examples (ampligraph/evaluation/metrics.py:71-75, :140-144, :180-185, :247-250)
+    from ampligraph_b200.evaluation import rank_score
+    assert hits_at_n_score(np.array([1, 12, 6, 2]), n=3) == 0.5
+    assert mrr_score(np.array([1, 12, 6, 2])) == 0.4375
+    assert rank_score(np.array([0, 0, 1, 0]), np.array([.434, .65, .21, .84])) == 4
+    assert abs(mr_score([5, 3, 4, 10, 1]) - 4.6) < 1e-12
 
 
 def test_row_shards_cover_table():

@@ -182,3 +182,72 @@ def test_legacy_adam_matches_closed_form():
     assert np.allclose(var.numpy(), [-0.001, 0.001, 0.0], atol=1e-6)
     lr_t = 0.001 * math.sqrt(1 - 0.999) / (1 - 0.9)
     assert np.allclose(var.numpy()[0], -lr_t * 0.1 / (math.sqrt(0.001) + 1e-7), rtol=1e-5)
+
+
+def _closed_form_dscores(name, P, N, margin, alpha, reduction):
+    """SURVEY.md 8(a) "Gradients the fused kernel must reproduce", stated in numpy (float64), independently of autograd.
+    P [B], N [eta, B] -> (dP [B], dN [eta, B])."""
+    eta = N.shape[0]
+    w = 1.0 if reduction == "sum" else 1.0 / eta
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+    if name == "pairwise":
+        dN = w * ((margin - P + N) >= 0)
+        return -dN.sum(0), dN
+    if name == "nll":
+        w2 = 1.0 if reduction == "sum" else 1.0 / (2 * eta)
+        inN, inP = (N >= -75) & (N <= 75), (P >= -75) & (P <= 75)
+        return -w2 * eta * sig(-P) * inP, w2 * sig(N) * inN
+    if name == "absolute_margin":
+        return np.full_like(P, -w * eta), w * ((margin + N) >= 0)
+    if name == "self_adversarial":
+        e = np.exp(alpha * N - (alpha * N).max(0))
+        p = e / e.sum(0)
+        l = -np.log1p(np.exp(N + margin))  # log sigmoid(-N - margin)
+        S = (p * l).sum(0)
+        return -sig(-(margin + P)), w * (p * sig(N + margin) - alpha * p * (l - S))
+    if name == "multiclass_nll":
+        inN, inP = (N >= -75) & (N <= 75), (P >= -75) & (P <= 75)
+        Nc, Pc = np.clip(N, -75, 75), np.clip(P, -75, 75)
+        D = w * np.exp(Nc).sum(0) + np.exp(Pc)
+        return (np.exp(Pc) / D - 1.0) * inP, w * np.exp(Nc) / D * inN
+    raise AssertionError(name)
+
+
+@pytest.mark.parametrize("reduction", ["sum", "mean"])
+@pytest.mark.parametrize("name", ["pairwise", "nll", "absolute_margin", "self_adversarial", "multiclass_nll"])
+def test_closed_form_loss_gradients_match_autograd(name, reduction):
+    """The dL/dscore formulas the CUDA kernel implements == autograd through the op-for-op loss
+    restatement that the reference's loss KATs pin (test_loss_kats)."""
+    rng = np.random.default_rng(5)
+    eta, B = 7, 33
+    P = rng.normal(0, 3, B)
+    N = rng.normal(0, 3, (eta, B))
+    P[0], N[0, 1], N[1, 2] = 80.0, -90.0, 76.0  # outside the +-75 clip of nll / multiclass_nll
+    margin, alpha = {"pairwise": 1.5, "absolute_margin": 0.7, "self_adversarial": 3.0}.get(name, 1.0), 0.5
+    tp = torch.tensor(P, dtype=torch.float64, requires_grad=True)
+    tn = torch.tensor(N, dtype=torch.float64, requires_grad=True)
+    kw = {"reduction": reduction}
+    if name in ("pairwise", "absolute_margin", "self_adversarial"):
+        kw["margin"] = margin
+    if name == "self_adversarial":
+        kw["alpha"] = alpha
+    ref_step.per_positive_loss(name, tp, tn, **kw).sum().backward()
+    dP, dN = _closed_form_dscores(name, P, N, margin, alpha, reduction)
+    assert np.allclose(tp.grad.numpy(), dP, rtol=1e-9, atol=1e-12)
+    assert np.allclose(tn.grad.numpy(), dN, rtol=1e-9, atol=1e-12)
+
+
+def test_legacy_sgd_and_adagrad_closed_form():
+    """tf.keras.optimizers.legacy SGD (with momentum) and Adagrad (initial accumulator 0.1, eps 1e-7) update rules."""
+    g = torch.tensor([1.0, -2.0, 0.5])
+    var = torch.zeros(3)
+    opt = ref_step.LegacyOptimizer("sgd", 0.1, momentum=0.9)
+    opt.step({"v": (var, g)})
+    opt.step({"v": (var, g)})
+    # accum_1 = -lr g ; accum_2 = 0.9 accum_1 - lr g ; var = accum_1 + accum_2
+    assert np.allclose(var.numpy(), (-0.1 * g - (0.9 * 0.1 + 0.1) * g).numpy(), rtol=1e-6)
+    var = torch.zeros(3)
+    opt = ref_step.LegacyOptimizer("adagrad", 0.05)
+    opt.step({"v": (var, g)})
+    want = -0.05 * g.numpy() / (np.sqrt(0.1 + g.numpy() ** 2) + 1e-7)
+    assert np.allclose(var.numpy(), want, rtol=1e-6)
