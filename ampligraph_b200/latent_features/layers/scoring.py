@@ -59,3 +59,11 @@ class RotatE(AbstractScoringLayer):
         super().__init__(k)
         self.internal_k = 2 * k  # RotatE.py:57
         self.max_rel_size = max_rel_size
+
+
+@register_layer("Random")
+class Random(AbstractScoringLayer):
+    """Registry parity with layers/scoring/Random.py:23-82 (uniform-random scores, the reference's test baseline).
+    It has no arithmetic to accelerate, so there is no kernel behind it: building a model with it raises."""
+    kernel_id = None
+

@@ -62,6 +62,9 @@ class ScoringBasedEmbeddingModel:
         self.eta, self.k, self.scoring_type, self.seed = int(eta), int(k), scoring_type, seed
         self.max_ent_size, self.max_rel_size = max_ent_size, max_rel_size
         self.scoring_layer = SCORING_LAYER_REGISTRY[scoring_type](k)
+        if self.scoring_layer.kernel_id is None:
+            raise NotImplementedError("scoring_type %r is the reference's random baseline: it is registered for parity of "
+                                      "the registry only and has no CUDA kernel" % scoring_type)
         self.internal_k = self.scoring_layer.internal_k
         self.data_indexer = True
         self.is_fitted = False

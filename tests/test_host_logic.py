@@ -54,7 +54,7 @@ def test_config_struct_matches_header():
 
 def test_registries_and_error_convention():
     from ampligraph_b200.latent_features import LOSS_REGISTRY, SCORING_LAYER_REGISTRY, loss_functions, optimizers, regularizers
-    assert set(SCORING_LAYER_REGISTRY) == {"TransE", "DistMult", "ComplEx", "HolE", "RotatE"}
+    assert set(SCORING_LAYER_REGISTRY) == {"TransE", "DistMult", "ComplEx", "HolE", "RotatE", "Random"}
     assert set(LOSS_REGISTRY) == {"pairwise", "nll", "absolute_margin", "self_adversarial", "multiclass_nll"}
     assert SCORING_LAYER_REGISTRY["ComplEx"](3).internal_k == 6 and SCORING_LAYER_REGISTRY["TransE"](7).internal_k == 7
     assert loss_functions.get("self_adversarial")._loss_parameters == {"reduction": "sum", "margin": 3, "alpha": 0.5}
@@ -75,6 +75,10 @@ def test_registries_and_error_convention():
         m.compile(loss="nll", entity_relation_initializer=[np.zeros((3, 8)), np.zeros((2, 8))])
     with pytest.raises(RuntimeError):
         ScoringBasedEmbeddingModel(eta=2, k=4).fit(np.zeros((1, 3)))  # not compiled
+    with pytest.raises(NotImplementedError):  # registry-parity stub of the reference's random baseline
+        ScoringBasedEmbeddingModel(eta=2, k=4, scoring_type="Random")
+    with pytest.raises(KeyError):
+        ScoringBasedEmbeddingModel(eta=2, k=4, scoring_type="ConvE")
 
 
 def test_data_indexer_first_seen_order():
