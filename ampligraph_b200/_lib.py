@@ -57,6 +57,8 @@ PROTOTYPES = {
     "kge_init_glorot_uniform": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, _P]),
     "kge_score_triples": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P]),
     "kge_generate_corruptions": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, C.c_uint64, _P, _P]),
+    "kge_philox4x32_10": (None, [_P, _P, _P]),
+    "kge_host_corruptions": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, _P]),
     "kge_train_step": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_uint64, C.c_uint64,
                                  _P, _P, _P, _P, _P, _P]),
     "kge_train_step_sharded": (C.c_int, [_P, C.c_int32, C.POINTER(KgeShardMap), _P, _P, _P, C.c_int64, _P, _P,
@@ -122,3 +124,15 @@ def check(rc):
     if rc == KGE_ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise RuntimeError(msg)
+
+
+def host_corruptions(triples, eta, n_ent, seed=0, step=0):
+    """CPU replay of the corruption stream of (seed, step): int32 [eta*B, 3], row j*B+i = j-th corruption of
+    positive i -- bit-identical to what the fused kernel draws on the device (kge_host_corruptions)."""
+    import numpy as np
+    t = np.ascontiguousarray(triples, dtype=np.int32).reshape(-1, 3)
+    out = np.empty((t.shape[0] * int(eta), 3), dtype=np.int32)
+    check(load().kge_host_corruptions(t.ctypes.data_as(_P), t.shape[0], int(eta), int(n_ent), int(seed), int(step),
+                                      out.ctypes.data_as(_P)))
+    return out
+

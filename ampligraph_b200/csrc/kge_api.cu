@@ -246,6 +246,31 @@ extern "C" int kge_generate_corruptions(kge_handle *h, const int32_t *triples_de
     return KGE_OK;
 }
 
+// ---- host-side replay of the corruption stream (no GPU, no handle) -----------------------------------------
+extern "C" void kge_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    const u32x4 v = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+
+extern "C" int kge_host_corruptions(const int32_t *triples_host, int64_t B, int32_t eta, int64_t n_ent, uint64_t seed,
+                                    uint64_t step, int32_t *corruptions_host)
+{
+    if (B < 0 || eta < 1 || n_ent < 1 || n_ent > 0x7fffffffLL)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_host_corruptions: need B >= 0, eta >= 1, 1 <= n_ent < 2^31");
+    if (B == 0) return KGE_OK;
+    if (!triples_host || !corruptions_host) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_host_corruptions: null pointer");
+    for (int64_t r = 0; r < B * (int64_t)eta; ++r) {  // same draw, same row order as kge_corruptions_kernel
+        const int64_t i = r % B;
+        int keep, repl;
+        draw_corruption(seed, step, (unsigned long long)r, (uint32_t)n_ent, &keep, &repl);
+        corruptions_host[3 * r + 0] = keep ? triples_host[3 * i + 0] : repl;
+        corruptions_host[3 * r + 1] = triples_host[3 * i + 1];
+        corruptions_host[3 * r + 2] = keep ? repl : triples_host[3 * i + 2];
+    }
+    return KGE_OK;
+}
+
 static int check_shard_map(const kge_handle *h, const kge_shard_map *map, const char *fn)
 {
     if (!map || map->struct_size != (int32_t)sizeof(kge_shard_map))

@@ -138,6 +138,17 @@ int kge_score_triples(kge_handle *h, const float *ent_dev, const float *rel_dev,
 int kge_generate_corruptions(kge_handle *h, const int32_t *triples_dev, int64_t B, uint64_t seed,
                              uint64_t step, int32_t *corruptions_dev /*[eta*B,3]*/, void *stream);
 
+/* Host-side replay of that stream -- plain CPU code, no GPU and no handle needed.  The corruption RNG is
+ * Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; the Random123
+ * known-answer vectors are checked in tests/test_oracle.py) with counter = (row j*B+i, step) and
+ * key = seed: keep_subj = x & 1, replacement id = (y * n_ent) >> 32.  kge_host_corruptions writes the same
+ * [eta*B,3] tensor kge_generate_corruptions / the fused kernel produce for (seed, step) on the device, so a
+ * run can be audited or reproduced without one (TensorFlow's own stream,
+ * CorruptionGenerationLayerTrain.py:55-74, is stateful and not reproducible outside TF). */
+void kge_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+int kge_host_corruptions(const int32_t *triples_host /*[B,3]*/, int64_t B, int32_t eta, int64_t n_ent,
+                         uint64_t seed, uint64_t step, int32_t *corruptions_host /*[eta*B,3]*/);
+
 /* train_step forward+backward (ScoringBasedEmbeddingModel.py:370-429, call :237-269,
  * Loss.__call__ loss_functions.py:185-225, tape.gradient optimizers.py:166).
  *   triples_dev     [B,3] int32 positives

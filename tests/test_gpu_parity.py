@@ -304,6 +304,12 @@ def test_philox_corruptions_structure_and_parity():
     assert abs(repl.mean() - (E - 1) / 2) < 0.05 * E  # uniform replacement ids
     corr2 = eng.generate_corruptions(_dev(t), seed=5, step=4).cpu().numpy()
     assert (corr2 != corr).any()  # the stream advances with the step
+    # the device draw is the published Philox4x32-10 stream: bit-identical to the library's CPU replay and to the
+    # oracle's independent statement of it (oracle/philox.py, pinned by the Random123 known answers)
+    from ampligraph_b200 import _lib
+    from oracle import philox
+    assert (corr == _lib.host_corruptions(t, eta, E, seed=5, step=3)).all()
+    assert (corr[:64] == philox.corruption_stream(t, eta, E, 5, 3)[:64]).all()
     # gradients of the Philox path == oracle fed with the materialised corruptions
     eng.forward_backward(_dev(t), None, seed=5, step=3)
     rs = _ref("DistMult", k, ent, rel, eta, "nll", {})

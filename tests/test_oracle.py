@@ -251,3 +251,44 @@ def test_legacy_sgd_and_adagrad_closed_form():
     opt.step({"v": (var, g)})
     want = -0.05 * g.numpy() / (np.sqrt(0.1 + g.numpy() ** 2) + 1e-7)
     assert np.allclose(var.numpy(), want, rtol=1e-6)
+
+
+RANDOM123_PHILOX4X32_10_KATS = [  # Random123 kat_vectors: (counter, key) -> output
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def test_philox_known_answers_oracle_and_library():
+    """The corruption RNG is the published Philox4x32-10: both the oracle's restatement and the library's
+    host entry point reproduce the Random123 known-answer vectors."""
+    from oracle import philox
+    from ampligraph_b200 import _lib
+    lib = _lib.load()
+    for ctr, key, want in RANDOM123_PHILOX4X32_10_KATS:
+        assert philox.philox4x32_10(ctr, key) == want
+        c, k, o = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), (C.c_uint32 * 4)()
+        lib.kge_philox4x32_10(c, k, o)
+        assert tuple(o) == want
+
+
+def test_host_corruption_replay_matches_oracle_stream():
+    """kge_host_corruptions (the CPU replay of what the fused kernel draws) == the oracle's statement of the stream,
+    and has the structure of CorruptionGenerationLayerTrain.py:52-88."""
+    from oracle import philox
+    from ampligraph_b200 import _lib
+    rng = np.random.default_rng(3)
+    E, B, eta = 1000, 37, 5
+    t = np.stack([rng.integers(0, E, B), rng.integers(0, 7, B), rng.integers(0, E, B)], 1).astype(np.int32)
+    for seed, step in ((0, 0), (5, 3), (2 ** 40 + 17, 2 ** 33 + 1)):
+        got = _lib.host_corruptions(t, eta, E, seed=seed, step=step)
+        assert (got == philox.corruption_stream(t, eta, E, seed, step)).all()
+        tiled = np.tile(t, (eta, 1))
+        assert (got[:, 1] == tiled[:, 1]).all()
+        assert ((got[:, 0] == tiled[:, 0]) | (got[:, 2] == tiled[:, 2])).all()
+        assert got.min() >= 0 and got[:, [0, 2]].max() < E
+    assert (_lib.host_corruptions(t, eta, E, seed=5, step=3) != _lib.host_corruptions(t, eta, E, seed=5, step=4)).any()
+    with pytest.raises(ValueError):
+        _lib.host_corruptions(t, 0, E)
