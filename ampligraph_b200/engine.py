@@ -20,6 +20,27 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_NVTX = os.environ.get("KGE_B200_NVTX", "0") == "1"
+
+
+def _traced(name):
+    """KGE_B200_NVTX=1: wrap the call in an NVTX range, so that `ncu --nvtx --nvtx-include "kge.train_step/"` (or an
+    nsys timeline) attributes kernels to the step phase that launched them.  Off (default): the method is untouched."""
+    def deco(fn):
+        if not _NVTX:
+            return fn
+
+        def wrapped(*a, **k):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
 class KGEEngine:
     def __init__(self, scoring_type, k, eta, n_ent, n_rel, loss="pairwise", loss_params=None,
                  optimizer="adam", optimizer_params=None, regularizer=None, device=0, neg_group=0,
@@ -154,6 +175,7 @@ class KGEEngine:
         _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.rel), self.n_rel, int(seed) * 2 + 1, self._stream()))
 
     # -- training ------------------------------------------------------------
+    @_traced("kge.train_step")
     def forward_backward(self, triples, negatives=None, seed=0, step=0, mode=_lib.STEP_FUSED,
                          scores_pos=None, scores_neg=None, dpos=None, dneg=None):
         """train_step up to tape.gradient: accumulates into g_ent/g_rel and loss_acc[0]."""
@@ -171,6 +193,7 @@ class KGEEngine:
         self._last_step = int(step)
         self.launches += 2 if self.scoring_type == "RotatE" else 1
 
+    @_traced("kge.optimizer_step")
     def apply_gradients(self):
         """optimizer.apply_gradients on both tables (dense semantics) + LP regulariser."""
         self.t += 1
@@ -207,6 +230,7 @@ class KGEEngine:
         return out
 
     # -- inference -------------------------------------------------------------
+    @_traced("kge.score_triples")
     def score(self, triples):
         assert triples.dtype == torch.int32 and triples.is_cuda and triples.is_contiguous()
         out = torch.empty(triples.shape[0], dtype=torch.float32, device=self.device)
@@ -215,6 +239,7 @@ class KGEEngine:
         self.launches += 2 if self.scoring_type == "RotatE" else 1
         return out
 
+    @_traced("kge.rank")
     def rank(self, triples, side, strategy="worst", filt_off=None, filt_idx=None, cand_ids=None, cand_begin=0,
              n_cand=None, out=None):
         """get_ranks for one side: returns/accumulates int32 counts (caller adds 1)."""
