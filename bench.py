@@ -16,7 +16,6 @@ own batch, NCCL all-reduce of the gradient tables before the (identical) optimiz
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
