@@ -11,7 +11,9 @@ self-adversarial loss (margin 3, alpha 0.5), Adam lr 1e-3, FB15K-237-shaped synt
 per epoch).  A step = one reference train_step on one batch: fused forward+backward kernel
 + dense Adam on both tables.  Metric: training triples/sec counting positives + eta
 negatives = B*(1+eta)*steps / time.  N>1: weak scaling, tables replicated, each rank its
-own batch, NCCL all-reduce of the gradient tables before the (identical) optimizer step.
+own batch; the gradient exchange is fused with the optimizer (peer-memory reduce-scatter +
+sharded Adam + all-gather in one kernel per table, parallel.DataParallelTrainer), with the
+NCCL all-reduce + full optimizer as fallback (KGE_B200_DP_MODE=nccl).
 """
 import argparse
 import json
