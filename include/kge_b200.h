@@ -90,7 +90,7 @@ typedef struct kge_config {
     int32_t device;       /* CUDA device ordinal */
     int32_t neg_group;    /* 0 = auto; >0 forces that many negatives resident per pass (testing) */
     int32_t scatter_mode; /* enum kge_scatter: how gradient rows reach the gradient tables */
-    int32_t reserved;     /* 0 (bit 0/1: shared-memory layout experiments -- pad row slots / warp regions to 128 B) */
+    int32_t reserved;     /* 0; experiment switches: bit 0/1 pad row slots / warp regions to 128 B, bit 2 two-warps-per-positive kernel */
 } kge_config;
 
 /* optimizers.get (optimizers.py:255-291) -> tf.keras.optimizers.legacy.{SGD,Adam,Adagrad};
