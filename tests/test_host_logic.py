@@ -209,3 +209,51 @@ def test_as_triple_array_sources(tmp_path):
         assert got.shape == (2, 3) and (got == X).all()
     with pytest.raises(ValueError):
         as_triple_array(str(tmp_path / "triples.parquet"))
+
+
+def test_filter_index_and_indexer_properties():
+    """Property tests (hypothesis) over ragged / empty / duplicated inputs: FilterIndex == brute force for both sides,
+    with and without an entities_subset; DataIndexer raw -> ind -> raw is the identity and ids are first-seen order."""
+    from hypothesis import given, settings, strategies as st
+    from ampligraph_b200.datasets import DataIndexer, FilterIndex
+
+    E, R = 7, 3
+    triple = st.tuples(st.integers(0, E - 1), st.integers(0, R - 1), st.integers(0, E - 1))
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(triple, min_size=0, max_size=40), st.lists(triple, min_size=0, max_size=12),
+           st.lists(st.integers(0, E - 1), unique=True, min_size=1, max_size=E))
+    def filters(data, queries, subset):
+        data_a = np.array(data, dtype=np.int64).reshape(-1, 3)
+        q = np.array(queries, dtype=np.int64).reshape(-1, 3)
+        fi = FilterIndex(data_a, E)
+        pos = np.full(E, -1, np.int64)
+        pos[np.array(subset)] = np.arange(len(subset))
+        for side, (a, b, c) in (("s", (1, 2, 0)), ("o", (0, 1, 2))):
+            for position_of in (None, pos):
+                off, ids = fi.lookup(q, side, position_of)
+                assert off.shape == (len(q) + 1,) and off[0] == 0 and off[-1] == len(ids) and ids.dtype == np.int32
+                for i, t in enumerate(q):
+                    known = sorted({d[c] for d in data if d[a] == t[a] and d[b] == t[b]})
+                    if position_of is not None:
+                        known = [int(pos[e]) for e in known if pos[e] >= 0]
+                    assert sorted(ids[off[i]:off[i + 1]].tolist()) == sorted(known)
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.lists(st.tuples(st.sampled_from("abcdefg"), st.sampled_from("xyz"), st.sampled_from("abcdefg")),
+                    min_size=1, max_size=30))
+    def indexer(rows):
+        X = np.array(rows, dtype=object)
+        ix = DataIndexer(X)
+        ind = ix.get_indexes(X, "t", "raw2ind")
+        assert ind.dtype == np.int32 and (ix.get_indexes(ind, "t", "ind2raw") == X).all()
+        seen = []
+        for s, _, o in rows:  # first-seen order scanning s then o of each row (data_indexer.py:385-397)
+            for e in (s, o):
+                if e not in seen:
+                    seen.append(e)
+        assert ix.ent_labels.tolist() == seen
+        assert ix.get_entities_count() == len(seen) and ix.get_relations_count() == len({r for _, r, _ in rows})
+
+    filters()
+    indexer()
