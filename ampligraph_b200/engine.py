@@ -218,7 +218,7 @@ class KGEEngine:
 
     def read_loss(self, reset=True):
         """(batch loss + regulariser loss) accumulated since the last reset; synchronises."""
-        v = self.loss_acc.sum().item()
+        v = float(self.loss_acc.cpu().sum())  # one 16-byte D2H copy (synchronising), summed on the host: no reduce kernel
         if reset:
             self.loss_acc.zero_()
         return v

@@ -317,7 +317,7 @@ def main_ours(args):
                 "warmup": args.warmup, "ms_per_step": t_step / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(world, {"p2p": "gradient reduce-scatter + sharded Adam + parameter all-gather fused in one kernel over NVLink peer memory", "nccl": "NCCL all-reduce of gradient tables"}.get(dp.mode, dp.mode)), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": B * 3 * 4, "d2h_bytes_per_step": 8},
+                "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": B * 3 * 4, "d2h_bytes_per_step": 16},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "kernel": "kge_train_kernel<ComplEx,2>",
