@@ -21,20 +21,23 @@ OPTIMIZERS = {"sgd": 0, "adam": 1, "adagrad": 2}
 SIDES = {"s": 0, "o": 1}
 STRATEGIES = {"worst": 0, "best": 1, "middle": 2}
 STEP_FUSED, STEP_FORWARD_ONLY, STEP_BACKWARD_EXT = 0, 1, 2
-SCATTER = {"bulk": 0, "red_v4": 1}
+RANK_MODES = {"auto": 0, "exact": 1}
+INIT_KINDS = {"uniform": 0, "normal": 1, "truncated_normal": 2, "constant": 3}
+ABI_VERSION = 2
 
 
 class KgeConfig(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("scoring", C.c_int32), ("k", C.c_int32), ("eta", C.c_int32),
                 ("n_ent", C.c_int64), ("n_rel", C.c_int64), ("loss", C.c_int32), ("reduction", C.c_int32),
                 ("margin", C.c_float), ("alpha", C.c_float), ("device", C.c_int32), ("neg_group", C.c_int32),
-                ("scatter_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("max_rel_size", C.c_int64), ("rank_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class KgeOptimizerConfig(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("kind", C.c_int32), ("learning_rate", C.c_float),
                 ("beta_1", C.c_float), ("beta_2", C.c_float), ("epsilon", C.c_float), ("momentum", C.c_float),
-                ("initial_accumulator_value", C.c_float), ("reg_p", C.c_int32), ("reg_lambda", C.c_float)]
+                ("initial_accumulator_value", C.c_float), ("reg_p", C.c_int32), ("reg_lambda", C.c_float),
+                ("reg_p2", C.c_int32), ("reg_lambda2", C.c_float)]
 
 
 class KgeShardMap(C.Structure):
@@ -55,6 +58,7 @@ PROTOTYPES = {
     "kge_pack_rows": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "kge_unpack_rows": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "kge_init_glorot_uniform": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, _P]),
+    "kge_init_table": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_uint64, _P]),
     "kge_score_triples": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P]),
     "kge_generate_corruptions": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, C.c_uint64, _P, _P]),
     "kge_philox4x32_10": (None, [_P, _P, _P]),
@@ -64,7 +68,7 @@ PROTOTYPES = {
     "kge_train_step_sharded": (C.c_int, [_P, C.c_int32, C.POINTER(KgeShardMap), _P, _P, _P, C.c_int64, _P, _P,
                                          C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P]),
     "kge_rank_sharded": (C.c_int, [_P, C.POINTER(KgeShardMap), C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64,
-                                   _P, _P, C.c_int64, _P, _P]),
+                                   _P, _P, C.c_int64, _P, _P, _P, C.c_int64, _P]),
     "kge_optimizer_step": (C.c_int, [_P, C.POINTER(KgeOptimizerConfig), C.c_int64, _P, _P, _P, _P, C.c_int64,
                                      _P, _P]),
     "kge_set_row_stamps": (C.c_int, [_P, _P, _P]),
@@ -75,9 +79,16 @@ PROTOTYPES = {
                                           C.c_int32, _P, _P]),
     "kge_optimizer_step_sharded": (C.c_int, [_P, C.POINTER(KgeOptimizerConfig), C.c_int64, C.c_int32, C.c_int32,
                                              C.POINTER(_P), C.POINTER(_P), _P, _P, C.c_int64, C.c_int64, _P, _P]),
+    "kge_optimizer_step_exchange": (C.c_int, [_P, C.POINTER(KgeOptimizerConfig), C.POINTER(KgeOptimizerConfig), C.c_int64,
+                                              C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(_P), _P, _P, _P, C.c_int64,
+                                              C.c_int64, C.POINTER(_P), C.c_uint32, C.c_int32, _P, _P]),
+    "kge_peer_barrier": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.c_int32, C.c_uint32, _P]),
     "kge_rank": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P,
-                           C.c_int64, _P, _P]),
-    "kge_rank_workspace_bytes": (C.c_int64, [_P, C.c_int64]),
+                           C.c_int64, _P, _P, _P, C.c_int64, _P]),
+    "kge_rank_finalize": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
+    "kge_corruption_scores": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P,
+                                        C.c_int64, _P]),
+    "kge_rank_workspace_bytes": (C.c_int64, [_P, C.c_int64, C.c_int64]),
 }
 
 _lib = None
@@ -108,8 +119,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.kge_abi_version() != 1:
-        raise RuntimeError("libkge_b200.so ABI version %d, binding expects 1" % lib.kge_abi_version())
+    if lib.kge_abi_version() != ABI_VERSION:
+        raise RuntimeError("libkge_b200.so ABI version %d, binding expects %d" % (lib.kge_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

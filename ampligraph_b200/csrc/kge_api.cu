@@ -16,18 +16,38 @@ struct kge_handle {
     int max_smem;
     float score_scale;  // HolE 2/k
     float rot_div;      // RotatE range/pi
-    float *rot;         // [n_rel, ld] rotation table workspace (RotatE)
+    // the only device memory the library owns (allocated once by kge_create, freed by kge_destroy):
+    float *rot;              // [n_rel, ld] rotation table (RotatE only)
+    unsigned *done_counter;  // last-CTA counter of kge_optimizer_step_exchange
     // training launch geometry
     int nit, G, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats, resident;
-    int team, team_nit, team_region, team_count;
-    // ranking workspace (grown on demand)
     int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
     float *stash;                // caller-owned row stash for sharded runs (kge_set_row_stash) or nullptr
     long long stash_rows;
-    long long ws_b;
-    float *ws_q;      // 3 * ws_b * ld floats: qvec_s | qvec_o | qaux
-    int32_t *ws_i;    // 4 * ws_b ints: qpos | cnt[3]
 };
+
+// Make the handle's device current for the duration of an entry point (two handles on different GPUs
+// driven from one thread); restores the caller's device on return.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define KGE_GUARD(h)                       \
+    DeviceGuard guard_((h)->cfg.device);   \
+    if (guard_.err != cudaSuccess) return cuda_fail(guard_.err, "cudaSetDevice")
 
 static thread_local char g_err[512] = "";
 
@@ -64,8 +84,9 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
         return fail(KGE_ERR_INVALID_ARGUMENT, "Could not interpret loss identifier: %d", cfg->loss);
     if (cfg->reduction != KGE_REDUCE_SUM && cfg->reduction != KGE_REDUCE_MEAN)
         return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for reduction!");
-    if (cfg->scatter_mode != KGE_SCATTER_BULK && cfg->scatter_mode != KGE_SCATTER_RED_V4)
-        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: unknown scatter_mode %d", cfg->scatter_mode);
+    if (cfg->rank_mode != KGE_RANK_MODE_AUTO && cfg->rank_mode != KGE_RANK_MODE_EXACT)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: unknown rank_mode %d", cfg->rank_mode);
+    if (cfg->max_rel_size < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: max_rel_size < 0");
     if (cfg->k < 1 || cfg->eta < 1 || cfg->n_ent < 1 || cfg->n_rel < 1)
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: k, eta, n_ent, n_rel must be >= 1");
     if (cfg->n_ent > 0x7fffffffLL || cfg->n_rel > 0x7fffffffLL)
@@ -78,7 +99,8 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev)
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: device %d out of range [0,%d)", cfg->device, ndev);
-    KGE_CUDA(cudaSetDevice(cfg->device), "cudaSetDevice");
+    DeviceGuard guard_(cfg->device);
+    if (guard_.err != cudaSuccess) return cuda_fail(guard_.err, "cudaSetDevice");
     cudaDeviceProp prop;
     KGE_CUDA(cudaGetDeviceProperties(&prop, cfg->device), "cudaGetDeviceProperties");
     if (prop.major < 10)
@@ -99,7 +121,7 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     h->sm_count = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     h->score_scale = (cfg->scoring == KGE_HOLE) ? hole_scale(L.K) : 1.f;
-    h->rot_div = (cfg->scoring == KGE_ROTATE) ? rotate_divisor(L.K, cfg->n_rel) : 1.f;
+    h->rot_div = (cfg->scoring == KGE_ROTATE) ? rotate_divisor(L.K, cfg->max_rel_size > 0 ? cfg->max_rel_size : cfg->n_rel) : 1.f;
 
     // ---- training geometry: one warp per positive; its slot holds (3+G) row windows ----
     // window = wk floats per half (<= 128*NIT so that NIT float4 per lane cover it); rows wider than
@@ -110,10 +132,7 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     h->wk = L.kp <= 512 ? L.kp : 512;
     h->n_cb = (L.kp + h->wk - 1) / h->wk;
     h->eta_pad = (cfg->eta + 3) / 4 * 4;
-    // layout experiments (kge_config.reserved): bit0 pads each row slot to a 128-byte multiple,
-    // bit1 pads the per-warp region to a 128-byte multiple
-    int row_bytes = L.halves * h->wk * 4, aux = 3 * h->eta_pad * 4 + 16;
-    if (cfg->reserved & 1) row_bytes = (row_bytes + 127) / 128 * 128;
+    const int row_bytes = L.halves * h->wk * 4, aux = 3 * h->eta_pad * 4 + 16;
     h->slot_floats = row_bytes / 4;
     const int max_warps = KGE_TRAIN_THREADS(cfg->scoring, h->nit) / 32;
     // Residency policy, tuned on B200 (scripts/kbench.py sweep, profiles/): keep all eta corruptions resident
@@ -136,26 +155,9 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
         }
     }
     h->resident = res ? 1 : 0;
-    // team mode (kge_config.reserved bit 2, experiment): two warps per positive share one slot
-    h->team = 0;
-    if ((cfg->reserved & 4) && res && cfg->scatter_mode == KGE_SCATTER_RED_V4 && cfg->scoring != KGE_ROTATE &&
-        (nch + 63) / 64 <= 2) {
-        const int tnit_raw = (nch + 63) / 64;
-        const int tnit = tnit_raw <= 1 ? 1 : tnit_raw <= 2 ? 2 : 4;
-        const int tregion = (3 + cfg->eta) * row_bytes + 2 * (3 * h->eta_pad * 4) + 2 * (h->eta_pad + 4) * 4 + 16;
-        int teams = h->max_smem / tregion;
-        if (teams > KGE_TEAM_THREADS / 64) teams = KGE_TEAM_THREADS / 64;
-        if (teams >= 2) {
-            h->team = 1;
-            h->team_nit = tnit;
-            h->team_region = tregion;
-            h->team_count = teams;
-        }
-    }
     h->G = G;
     h->rows_bytes = (res ? 3 + G : 3 + 2 * G) * row_bytes;
     h->region_bytes = h->rows_bytes + aux;
-    if (cfg->reserved & 2) h->region_bytes = (h->region_bytes + 127) / 128 * 128;
     int warps = h->max_smem / h->region_bytes;
     if (warps > max_warps) warps = max_warps;
     h->warps = warps;  // 0 => even (3+1) windows do not fit (reported by kge_train_step)
@@ -164,6 +166,11 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
         cudaError_t e2 = cudaMalloc(&h->rot, (size_t)cfg->n_rel * L.ld * sizeof(float));
         if (e2 != cudaSuccess) { delete h; return cuda_fail(e2, "cudaMalloc(rotation table)"); }
     }
+    {
+        cudaError_t e2 = cudaMalloc(&h->done_counter, sizeof(unsigned));
+        if (e2 == cudaSuccess) e2 = cudaMemset(h->done_counter, 0, sizeof(unsigned));
+        if (e2 != cudaSuccess) { if (h->rot) cudaFree(h->rot); delete h; return cuda_fail(e2, "cudaMalloc(counter)"); }
+    }
     *out = h;
     return KGE_OK;
 }
@@ -171,10 +178,9 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
 extern "C" void kge_destroy(kge_handle *h)
 {
     if (!h) return;
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard guard_(h->cfg.device);
     if (h->rot) cudaFree(h->rot);
-    if (h->ws_q) cudaFree(h->ws_q);
-    if (h->ws_i) cudaFree(h->ws_i);
+    if (h->done_counter) cudaFree(h->done_counter);
     delete h;
 }
 
@@ -182,8 +188,10 @@ extern "C" int32_t kge_internal_k(const kge_handle *h) { return h ? h->L.K : 0; 
 extern "C" int32_t kge_half_stride(const kge_handle *h) { return h ? h->L.kp : 0; }
 extern "C" int32_t kge_row_stride(const kge_handle *h) { return h ? h->L.ld : 0; }
 
-#define KGE_CHECK_HANDLE(h, fn) \
-    if (!(h)) return fail(KGE_ERR_INVALID_ARGUMENT, fn ": null handle")
+// null check + device guard (every entry point below launches on the handle's device)
+#define KGE_CHECK_HANDLE(h, fn)                                           \
+    if (!(h)) return fail(KGE_ERR_INVALID_ARGUMENT, fn ": null handle"); \
+    KGE_GUARD(h)
 
 extern "C" int kge_pack_rows(kge_handle *h, const float *dense_dev, float *table_dev, int64_t rows, void *stream)
 {
@@ -205,6 +213,18 @@ extern "C" int kge_init_glorot_uniform(kge_handle *h, float *table_dev, int64_t 
     KGE_CHECK_HANDLE(h, "kge_init_glorot_uniform");
     if (rows < 0 || (rows > 0 && !table_dev)) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_init_glorot_uniform: bad argument");
     KGE_CUDA(launch_glorot(h->L, table_dev, rows, seed, (cudaStream_t)stream), "kge_init_glorot_uniform");
+    return KGE_OK;
+}
+
+extern "C" int kge_init_table(kge_handle *h, float *table_dev, int64_t rows, int32_t kind, float a, float b, uint64_t seed,
+                              void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_init_table");
+    if (rows < 0 || (rows > 0 && !table_dev)) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_init_table: bad argument");
+    if (kind < KGE_INIT_UNIFORM || kind > KGE_INIT_CONSTANT) return fail(KGE_ERR_INVALID_ARGUMENT, "Unknown initializer kind: %d", kind);
+    if ((kind == KGE_INIT_NORMAL || kind == KGE_INIT_TRUNCATED_NORMAL) && b < 0.f)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_init_table: negative stddev");
+    KGE_CUDA(launch_init_table(h->L, table_dev, rows, kind, a, b, seed, (cudaStream_t)stream), "kge_init_table");
     return KGE_OK;
 }
 
@@ -340,7 +360,6 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
     p.loss = h->cfg.loss;
     p.reduction = h->cfg.reduction;
     p.mode = mode;
-    p.scatter_mode = h->cfg.scatter_mode;
     p.margin = h->cfg.margin;
     p.alpha = h->cfg.alpha;
     p.score_scale = h->score_scale;
@@ -363,13 +382,6 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
             p.stamp_ent_shard[q] = map->stamp_ent[q];
             if (!map->stamp_ent[q]) p.stamp_ent = nullptr;  // all or nothing
         }
-    }
-    if (h->team && !(map && map->world > 1)) {
-        p.team = 1;
-        p.region_bytes = h->team_region;
-        KGE_CUDA(launch_train(p, h->team_nit, h->sm_count, h->team_count * 64, (size_t)h->team_count * h->team_region, st),
-                 "kge_train_step(team)");
-        return KGE_OK;
     }
     KGE_CUDA(launch_train(p, h->nit, h->sm_count, h->warps * 32, (size_t)h->warps * h->region_bytes, st),
              "kge_train_step");
@@ -404,35 +416,55 @@ extern "C" int kge_train_step_sharded(kge_handle *h, int32_t mode, const kge_sha
                            dpos_dev, dneg_dev, stream);
 }
 
-extern "C" int kge_optimizer_step(kge_handle *h, const kge_optimizer_config *opt, int64_t t, float *table_dev,
-                                  float *grad_dev, float *slot0_dev, float *slot1_dev, int64_t rows,
-                                  double *reg_loss_dev, void *stream)
+static int check_optim(const kge_optimizer_config *opt, const char *fn)
 {
-    KGE_CHECK_HANDLE(h, "kge_optimizer_step");
     if (!opt || opt->struct_size != (int32_t)sizeof(kge_optimizer_config))
-        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: bad kge_optimizer_config (ABI mismatch)");
+        return fail(KGE_ERR_INVALID_ARGUMENT, "%s: bad kge_optimizer_config (ABI mismatch)", fn);
     if (opt->kind < KGE_OPT_SGD || opt->kind > KGE_OPT_ADAGRAD)
         return fail(KGE_ERR_INVALID_ARGUMENT, "Could not interpret optimizer identifier: %d", opt->kind);
-    if (rows < 0 || t < 1) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: rows >= 0 and t >= 1 required");
-    if (rows == 0) return KGE_OK;
-    if (!table_dev || !grad_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: null table/grad");
-    const bool need0 = opt->kind != KGE_OPT_SGD || opt->momentum != 0.f;
-    const bool need1 = opt->kind == KGE_OPT_ADAM;
-    if ((need0 && !slot0_dev) || (need1 && !slot1_dev))
-        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: optimizer slot buffer missing");
-    if (opt->reg_p < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: reg_p < 0");
-    OptimParams o;
+    if (opt->reg_p < 0 || opt->reg_p2 < 0 || (opt->reg_p == 0 && opt->reg_p2 != 0))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "%s: bad regulariser (reg_p >= 0; reg_p2 needs reg_p)", fn);
+    return KGE_OK;
+}
+static RegParams reg_of(const kge_optimizer_config *opt)
+{
+    RegParams r;
+    r.p = opt->reg_p; r.lambda = opt->reg_lambda; r.p2 = opt->reg_p2; r.lambda2 = opt->reg_lambda2;
+    return r;
+}
+static void fill_optim(const kge_optimizer_config *opt, int64_t t, OptimParams &o)
+{
     o.kind = opt->kind;
     o.lr = opt->learning_rate;
     o.beta1 = opt->beta_1;
     o.beta2 = opt->beta_2;
     o.eps = opt->epsilon;
     o.momentum = opt->momentum;
-    o.reg_p = opt->reg_p;
-    o.reg_lambda = opt->reg_lambda;
-    // legacy Adam: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+    o.reg = reg_of(opt);
+    // legacy Adam: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), in fp64 on the host
     o.lr_t = (float)((double)opt->learning_rate * sqrt(1.0 - pow((double)opt->beta_2, (double)t)) /
                      (1.0 - pow((double)opt->beta_1, (double)t)));
+}
+static bool slots_ok(const kge_optimizer_config *opt, const float *s0, const float *s1)
+{
+    const bool need0 = opt->kind != KGE_OPT_SGD || opt->momentum != 0.f;
+    const bool need1 = opt->kind == KGE_OPT_ADAM;
+    return !((need0 && !s0) || (need1 && !s1));
+}
+
+extern "C" int kge_optimizer_step(kge_handle *h, const kge_optimizer_config *opt, int64_t t, float *table_dev,
+                                  float *grad_dev, float *slot0_dev, float *slot1_dev, int64_t rows,
+                                  double *reg_loss_dev, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_optimizer_step");
+    if (int rc = check_optim(opt, "kge_optimizer_step")) return rc;
+    if (rows < 0 || t < 1) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: rows >= 0 and t >= 1 required");
+    if (rows == 0) return KGE_OK;
+    if (!table_dev || !grad_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: null table/grad");
+    if (!slots_ok(opt, slot0_dev, slot1_dev))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step: optimizer slot buffer missing");
+    OptimParams o;
+    fill_optim(opt, t, o);
     KGE_CUDA(launch_optimizer(o, table_dev, grad_dev, slot0_dev, slot1_dev, rows * (long long)h->L.ld, reg_loss_dev,
                               h->sm_count, (cudaStream_t)stream),
              "kge_optimizer_step");
@@ -460,36 +492,16 @@ extern "C" int kge_set_row_stash(kge_handle *h, float *stash_dev, int64_t rows)
 
 extern "C" int32_t kge_step_stamp(uint64_t step) { return (int32_t)(step & 0x3fffffffu) + 1; }
 
-static int fill_optim(const kge_optimizer_config *opt, int64_t t, OptimParams &o)
-{
-    o.kind = opt->kind;
-    o.lr = opt->learning_rate;
-    o.beta1 = opt->beta_1;
-    o.beta2 = opt->beta_2;
-    o.eps = opt->epsilon;
-    o.momentum = opt->momentum;
-    o.reg_p = opt->reg_p;
-    o.reg_lambda = opt->reg_lambda;
-    o.lr_t = (float)((double)opt->learning_rate * sqrt(1.0 - pow((double)opt->beta_2, (double)t)) /
-                     (1.0 - pow((double)opt->beta_1, (double)t)));
-    return 0;
-}
-
 extern "C" int kge_optimizer_step_lazy(kge_handle *h, const kge_optimizer_config *opt, int64_t t, float *table_dev,
                                        float *grad_dev, float *slot0_dev, float *slot1_dev, int64_t rows,
                                        const int32_t *row_stamp_dev, int32_t stamp, double *reg_loss_dev, void *stream)
 {
     KGE_CHECK_HANDLE(h, "kge_optimizer_step_lazy");
-    if (!opt || opt->struct_size != (int32_t)sizeof(kge_optimizer_config))
-        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_lazy: bad kge_optimizer_config (ABI mismatch)");
-    if (opt->kind < KGE_OPT_SGD || opt->kind > KGE_OPT_ADAGRAD)
-        return fail(KGE_ERR_INVALID_ARGUMENT, "Could not interpret optimizer identifier: %d", opt->kind);
+    if (int rc = check_optim(opt, "kge_optimizer_step_lazy")) return rc;
     if (rows < 0 || t < 1) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_lazy: rows >= 0 and t >= 1 required");
     if (rows == 0) return KGE_OK;
     if (!table_dev || !grad_dev || !row_stamp_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_lazy: null pointer");
-    const bool need0 = opt->kind != KGE_OPT_SGD || opt->momentum != 0.f;
-    const bool need1 = opt->kind == KGE_OPT_ADAM;
-    if ((need0 && !slot0_dev) || (need1 && !slot1_dev))
+    if (!slots_ok(opt, slot0_dev, slot1_dev))
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_lazy: optimizer slot buffer missing");
     OptimParams o;
     fill_optim(opt, t, o);
@@ -499,26 +511,27 @@ extern "C" int kge_optimizer_step_lazy(kge_handle *h, const kge_optimizer_config
     return KGE_OK;
 }
 
+static int check_world(int32_t world, int32_t rank, const char *fn)
+{
+    if (world < 1 || world > KGE_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "%s: world must be 1..%d and 0 <= rank < world", fn, KGE_MAX_PEERS);
+    return KGE_OK;
+}
+
 extern "C" int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_config *opt, int64_t t, int32_t world,
                                           int32_t rank, float *const *peer_tables, float *const *peer_grads,
                                           float *slot0_shard_dev, float *slot1_shard_dev, int64_t row_begin,
                                           int64_t row_end, double *reg_loss_dev, void *stream)
 {
     KGE_CHECK_HANDLE(h, "kge_optimizer_step_sharded");
-    if (!opt || opt->struct_size != (int32_t)sizeof(kge_optimizer_config))
-        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: bad kge_optimizer_config (ABI mismatch)");
-    if (opt->kind < KGE_OPT_SGD || opt->kind > KGE_OPT_ADAGRAD)
-        return fail(KGE_ERR_INVALID_ARGUMENT, "Could not interpret optimizer identifier: %d", opt->kind);
-    if (world < 1 || world > KGE_MAX_PEERS || rank < 0 || rank >= world)
-        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: world must be 1..%d and 0 <= rank < world", KGE_MAX_PEERS);
+    if (int rc = check_optim(opt, "kge_optimizer_step_sharded")) return rc;
+    if (int rc = check_world(world, rank, "kge_optimizer_step_sharded")) return rc;
     if (row_begin < 0 || row_end < row_begin || t < 1) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: bad row range / t");
     if (row_end == row_begin) return KGE_OK;
     if (!peer_tables || !peer_grads) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: null pointer arrays");
     for (int q = 0; q < world; ++q)
         if (!peer_tables[q] || !peer_grads[q]) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: null peer pointer for rank %d", q);
-    const bool need0 = opt->kind != KGE_OPT_SGD || opt->momentum != 0.f;
-    const bool need1 = opt->kind == KGE_OPT_ADAM;
-    if ((need0 && !slot0_shard_dev) || (need1 && !slot1_shard_dev))
+    if (!slots_ok(opt, slot0_shard_dev, slot1_shard_dev))
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_sharded: optimizer slot buffer missing");
     OptimParams o;
     fill_optim(opt, t, o);
@@ -529,16 +542,99 @@ extern "C" int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_con
     return KGE_OK;
 }
 
-extern "C" int64_t kge_rank_workspace_bytes(const kge_handle *h, int64_t b)
+extern "C" int kge_optimizer_step_exchange(kge_handle *h, const kge_optimizer_config *opt_ent,
+                                           const kge_optimizer_config *opt_rel, int64_t t, int32_t world, int32_t rank,
+                                           float *const *peer_tables, float *const *peer_grads, float *zero_grads_dev,
+                                           float *slot0_shard_dev, float *slot1_shard_dev, int64_t row_begin,
+                                           int64_t row_end, uint32_t *const *peer_flags, uint32_t token, int32_t phases,
+                                           double *reg_loss_dev, void *stream)
 {
-    if (!h || b < 0) return 0;
-    return (int64_t)(3 * b * h->L.ld * sizeof(float) + 4 * b * sizeof(int32_t));
+    KGE_CHECK_HANDLE(h, "kge_optimizer_step_exchange");
+    if (int rc = check_optim(opt_ent, "kge_optimizer_step_exchange")) return rc;
+    if (int rc = check_optim(opt_rel, "kge_optimizer_step_exchange")) return rc;
+    if (int rc = check_world(world, rank, "kge_optimizer_step_exchange")) return rc;
+    if (opt_ent->kind != opt_rel->kind || opt_ent->learning_rate != opt_rel->learning_rate || opt_ent->beta_1 != opt_rel->beta_1 ||
+        opt_ent->beta_2 != opt_rel->beta_2 || opt_ent->epsilon != opt_rel->epsilon || opt_ent->momentum != opt_rel->momentum)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_exchange: the two tables may differ in their regulariser only");
+    const int64_t total_rows = h->cfg.n_ent + h->cfg.n_rel;
+    if (row_begin < 0 || row_end < row_begin || row_end > total_rows || t < 1)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_exchange: bad row range / t");
+    if (phases < 0 || phases > 3) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_exchange: phases must be 0..3");
+    if (!peer_tables || !peer_grads || (phases && !peer_flags))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_exchange: null pointer arrays");
+    for (int q = 0; q < world; ++q)
+        if (!peer_tables[q] || !peer_grads[q] || (phases && !peer_flags[q]))
+            return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_exchange: null peer pointer for rank %d", q);
+    if (row_end > row_begin && !slots_ok(opt_ent, slot0_shard_dev, slot1_shard_dev))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_exchange: optimizer slot buffer missing");
+    OptimParams o;
+    fill_optim(opt_ent, t, o);
+    ExchangeParams x;
+    memset(&x, 0, sizeof(x));
+    x.world = world; x.rank = rank; x.phases = phases;
+    for (int q = 0; q < world; ++q) { x.table[q] = peer_tables[q]; x.grad[q] = peer_grads[q]; x.flags[q] = phases ? peer_flags[q] : nullptr; }
+    x.token = token;
+    x.zero_grad = zero_grads_dev;
+    const long long ld4 = h->L.ld / 4;
+    x.total4 = total_rows * ld4;
+    x.off4 = row_begin * ld4;
+    x.n4 = (row_end - row_begin) * ld4;
+    x.ent4 = h->cfg.n_ent * ld4;
+    x.reg_ent = reg_of(opt_ent);
+    x.reg_rel = reg_of(opt_rel);
+    x.slot0 = slot0_shard_dev; x.slot1 = slot1_shard_dev;
+    x.reg_loss = reg_loss_dev;
+    x.done_counter = h->done_counter;
+    KGE_CUDA(launch_optimizer_exchange(o, x, h->sm_count, (cudaStream_t)stream), "kge_optimizer_step_exchange");
+    return KGE_OK;
+}
+
+extern "C" int kge_peer_barrier(kge_handle *h, int32_t world, int32_t rank, uint32_t *const *peer_flags, int32_t slot,
+                                uint32_t token, void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_peer_barrier");
+    if (int rc = check_world(world, rank, "kge_peer_barrier")) return rc;
+    if (slot < 0 || slot > 1 || !peer_flags) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_peer_barrier: bad slot / null flags");
+    for (int q = 0; q < world; ++q)
+        if (!peer_flags[q]) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_peer_barrier: null flag pad for rank %d", q);
+    KGE_CUDA(launch_peer_barrier(world, rank, peer_flags, slot, token, (cudaStream_t)stream), "kge_peer_barrier");
+    return KGE_OK;
+}
+
+// ---- ranking ---------------------------------------------------------------------------------------------
+// caller-owned workspace, carved into 256-byte aligned regions
+struct RankWorkspace {
+    float *qs, *qo, *qaux;   // [b, ld] query vectors (subject side / object side / RotatE object rows)
+    int32_t *qpos, *cnt;     // [b], [b,3]
+    size_t bytes;
+};
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static RankWorkspace carve_rank_workspace(const kge_handle *h, void *base, int64_t b, int64_t /*n_cand*/)
+{
+    RankWorkspace w;
+    char *p = (char *)base;
+    size_t off = 0;
+    const size_t qbytes = align256((size_t)b * h->L.ld * sizeof(float));
+    w.qs = (float *)(p + off); off += qbytes;
+    w.qo = (float *)(p + off); off += qbytes;
+    w.qaux = (float *)(p + off); off += qbytes;
+    w.qpos = (int32_t *)(p + off); off += align256((size_t)b * sizeof(int32_t));
+    w.cnt = (int32_t *)(p + off); off += align256((size_t)3 * b * sizeof(int32_t));
+    w.bytes = off;
+    return w;
+}
+
+extern "C" int64_t kge_rank_workspace_bytes(const kge_handle *h, int64_t b, int64_t n_cand)
+{
+    if (!h || b < 0 || n_cand < 0) return 0;
+    return (int64_t)carve_rank_workspace(h, nullptr, b, n_cand).bytes;
 }
 
 static int rank_impl(kge_handle *h, const kge_shard_map *map, int64_t filt_base, int32_t side, int32_t strategy,
                      const float *ent_dev, const float *rel_dev, const int32_t *triples_dev, int64_t b,
                      const int32_t *cand_ids_dev, int64_t cand_begin, int64_t n_cand, const int64_t *filt_off_dev,
-                     const int32_t *filt_idx_dev, int64_t n_filt, int32_t *ranks_dev, void *stream)
+                     const int32_t *filt_idx_dev, int64_t n_filt, int32_t *ranks_dev, int32_t *counts_dev,
+                     float *scores_dev, void *workspace_dev, int64_t workspace_bytes, void *stream)
 {
     KGE_CHECK_HANDLE(h, "kge_rank");
     if (side != KGE_SIDE_S && side != KGE_SIDE_O) return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for corrupt_side");
@@ -546,25 +642,21 @@ static int rank_impl(kge_handle *h, const kge_shard_map *map, int64_t filt_base,
         return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for ranking_strategy");
     if (b < 0 || n_cand < 0 || cand_begin < 0 || n_filt < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: negative size");
     if (b == 0) return KGE_OK;
-    if (!ent_dev || !rel_dev || !triples_dev || !ranks_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: null pointer");
+    if (!ent_dev || !rel_dev || !triples_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: null pointer");
+    if (!ranks_dev && !counts_dev && !scores_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: no output buffer");
     if (cand_ids_dev && cand_begin != 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: cand_begin must be 0 with cand_ids_dev");
     if (!map && !cand_ids_dev && cand_begin + n_cand > h->cfg.n_ent)
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: candidate range [%lld,%lld) exceeds n_ent %lld",
                     (long long)cand_begin, (long long)(cand_begin + n_cand), (long long)h->cfg.n_ent);
     if ((filt_off_dev == nullptr) != (filt_idx_dev == nullptr) && n_filt > 0)
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: filter offsets and indices must be given together");
+    const int64_t need = kge_rank_workspace_bytes(h, b, n_cand);
+    if (!workspace_dev || workspace_bytes < need)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: workspace of %lld bytes needed (kge_rank_workspace_bytes), got %lld",
+                    (long long)need, (long long)(workspace_dev ? workspace_bytes : 0));
+    if (((uintptr_t)workspace_dev & 255u) != 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (b > h->ws_b) {
-        KGE_CUDA(cudaStreamSynchronize(st), "kge_rank: sync before growing workspace");
-        if (h->ws_q) cudaFree(h->ws_q);
-        if (h->ws_i) cudaFree(h->ws_i);
-        h->ws_q = nullptr; h->ws_i = nullptr; h->ws_b = 0;
-        KGE_CUDA(cudaMalloc(&h->ws_q, (size_t)3 * b * h->L.ld * sizeof(float)), "kge_rank: cudaMalloc workspace");
-        KGE_CUDA(cudaMalloc(&h->ws_i, (size_t)4 * b * sizeof(int32_t)), "kge_rank: cudaMalloc workspace");
-        h->ws_b = b;
-    }
-    float *qs = h->ws_q, *qo = qs + (size_t)b * h->L.ld, *qaux = qo + (size_t)b * h->L.ld;
-    int32_t *qpos = h->ws_i, *cnt = qpos + b;
+    const RankWorkspace w = carve_rank_workspace(h, workspace_dev, b, n_cand);
     if (int rc = refresh_rotation(h, rel_dev, st)) return rc;
     ShardView sv;
     memset(&sv, 0, sizeof(sv));
@@ -573,46 +665,51 @@ static int rank_impl(kge_handle *h, const kge_shard_map *map, int64_t filt_base,
         sv.rows_per_shard = (int)map->rows_per_shard;
         for (int q = 0; q < map->world; ++q) sv.ent[q] = map->ent[q];
     }
-    KGE_CUDA(launch_rank_prepare(h->L, sv, ent_dev, rel_dev, h->rot, triples_dev, b, h->score_scale, qs, qo, qaux, qpos, st),
+    KGE_CUDA(launch_rank_prepare(h->L, sv, ent_dev, rel_dev, h->rot, triples_dev, b, h->score_scale, w.qs, w.qo, w.qaux,
+                                 w.qpos, st),
              "kge_rank: prepare");
-    KGE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)3 * b * sizeof(int32_t), st), "kge_rank: memset");
+    // raw counters: the caller's accumulator, or a zeroed scratch that is finalized into ranks_dev below
+    int32_t *cnt = counts_dev ? counts_dev : w.cnt;
+    if (!counts_dev) KGE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)3 * b * sizeof(int32_t), st), "kge_rank: memset");
     RankParams p;
     memset(&p, 0, sizeof(p));
     p.L = h->L;
     p.side = side;
     p.strategy = strategy;
     p.ent = ent_dev;
-    p.qvec = side == KGE_SIDE_S ? qs : qo;
-    p.qaux = qaux;
-    p.qpos = qpos;
+    p.qvec = side == KGE_SIDE_S ? w.qs : w.qo;
+    p.qaux = w.qaux;
+    p.qpos = w.qpos;
     p.cand_ids = cand_ids_dev;
     p.cand_begin = cand_begin;
     p.n_cand = n_cand;
     p.b = b;
     p.scale = h->score_scale;
     p.filt_base = filt_base;
+    p.scores = scores_dev;
     KGE_CUDA(launch_rank_count(p, cnt, st), "kge_rank: count");
     if (filt_off_dev && n_filt > 0)
         KGE_CUDA(launch_rank_filter_n(p, (const long long *)filt_off_dev, filt_idx_dev, n_filt, cnt, st), "kge_rank: filter");
-    KGE_CUDA(launch_rank_finalize(cnt, b, strategy, ranks_dev, st), "kge_rank: finalize");
+    if (!counts_dev && ranks_dev) KGE_CUDA(launch_rank_finalize(cnt, b, strategy, ranks_dev, st), "kge_rank: finalize");
     return KGE_OK;
 }
 
 extern "C" int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const float *ent_dev, const float *rel_dev,
                         const int32_t *triples_dev, int64_t b, const int32_t *cand_ids_dev, int64_t cand_begin,
                         int64_t n_cand, const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
-                        int32_t *ranks_dev, void *stream)
+                        int32_t *ranks_dev, int32_t *counts_dev, void *workspace_dev, int64_t workspace_bytes, void *stream)
 {
     return rank_impl(h, nullptr, 0, side, strategy, ent_dev, rel_dev, triples_dev, b, cand_ids_dev, cand_begin, n_cand,
-                     filt_off_dev, filt_idx_dev, n_filt, ranks_dev, stream);
+                     filt_off_dev, filt_idx_dev, n_filt, ranks_dev, counts_dev, nullptr, workspace_dev, workspace_bytes, stream);
 }
 
 extern "C" int kge_rank_sharded(kge_handle *h, const kge_shard_map *map, int32_t rank, int32_t side, int32_t strategy,
                                 const float *rel_dev, const int32_t *triples_dev, int64_t b,
                                 const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
-                                int32_t *ranks_dev, void *stream)
+                                int32_t *ranks_dev, int32_t *counts_dev, void *workspace_dev, int64_t workspace_bytes,
+                                void *stream)
 {
-    KGE_CHECK_HANDLE(h, "kge_rank_sharded");
+    if (!h) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank_sharded: null handle");
     if (int rc = check_shard_map(h, map, "kge_rank_sharded")) return rc;
     if (rank < 0 || rank >= map->world) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank_sharded: rank out of range");
     const int64_t first = (int64_t)rank * map->rows_per_shard;
@@ -620,5 +717,28 @@ extern "C" int kge_rank_sharded(kge_handle *h, const kge_shard_map *map, int32_t
     if (n_local > map->rows_per_shard) n_local = map->rows_per_shard;
     if (n_local < 0) n_local = 0;
     return rank_impl(h, map, first, side, strategy, map->ent[rank], rel_dev, triples_dev, b, nullptr, 0, n_local,
-                     filt_off_dev, filt_idx_dev, n_filt, ranks_dev, stream);
+                     filt_off_dev, filt_idx_dev, n_filt, ranks_dev, counts_dev, nullptr, workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" int kge_rank_finalize(kge_handle *h, const int32_t *counts_dev, int64_t b, int32_t strategy, int32_t *ranks_dev,
+                                 void *stream)
+{
+    KGE_CHECK_HANDLE(h, "kge_rank_finalize");
+    if (strategy < KGE_RANK_WORST || strategy > KGE_RANK_MIDDLE)
+        return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for ranking_strategy");
+    if (b < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank_finalize: b < 0");
+    if (b == 0) return KGE_OK;
+    if (!counts_dev || !ranks_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank_finalize: null pointer");
+    KGE_CUDA(launch_rank_finalize(counts_dev, b, strategy, ranks_dev, (cudaStream_t)stream), "kge_rank_finalize");
+    return KGE_OK;
+}
+
+extern "C" int kge_corruption_scores(kge_handle *h, int32_t side, const float *ent_dev, const float *rel_dev,
+                                     const int32_t *triples_dev, int64_t b, const int32_t *cand_ids_dev,
+                                     int64_t cand_begin, int64_t n_cand, float *scores_dev, void *workspace_dev,
+                                     int64_t workspace_bytes, void *stream)
+{
+    if (b > 0 && n_cand > 0 && !scores_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_corruption_scores: null output");
+    return rank_impl(h, nullptr, 0, side, KGE_RANK_WORST, ent_dev, rel_dev, triples_dev, b, cand_ids_dev, cand_begin, n_cand,
+                     nullptr, nullptr, 0, nullptr, nullptr, scores_dev, workspace_dev, workspace_bytes, stream);
 }

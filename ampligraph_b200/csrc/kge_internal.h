@@ -8,7 +8,6 @@
 #define KGE_MAX_PEERS 8
 #define KGE_MIN_RESIDENT_WARPS 8  // tuned on B200: fewer warps/SM than this costs more than re-gathering
 #define KGE_TARGET_WARPS 10
-#define KGE_TEAM_THREADS 640  // team kernel: up to 10 teams of 2 warps (register cap 96/thread)
 
 namespace kge {
 
@@ -28,11 +27,9 @@ struct TrainParams {
     int wk, n_cb;                 // column window (floats per half) and number of windows per row
     int slot_floats;              // stride between row windows in the shared-memory slot
     int resident;                 // 1: one window, one group, rows stay in place between the passes
-    int team;                     // 1: two warps per positive (kge_train_team_kernel), resident + red.v4 only
     int eta_pad;                  // round_up(eta,4)
     int rows_bytes, region_bytes; // per-warp shared-memory carve-up
     int loss, reduction, mode;
-    int scatter_mode;             // enum kge_scatter
     float margin, alpha, score_scale, inv_div;
     double *loss_out;
     float *scores_pos, *scores_neg;
@@ -61,13 +58,33 @@ cudaError_t launch_score_triples(const Layout &L, int nit, const float *ent, con
                                  cudaStream_t st);
 cudaError_t launch_pack(const Layout &L, const float *src, float *dst, long long rows, bool unpack, cudaStream_t st);
 cudaError_t launch_glorot(const Layout &L, float *table, long long rows, unsigned long long seed, cudaStream_t st);
+cudaError_t launch_init_table(const Layout &L, float *table, long long rows, int kind, float a, float b,
+                              unsigned long long seed, cudaStream_t st);
 
 // kge_optim.cu
+struct RegParams {  // lambda*sum|x|^p (+ optional second term: Keras 'l1_l2')
+    int p, p2;
+    float lambda, lambda2;
+};
 struct OptimParams {
     int kind;
     float lr, lr_t, beta1, beta2, eps, momentum;
-    int reg_p;
-    float reg_lambda;
+    RegParams reg;
+};
+struct ExchangeParams {  // kge_optimizer_step_exchange
+    int world, rank, phases;
+    float *table[KGE_MAX_PEERS];        // [ent|rel] parameter block of every rank
+    const float *grad[KGE_MAX_PEERS];   // this step's gradient block of every rank
+    unsigned *flags[KGE_MAX_PEERS];     // flag pad of every rank: 2*world uint32
+    unsigned token;
+    float *zero_grad;                   // local: next step's gradient block, zeroed here (or nullptr)
+    long long total4;                   // float4s in one block
+    long long off4, n4;                 // this rank's shard
+    long long ent4;                     // float4s of the entity part (regulariser switch point)
+    RegParams reg_ent, reg_rel;
+    float *slot0, *slot1;
+    double *reg_loss;
+    unsigned *done_counter;             // handle-owned device counter (last-CTA detection), self-resetting
 };
 cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
                              long long n_floats, double *reg_loss, int sm_count, cudaStream_t st);
@@ -78,6 +95,8 @@ cudaError_t launch_optimizer_lazy(const OptimParams &o, float *table, float *gra
 cudaError_t launch_optimizer_sharded(const OptimParams &o, int world, int rank, float *const *tables, float *const *grads,
                                      float *slot0, float *slot1, long long off_floats, long long n_floats,
                                      double *reg_loss, int sm_count, cudaStream_t st);
+cudaError_t launch_optimizer_exchange(const OptimParams &o, const ExchangeParams &x, int sm_count, cudaStream_t st);
+cudaError_t launch_peer_barrier(int world, int rank, unsigned *const *flags, int slot, unsigned token, cudaStream_t st);
 
 // kge_rank.cu
 struct ShardView {  // row-sharded entity table seen through peer pointers (world <= 1: not sharded)
@@ -95,6 +114,7 @@ struct RankParams {
     long long cand_begin, n_cand, b;
     long long filt_base;   // subtracted from filter ids (global id of the local shard's first row)
     float scale;           // HolE
+    float *scores;         // nullptr, or [b, n_cand] output of every candidate's score (kge_corruption_scores)
 };
 cudaError_t launch_rank_prepare(const Layout &L, const ShardView &sv, const float *ent, const float *rel, const float *rot,
                                 const int32_t *triples, long long b, float scale, float *qvec_s, float *qvec_o,

@@ -113,6 +113,59 @@ __global__ void kge_glorot_kernel(float *__restrict__ table, long long rows, int
     table[idx] = v;
 }
 
+// --------------------------------------------------------------------------
+// The other initialisers tf.keras.initializers.get resolves (EmbeddingLookupLayer.py:105-129), reduced by the
+// caller to four kinds.  One Philox4x32-10 block per element: x,y -> Box-Muller pair, z,w -> a second pair for
+// the truncated normal's first resample; further resamples bump the counter's third word.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ float u01(uint32_t bits) { return ((float)(bits >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+__device__ __forceinline__ float box_muller(uint32_t a, uint32_t b)
+{
+    return sqrtf(-2.f * logf(u01(a))) * cospif(2.f * u01(b));
+}
+
+__global__ void kge_init_table_kernel(float *__restrict__ table, long long rows, int k, int kp, int halves, int kind,
+                                      float a, float b, unsigned long long seed)
+{
+    const int ld = halves * kp;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * ld) return;
+    long long r = idx / ld;
+    int c = (int)(idx - r * ld), h = c / kp, d = c - h * kp;
+    float v = 0.f;
+    if (d < k) {
+        const unsigned long long e = (unsigned long long)r * (unsigned long long)(halves * k) + (unsigned long long)(h * k + d);
+        u32x4 x = philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), 0x494e4954u /*'INIT'*/, 0u, (uint32_t)seed,
+                                (uint32_t)(seed >> 32));
+        if (kind == KGE_INIT_UNIFORM) {
+            v = fmaf(b - a, (float)(x.x >> 8) * (1.0f / 16777216.0f), a);
+        } else if (kind == KGE_INIT_NORMAL) {
+            v = fmaf(b, box_muller(x.x, x.y), a);
+        } else if (kind == KGE_INIT_TRUNCATED_NORMAL) {
+            float n = box_muller(x.x, x.y);
+            if (fabsf(n) > 2.f) n = box_muller(x.z, x.w);
+            for (uint32_t t = 1; fabsf(n) > 2.f && t < 64u; ++t) {  // P(|n|>2) = 4.6 %: a handful of elements get here
+                x = philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), 0x494e4954u, t, (uint32_t)seed, (uint32_t)(seed >> 32));
+                n = box_muller(x.x, x.y);
+                if (fabsf(n) > 2.f) n = box_muller(x.z, x.w);
+            }
+            v = fmaf(b, fminf(fmaxf(n, -2.f), 2.f), a);
+        } else {
+            v = a;
+        }
+    }
+    table[idx] = v;
+}
+
+cudaError_t launch_init_table(const Layout &L, float *table, long long rows, int kind, float a, float b,
+                              unsigned long long seed, cudaStream_t st)
+{
+    long long n = rows * L.ld;
+    if (n == 0) return cudaSuccess;
+    kge_init_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(table, rows, L.k, L.kp, L.halves, kind, a, b, seed);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_glorot(const Layout &L, float *table, long long rows, unsigned long long seed, cudaStream_t st)
 {
     long long n = rows * L.ld;

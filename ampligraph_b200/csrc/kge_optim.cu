@@ -1,25 +1,84 @@
-// kge_optim.cu -- dense optimizer update of one embedding table (sm_100a).
+// kge_optim.cu -- optimizer update of the embedding tables (sm_100a).
 //
 // Replaces OptimizerWrapper.minimize -> tf.keras.optimizers.legacy.*.apply_gradients
-// (optimizers.py:136-168) and the LP regulariser (regularizers.py:14-37), fused:
+// (optimizers.py:136-168) and the regularisers attached to the tables
+// (regularizers.py:14-37, EmbeddingLookupLayer.py:131-155), fused:
 // one streaming pass reads {table, grad, slots}, writes {table, slots} and zeroes
 // the gradient accumulator for the next step.  Semantics are the reference's
 // DENSE ones: legacy Keras sums duplicate IndexedSlices rows first and Adam then
 // decays m, v and moves EVERY row each step, touched or not.
 // Bound: HBM, 8 fp32 streams per element for Adam (4 read + 4 written).
+//
+// Multi-GPU variants (replicated tables): kge_optim_sharded_kernel (one table, caller
+// brackets it with barriers) and kge_optim_exchange_kernel (both tables, the cross-rank
+// barriers are flag exchanges INSIDE the kernel: one launch per step).
 #include <math.h>
 
 #include "kge_internal.h"
 
 namespace kge {
 
-__device__ __forceinline__ float reg_grad(float x, int p, float lam, float *pow_out)
+// d/dx lam*|x|^p = lam*p*|x|^(p-1)*sign(x); *loss += lam*|x|^p
+__device__ __forceinline__ float lp_term(float x, int p, float lam, float *loss)
 {
-    // d/dx lam*|x|^p = lam*p*|x|^(p-1)*sign(x)
-    float ax = fabsf(x), sg = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
-    float pm1 = (p == 2) ? ax : (p == 3) ? ax * ax : (p == 1) ? 1.f : powf(ax, (float)(p - 1));
-    *pow_out = pm1 * ax;
+    const float ax = fabsf(x), sg = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+    const float pm1 = (p == 2) ? ax : (p == 3) ? ax * ax : (p == 1) ? 1.f : powf(ax, (float)(p - 1));
+    *loss += lam * (pm1 * ax);
     return lam * (float)p * pm1 * sg;
+}
+__device__ __forceinline__ float reg_grad(float x, const RegParams &r, float *loss)
+{
+    float g = lp_term(x, r.p, r.lambda, loss);
+    if (r.p2 > 0) g += lp_term(x, r.p2, r.lambda2, loss);
+    return g;
+}
+
+// one element of the legacy update rules (optimizers.py:255-291 -> tf.keras.optimizers.legacy.*)
+template <int KIND>
+__device__ __forceinline__ void apply_rule(float &x, float gg, float &a, float &b, const OptimParams &o)
+{
+    if (KIND == KGE_OPT_ADAM) {
+        a = fmaf(gg - a, 1.f - o.beta1, a);       // m += (g-m)(1-b1)
+        b = fmaf(gg * gg - b, 1.f - o.beta2, b);  // v += (g^2-v)(1-b2)
+        x -= (a * o.lr_t) / (sqrtf(b) + o.eps);
+    } else if (KIND == KGE_OPT_ADAGRAD) {
+        a = fmaf(gg, gg, a);
+        x -= o.lr * gg / (sqrtf(a) + o.eps);
+    } else {  // SGD (momentum optional)
+        if (o.momentum != 0.f) { a = o.momentum * a - o.lr * gg; x += a; }
+        else x -= o.lr * gg;
+    }
+}
+
+template <int KIND, bool REG>
+__device__ __forceinline__ float4 update4(float4 x4, float4 g4, float4 &a4, float4 &b4, const OptimParams &o,
+                                          const RegParams &reg, float &racc)
+{
+    float x[4] = {x4.x, x4.y, x4.z, x4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+    float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float gg = g[e];
+        if (REG) gg += reg_grad(x[e], reg, &racc);
+        apply_rule<KIND>(x[e], gg, a[e], b[e], o);
+    }
+    a4 = make_float4(a[0], a[1], a[2], a[3]);
+    b4 = make_float4(b[0], b[1], b[2], b[3]);
+    return make_float4(x[0], x[1], x[2], x[3]);
+}
+
+// block-reduce the per-thread regulariser loss and add it to the double accumulator
+__device__ __forceinline__ void flush_reg_loss(float racc, double *reg_loss)
+{
+    racc = warp_sum(racc);
+    __shared__ float part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = racc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) t += (double)part[w];
+        if (t != 0.0) atomicAdd(reg_loss, t);
+    }
 }
 
 template <int KIND, bool REG>
@@ -27,60 +86,33 @@ __global__ void __launch_bounds__(256) kge_optim_kernel(float4 *__restrict__ var
                                                         float4 *__restrict__ s0, float4 *__restrict__ s1,
                                                         long long n4, OptimParams o, double *reg_loss)
 {
+    constexpr bool S0 = KIND != KGE_OPT_SGD, S1 = KIND == KGE_OPT_ADAM;
+    const bool mom = KIND == KGE_OPT_SGD && o.momentum != 0.f;
     float racc = 0.f;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 x4 = var[i], g4 = grad[i];
-        float x[4] = {x4.x, x4.y, x4.z, x4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
-        float a[4], b[4];
-        if (KIND != KGE_OPT_SGD || o.momentum != 0.f) { float4 t = s0[i]; a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
-        if (KIND == KGE_OPT_ADAM) { float4 t = s1[i]; b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w; }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float gg = g[e];
-            if (REG) { float pw; gg += reg_grad(x[e], o.reg_p, o.reg_lambda, &pw); racc += pw; }
-            if (KIND == KGE_OPT_ADAM) {
-                a[e] = fmaf(gg - a[e], 1.f - o.beta1, a[e]);       // m += (g-m)(1-b1)
-                b[e] = fmaf(gg * gg - b[e], 1.f - o.beta2, b[e]);  // v += (g^2-v)(1-b2)
-                x[e] -= (a[e] * o.lr_t) / (sqrtf(b[e]) + o.eps);
-            } else if (KIND == KGE_OPT_ADAGRAD) {
-                a[e] = fmaf(gg, gg, a[e]);
-                x[e] -= o.lr * gg / (sqrtf(a[e]) + o.eps);
-            } else {  // SGD (momentum optional)
-                if (o.momentum != 0.f) { a[e] = o.momentum * a[e] - o.lr * gg; x[e] += a[e]; }
-                else x[e] -= o.lr * gg;
-            }
-        }
-        var[i] = make_float4(x[0], x[1], x[2], x[3]);
-        if (KIND != KGE_OPT_SGD || o.momentum != 0.f) s0[i] = make_float4(a[0], a[1], a[2], a[3]);
-        if (KIND == KGE_OPT_ADAM) s1[i] = make_float4(b[0], b[1], b[2], b[3]);
-        grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x4 = var[i], g4 = grad[i], a4 = z, b4 = z;
+        if (S0 || mom) a4 = s0[i];
+        if (S1) b4 = s1[i];
+        var[i] = update4<KIND, REG>(x4, g4, a4, b4, o, o.reg, racc);
+        if (S0 || mom) s0[i] = a4;
+        if (S1) s1[i] = b4;
+        grad[i] = z;
     }
-    if (REG && reg_loss) {
-        racc = warp_sum(racc);
-        __shared__ float part[8];
-        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = racc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)part[w];
-            if (t != 0.0) atomicAdd(reg_loss, (double)o.reg_lambda * t);
-        }
-    }
+    if (REG && reg_loss) flush_reg_loss(racc, reg_loss);
 }
 
 // --------------------------------------------------------------------------
-// Data-parallel optimizer step FUSED with the gradient exchange over NVLink peer memory.
+// Data-parallel optimizer step FUSED with the gradient exchange over NVLink peer memory, ONE table.
 // Tables are replicated, every rank holds a full gradient table produced by its own batch.
 // Rank r owns the row shard [begin, end): it loads that shard of EVERY rank's gradient table
 // (peer loads through NVSwitch), sums them in rank order (deterministic, identical on all
 // ranks), applies the optimizer to its shard -- slots exist only for the shard -- and stores
 // the updated parameters into EVERY rank's table (peer stores).  One kernel = reduce-scatter
-// + sharded optimizer + all-gather; it replaces all-reduce(grad) + a full-table optimizer
-// pass on every replica.  Per rank: (N-1)/N * table bytes in and out over NVLink, optimizer
-// HBM traffic and slot memory divided by N.  The caller brackets it with two cross-rank
-// barriers (all gradients complete / all parameters delivered) and zeroes its own gradient
-// table afterwards.
+// + sharded optimizer + all-gather.  The caller brackets it with two cross-rank barriers and
+// zeroes its own gradient table afterwards (the row-sharded trainer uses it for the small,
+// replicated relation table; the data-parallel trainer uses kge_optim_exchange_kernel).
 // --------------------------------------------------------------------------
 struct PeerPtrs {
     float4 *table[KGE_MAX_PEERS];
@@ -92,7 +124,10 @@ __global__ void __launch_bounds__(256) kge_optim_sharded_kernel(PeerPtrs pp, int
                                                                 float4 *__restrict__ s1, long long off4,
                                                                 long long n4, OptimParams o, double *reg_loss)
 {
+    constexpr bool S0 = KIND != KGE_OPT_SGD, S1 = KIND == KGE_OPT_ADAM;
+    const bool mom = KIND == KGE_OPT_SGD && o.momentum != 0.f;
     float racc = 0.f;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const long long gi = off4 + i;
@@ -100,49 +135,21 @@ __global__ void __launch_bounds__(256) kge_optim_sharded_kernel(PeerPtrs pp, int
 #pragma unroll
         for (int q = 0; q < KGE_MAX_PEERS; ++q)
             if (q < world) gq[q] = __ldcg(pp.grad[q] + gi);  // peer (or local) load, L2-coherent
-        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 g4 = z;
 #pragma unroll
         for (int q = 0; q < KGE_MAX_PEERS; ++q)
-            if (q < world) { g[0] += gq[q].x; g[1] += gq[q].y; g[2] += gq[q].z; g[3] += gq[q].w; }
-        float4 x4 = pp.table[rank][gi];  // all replicas are identical; read the local one
-        float x[4] = {x4.x, x4.y, x4.z, x4.w};
-        float a[4], b[4];
-        if (KIND != KGE_OPT_SGD || o.momentum != 0.f) { float4 t = s0[i]; a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
-        if (KIND == KGE_OPT_ADAM) { float4 t = s1[i]; b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w; }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float gg = g[e];
-            if (REG) { float pw; gg += reg_grad(x[e], o.reg_p, o.reg_lambda, &pw); racc += pw; }
-            if (KIND == KGE_OPT_ADAM) {
-                a[e] = fmaf(gg - a[e], 1.f - o.beta1, a[e]);
-                b[e] = fmaf(gg * gg - b[e], 1.f - o.beta2, b[e]);
-                x[e] -= (a[e] * o.lr_t) / (sqrtf(b[e]) + o.eps);
-            } else if (KIND == KGE_OPT_ADAGRAD) {
-                a[e] = fmaf(gg, gg, a[e]);
-                x[e] -= o.lr * gg / (sqrtf(a[e]) + o.eps);
-            } else {
-                if (o.momentum != 0.f) { a[e] = o.momentum * a[e] - o.lr * gg; x[e] += a[e]; }
-                else x[e] -= o.lr * gg;
-            }
-        }
-        const float4 xn = make_float4(x[0], x[1], x[2], x[3]);
+            if (q < world) { g4.x += gq[q].x; g4.y += gq[q].y; g4.z += gq[q].z; g4.w += gq[q].w; }
+        float4 x4 = pp.table[rank][gi], a4 = z, b4 = z;  // all replicas are identical; read the local one
+        if (S0 || mom) a4 = s0[i];
+        if (S1) b4 = s1[i];
+        const float4 xn = update4<KIND, REG>(x4, g4, a4, b4, o, o.reg, racc);
 #pragma unroll
         for (int q = 0; q < KGE_MAX_PEERS; ++q)
             if (q < world) __stcg(pp.table[q] + gi, xn);  // deliver the updated rows to every replica
-        if (KIND != KGE_OPT_SGD || o.momentum != 0.f) s0[i] = make_float4(a[0], a[1], a[2], a[3]);
-        if (KIND == KGE_OPT_ADAM) s1[i] = make_float4(b[0], b[1], b[2], b[3]);
+        if (S0 || mom) s0[i] = a4;
+        if (S1) s1[i] = b4;
     }
-    if (REG && reg_loss) {
-        racc = warp_sum(racc);
-        __shared__ float part[8];
-        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = racc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)part[w];
-            if (t != 0.0) atomicAdd(reg_loss, (double)o.reg_lambda * t);
-        }
-    }
+    if (REG && reg_loss) flush_reg_loss(racc, reg_loss);
 }
 
 cudaError_t launch_optimizer_sharded(const OptimParams &o, int world, int rank, float *const *tables, float *const *grads,
@@ -159,7 +166,7 @@ cudaError_t launch_optimizer_sharded(const OptimParams &o, int world, int rank, 
     long long want = (n4 + 255) / 256;
     int grid = (int)(want < (long long)sm_count * 8 ? want : (long long)sm_count * 8);
     float4 *a = (float4 *)slot0, *b = (float4 *)slot1;
-    const bool reg = o.reg_p > 0;
+    const bool reg = o.reg.p > 0;
     const long long off4 = off_floats / 4;
 #define KGE_OPTS(K)                                                                                          \
     if (reg) kge_optim_sharded_kernel<K, true><<<grid, 256, 0, st>>>(pp, world, rank, a, b, off4, n4, o, reg_loss); \
@@ -171,6 +178,206 @@ cudaError_t launch_optimizer_sharded(const OptimParams &o, int world, int rank, 
     default: return cudaErrorInvalidValue;
     }
 #undef KGE_OPTS
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------
+// Cross-rank flag barrier over peer memory.  Every rank owns a pad of 2*world uint32 (slot s, writer
+// q at pad[s*world + q]); a rank signals by storing a strictly increasing token into ITS entry of
+// every rank's pad (st.release.sys through the peer mapping) and waits by polling its own pad
+// (ld.acquire.sys, local memory).  Tokens only grow, so flags are never reset.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// token comparison that survives wrap-around of the 32-bit counter
+__device__ __forceinline__ bool token_reached(unsigned seen, unsigned token) { return (int)(seen - token) >= 0; }
+
+struct FlagPtrs {
+    unsigned *pad[KGE_MAX_PEERS];
+};
+// thread q < world signals rank q; call from one warp
+__device__ __forceinline__ void flags_signal(const FlagPtrs &f, int world, int rank, int slot, unsigned token, int lane)
+{
+    if (lane < world) st_release_sys(f.pad[lane] + slot * world + rank, token);
+}
+// thread q < world waits for rank q's signal in the local pad; call from one warp
+__device__ __forceinline__ void flags_wait(const FlagPtrs &f, int world, int rank, int slot, unsigned token, int lane)
+{
+    if (lane < world) {
+        const unsigned *p = f.pad[rank] + slot * world + lane;
+        while (!token_reached(ld_acquire_sys(p), token)) __nanosleep(64);
+    }
+    __syncwarp();
+}
+
+__global__ void kge_peer_barrier_kernel(FlagPtrs f, int world, int rank, int slot, unsigned token)
+{
+    __threadfence_system();
+    flags_signal(f, world, rank, slot, token, threadIdx.x);
+    flags_wait(f, world, rank, slot, token, threadIdx.x);
+}
+
+cudaError_t launch_peer_barrier(int world, int rank, unsigned *const *flags, int slot, unsigned token, cudaStream_t st)
+{
+    FlagPtrs f;
+    for (int q = 0; q < KGE_MAX_PEERS; ++q) f.pad[q] = q < world ? flags[q] : nullptr;
+    kge_peer_barrier_kernel<<<1, 32, 0, st>>>(f, world, rank, slot, token);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------
+// The ONE-LAUNCH data-parallel step tail (kge_optimizer_step_exchange): both replicated tables as
+// one contiguous [ent|rel] block.
+//   phase 1  every CTA: warp 0 signals slot 0 (idempotent: all CTAs store the same token, so no CTA
+//            depends on another CTA of this grid being scheduled) and waits until every rank has
+//            entered the kernel -- i.e. finished its training kernel, by stream order: all gradient
+//            blocks are complete.
+//   phase 2  reduce-scatter + optimizer + all-gather over this rank's shard, 4 float4 per thread per
+//            trip (4*world peer loads in flight per thread); the local NEXT-step gradient block is
+//            zeroed on the way (gradient blocks are double-buffered, nobody memsets).
+//   phase 3  each CTA fences its peer stores at system scope and counts itself done; the LAST CTA
+//            signals slot 1 to every rank and waits for every rank's slot-1 token, which holds the
+//            kernel open until all parameters destined for this rank have landed: the next kernel
+//            on the stream may read the tables.
+// --------------------------------------------------------------------------
+struct ExchangeArgs {
+    float4 *table[KGE_MAX_PEERS];
+    const float4 *grad[KGE_MAX_PEERS];
+    FlagPtrs flags;
+    float4 *zero_grad;
+    float4 *s0, *s1;
+    long long total4, off4, n4, ent4;
+    RegParams reg_ent, reg_rel;
+    double *reg_loss;
+    unsigned *done_counter;
+    unsigned token;
+    int world, rank, phases;
+};
+
+template <int KIND, bool REG, int WORLD>
+__global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeArgs x, const OptimParams o)
+{
+    constexpr bool S0 = KIND != KGE_OPT_SGD, S1 = KIND == KGE_OPT_ADAM;
+    constexpr int U = WORLD <= 4 ? 4 : 2;  // float4s per thread per trip (U*WORLD peer loads in flight per thread)
+    const bool mom = KIND == KGE_OPT_SGD && o.momentum != 0.f;
+    const int rank = x.rank;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+
+    // zero the next step's local gradient block: independent of the peers, overlaps the barrier wait
+    if (x.zero_grad)
+        for (long long i = tid; i < x.total4; i += nthreads) __stcg(x.zero_grad + i, z);
+
+    if (x.phases & 1) {
+        if (threadIdx.x < 32) {
+            flags_signal(x.flags, WORLD, rank, 0, x.token, threadIdx.x);
+            flags_wait(x.flags, WORLD, rank, 0, x.token, threadIdx.x);
+        }
+        __syncthreads();
+    }
+
+    float racc = 0.f;
+    for (long long base = tid; base < x.n4; base += nthreads * U) {
+        float4 gq[U][WORLD];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + u * nthreads;
+            if (i < x.n4) {
+#pragma unroll
+                for (int q = 0; q < WORLD; ++q) gq[u][q] = __ldcg(x.grad[q] + x.off4 + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + u * nthreads;
+            if (i >= x.n4) continue;
+            const long long gi = x.off4 + i;
+            float4 g4 = gq[u][0];
+#pragma unroll
+            for (int q = 1; q < WORLD; ++q) { g4.x += gq[u][q].x; g4.y += gq[u][q].y; g4.z += gq[u][q].z; g4.w += gq[u][q].w; }
+            float4 x4 = x.table[rank][gi], a4 = z, b4 = z;
+            if (S0 || mom) a4 = x.s0[i];
+            if (S1) b4 = x.s1[i];
+            const float4 xn = update4<KIND, REG>(x4, g4, a4, b4, o, gi < x.ent4 ? x.reg_ent : x.reg_rel, racc);
+#pragma unroll
+            for (int q = 0; q < WORLD; ++q) __stcg(x.table[q] + gi, xn);
+            if (S0 || mom) x.s0[i] = a4;
+            if (S1) x.s1[i] = b4;
+        }
+    }
+    if (REG && x.reg_loss) flush_reg_loss(racc, x.reg_loss);
+
+    if (x.phases & 2) {
+        __threadfence_system();  // this thread's peer stores are performed before the CTA reports done
+        __syncthreads();
+        __shared__ int last;
+        if (threadIdx.x == 0) last = (atomicAdd(x.done_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (last && threadIdx.x < 32) {
+            if (threadIdx.x == 0) *x.done_counter = 0u;  // self-reset for the next launch (stream-ordered)
+            __threadfence_system();
+            flags_signal(x.flags, WORLD, rank, 1, x.token, threadIdx.x);
+            flags_wait(x.flags, WORLD, rank, 1, x.token, threadIdx.x);
+        }
+    }
+}
+
+cudaError_t launch_optimizer_exchange(const OptimParams &o, const ExchangeParams &xp, int sm_count, cudaStream_t st)
+{
+    ExchangeArgs a;
+    for (int q = 0; q < KGE_MAX_PEERS; ++q) {
+        a.table[q] = q < xp.world ? (float4 *)xp.table[q] : nullptr;
+        a.grad[q] = q < xp.world ? (const float4 *)xp.grad[q] : nullptr;
+        a.flags.pad[q] = q < xp.world ? xp.flags[q] : nullptr;
+    }
+    a.zero_grad = (float4 *)xp.zero_grad;
+    a.s0 = (float4 *)xp.slot0;
+    a.s1 = (float4 *)xp.slot1;
+    a.total4 = xp.total4; a.off4 = xp.off4; a.n4 = xp.n4; a.ent4 = xp.ent4;
+    a.reg_ent = xp.reg_ent; a.reg_rel = xp.reg_rel;
+    a.reg_loss = xp.reg_loss;
+    a.done_counter = xp.done_counter;
+    a.token = xp.token;
+    a.world = xp.world; a.rank = xp.rank; a.phases = xp.phases;
+    // no CTA ever waits for another CTA of this grid (phase 1 is per CTA, phase 3 is the last finisher alone), so the
+    // grid need not be co-resident; a few CTAs per SM are enough to keep the NVLink loads in flight
+    long long work = a.n4 > a.total4 / 4 ? a.n4 : a.total4 / 4;
+    long long want = (work + 255) / 256;
+    if (want < 1) want = 1;
+    int grid = (int)(want < (long long)sm_count * 4 ? want : (long long)sm_count * 4);
+    const bool reg = xp.reg_ent.p > 0 || xp.reg_rel.p > 0;
+#define KGE_OPTX2(K, W)                                                                   \
+    if (reg) kge_optim_exchange_kernel<K, true, W><<<grid, 256, 0, st>>>(a, o);           \
+    else kge_optim_exchange_kernel<K, false, W><<<grid, 256, 0, st>>>(a, o);
+#define KGE_OPTX(K)                                                                       \
+    switch (xp.world) {                                                                   \
+    case 1: KGE_OPTX2(K, 1) break;                                                        \
+    case 2: KGE_OPTX2(K, 2) break;                                                        \
+    case 3: KGE_OPTX2(K, 3) break;                                                        \
+    case 4: KGE_OPTX2(K, 4) break;                                                        \
+    case 5: KGE_OPTX2(K, 5) break;                                                        \
+    case 6: KGE_OPTX2(K, 6) break;                                                        \
+    case 7: KGE_OPTX2(K, 7) break;                                                        \
+    case 8: KGE_OPTX2(K, 8) break;                                                        \
+    default: return cudaErrorInvalidValue;                                                \
+    }
+    switch (o.kind) {
+    case KGE_OPT_SGD: KGE_OPTX(KGE_OPT_SGD) break;
+    case KGE_OPT_ADAM: KGE_OPTX(KGE_OPT_ADAM) break;
+    case KGE_OPT_ADAGRAD: KGE_OPTX(KGE_OPT_ADAGRAD) break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef KGE_OPTX
+#undef KGE_OPTX2
     return cudaGetLastError();
 }
 
@@ -188,9 +395,12 @@ __global__ void __launch_bounds__(256) kge_optim_lazy_kernel(float *__restrict__
                                                              long long rows, int ld, const int *__restrict__ row_stamp,
                                                              int stamp, OptimParams o, double *reg_loss)
 {
+    constexpr bool S0 = KIND != KGE_OPT_SGD, S1 = KIND == KGE_OPT_ADAM;
+    const bool mom = KIND == KGE_OPT_SGD && o.momentum != 0.f;
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     float racc = 0.f;
     for (long long base = warp0 * 32; base < rows; base += n_warps * 32) {
         const long long r = base + lane;
@@ -201,35 +411,19 @@ __global__ void __launch_bounds__(256) kge_optim_lazy_kernel(float *__restrict__
             const size_t off = (size_t)(base + b) * ld;
             for (int c = lane * 4; c < ld; c += 128) {
                 float4 x4 = *reinterpret_cast<float4 *>(var + off + c), g4 = *reinterpret_cast<float4 *>(grad + off + c);
-                float x[4] = {x4.x, x4.y, x4.z, x4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w}, a[4], bb[4];
-                if (KIND != KGE_OPT_SGD || o.momentum != 0.f) { float4 t = *reinterpret_cast<float4 *>(s0 + off + c); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
-                if (KIND == KGE_OPT_ADAM) { float4 t = *reinterpret_cast<float4 *>(s1 + off + c); bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w; }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float gg = g[e];
-                    if (REG) { float pw; gg += reg_grad(x[e], o.reg_p, o.reg_lambda, &pw); racc += pw; }
-                    if (KIND == KGE_OPT_ADAM) {
-                        a[e] = fmaf(gg - a[e], 1.f - o.beta1, a[e]);
-                        bb[e] = fmaf(gg * gg - bb[e], 1.f - o.beta2, bb[e]);
-                        x[e] -= (a[e] * o.lr_t) / (sqrtf(bb[e]) + o.eps);
-                    } else if (KIND == KGE_OPT_ADAGRAD) {
-                        a[e] = fmaf(gg, gg, a[e]);
-                        x[e] -= o.lr * gg / (sqrtf(a[e]) + o.eps);
-                    } else {
-                        if (o.momentum != 0.f) { a[e] = o.momentum * a[e] - o.lr * gg; x[e] += a[e]; }
-                        else x[e] -= o.lr * gg;
-                    }
-                }
-                *reinterpret_cast<float4 *>(var + off + c) = make_float4(x[0], x[1], x[2], x[3]);
-                if (KIND != KGE_OPT_SGD || o.momentum != 0.f) *reinterpret_cast<float4 *>(s0 + off + c) = make_float4(a[0], a[1], a[2], a[3]);
-                if (KIND == KGE_OPT_ADAM) *reinterpret_cast<float4 *>(s1 + off + c) = make_float4(bb[0], bb[1], bb[2], bb[3]);
-                *reinterpret_cast<float4 *>(grad + off + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 a4 = z, b4 = z;
+                if (S0 || mom) a4 = *reinterpret_cast<float4 *>(s0 + off + c);
+                if (S1) b4 = *reinterpret_cast<float4 *>(s1 + off + c);
+                *reinterpret_cast<float4 *>(var + off + c) = update4<KIND, REG>(x4, g4, a4, b4, o, o.reg, racc);
+                if (S0 || mom) *reinterpret_cast<float4 *>(s0 + off + c) = a4;
+                if (S1) *reinterpret_cast<float4 *>(s1 + off + c) = b4;
+                *reinterpret_cast<float4 *>(grad + off + c) = z;
             }
         }
     }
     if (REG && reg_loss) {
         racc = warp_sum(racc);
-        if (lane == 0 && racc != 0.f) atomicAdd(reg_loss, (double)o.reg_lambda * (double)racc);
+        if (lane == 0 && racc != 0.f) atomicAdd(reg_loss, (double)racc);
     }
 }
 
@@ -240,7 +434,7 @@ cudaError_t launch_optimizer_lazy(const OptimParams &o, float *table, float *gra
     if (rows == 0) return cudaSuccess;
     long long want = (rows + 255) / 256;  // 8 warps x 32 rows per block
     int grid = (int)(want < (long long)sm_count * 8 ? want : (long long)sm_count * 8);
-    const bool reg = o.reg_p > 0;
+    const bool reg = o.reg.p > 0;
 #define KGE_OPTL(K)                                                                                                      \
     if (reg) kge_optim_lazy_kernel<K, true><<<grid, 256, 0, st>>>(table, grad, slot0, slot1, rows, ld, row_stamp, stamp, o, reg_loss); \
     else kge_optim_lazy_kernel<K, false><<<grid, 256, 0, st>>>(table, grad, slot0, slot1, rows, ld, row_stamp, stamp, o, reg_loss);
@@ -262,7 +456,7 @@ cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, fl
     long long want = (n4 + 255) / 256;
     int grid = (int)(want < (long long)sm_count * 8 ? want : (long long)sm_count * 8);
     float4 *v = (float4 *)table, *g = (float4 *)grad, *a = (float4 *)slot0, *b = (float4 *)slot1;
-    const bool reg = o.reg_p > 0;
+    const bool reg = o.reg.p > 0;
 #define KGE_OPT(K)                                                                            \
     if (reg) kge_optim_kernel<K, true><<<grid, 256, 0, st>>>(v, g, a, b, n4, o, reg_loss);    \
     else kge_optim_kernel<K, false><<<grid, 256, 0, st>>>(v, g, a, b, n4, o, reg_loss);

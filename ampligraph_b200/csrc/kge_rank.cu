@@ -295,8 +295,11 @@ __global__ void __launch_bounds__(RK_THREADS) kge_rank_tile_kernel(const RankPar
         int gt = 0, eq = 0;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const bool cok = (c0 + cg * 128 + lane + 32 * m) < p.n_cand;
-            const int qc = quantise(rank_finish<OP>(acc[m][i], p.scale));
+            const long long c = c0 + cg * 128 + lane + 32 * m;
+            const bool cok = c < p.n_cand;
+            const float sc = rank_finish<OP>(acc[m][i], p.scale);
+            if (p.scores && qok && cok) p.scores[(size_t)q * p.n_cand + c] = sc;
+            const int qc = quantise(sc);
             gt += __popc(__ballot_sync(0xffffffffu, cok && (qp < qc)));
             eq += __popc(__ballot_sync(0xffffffffu, cok && (qp == qc)));
         }
@@ -431,8 +434,11 @@ __global__ void __launch_bounds__(RD_THREADS, 2) kge_rank_dot_kernel(const RankP
             float lo, hi;
             asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[m][i >> 1]));
             const float a = (i & 1) ? hi : lo;
-            const bool cok = (c0 + cg * 128 + lane + 32 * m) < p.n_cand;
-            const int qc = quantise(rank_finish<OP_DOT>(a, p.scale));
+            const long long c = c0 + cg * 128 + lane + 32 * m;
+            const bool cok = c < p.n_cand;
+            const float sc = rank_finish<OP_DOT>(a, p.scale);
+            if (p.scores && qok && cok) p.scores[(size_t)q * p.n_cand + c] = sc;
+            const int qc = quantise(sc);
             gt += __popc(__ballot_sync(0xffffffffu, cok && (qp < qc)));
             eq += __popc(__ballot_sync(0xffffffffu, cok && (qp == qc)));
         }

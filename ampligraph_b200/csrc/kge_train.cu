@@ -12,13 +12,15 @@
 // time.  The warp's (3+G) embedding rows are gathered from HBM/L2 into its
 // shared-memory slot by the copy engine (cp.async.bulk, one 1-D bulk copy per
 // row, completion on a per-warp mbarrier); scores, loss and dL/dscore are
-// computed from shared memory; gradient rows are written IN PLACE over the
-// gathered rows and pushed to the gradient tables by the copy engine again
-// (cp.reduce.async.bulk ... .add.f32 -- an element-wise fp32 atomic add of a
-// whole row; scatter mode KGE_SCATTER_BULK) or, alternatively, emitted straight from
-// registers with red.global.add.v4.f32 (KGE_SCATTER_RED_V4).  The reference re-gathers s,p,o for every corruption
-// (3(1+eta) rows per positive); here each needed row moves once: (3+eta) rows
-// in, (3+eta) gradient rows out = 2(3+eta)*ld*4 bytes per positive.
+// computed from shared memory, which stays read-only after the gather; gradient
+// float4s go straight from registers to the gradient tables with
+// red.global.add.v4.f32.  (Round 1 also carried a copy-engine scatter --
+// cp.reduce.async.bulk of whole rows staged in shared memory -- and a
+// two-warps-per-positive variant; both measured slower on B200, 195 vs 165 us and
+// +10 % on cfg2, profiles/r1a_*, and were removed.)  The reference re-gathers
+// s,p,o for every corruption (3(1+eta) rows per positive); here each needed row
+// moves once: (3+eta) rows in, (3+eta) gradient rows out = 2(3+eta)*ld*4 bytes
+// per positive.
 #include <math.h>
 
 #include "kge_internal.h"
@@ -92,24 +94,17 @@ __device__ __forceinline__ float4 f4sgn(float4 a) { return make_float4(sgnf(a.x)
 __device__ __forceinline__ float f4abssum(float4 a) { return (fabsf(a.x) + fabsf(a.y)) + (fabsf(a.z) + fabsf(a.w)); }
 
 // --------------------------------------------------------------------------
-// gradient sinks: where a computed gradient float4 goes.
-//   SinkSmem  overwrite the gathered row in shared memory (pushed later, whole row at a
-//             time, by cp.reduce.async.bulk -- the copy engine does the atomics)
-//   SinkRed   red.global.add.v4.f32 straight from registers into the gradient table
+// gradient sink: red.global.add.v4.f32 straight from registers into the gradient table
+// (the scorers keep a Sink template parameter so that a profiling build can swap it).
 // --------------------------------------------------------------------------
 __device__ __forceinline__ void red_add_v4(float *g, float4 v)
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
-struct SinkSmem {
-    static constexpr bool kDirect = false;
-    static __device__ __forceinline__ void put(float *slot, float *, int soff, int, float4 v) { f4st(slot + soff, v); }
-};
 // -DKGE_PROFILE_NOSCATTER builds a profiling variant that drops the gradient scatter (how much of the kernel the atomics
 // cost).  The product never tests a run-time flag here: a branch around every RED cost 3.5 % (cfg2) to 11 % (cfg3).
 struct SinkRed {
-    static constexpr bool kDirect = true;
     static __device__ __forceinline__ void put(float *, float *grow, int, int goff, float4 v)
     {
 #ifdef KGE_PROFILE_NOSCATTER
@@ -515,7 +510,6 @@ struct Scorer<KGE_ROTATE, NIT> {
                 Sink::put(o, go, 4 * c, 4 * c, a + Zsr[it]);
                 Sink::put(o, go, hs + 4 * c, kp + 4 * c, b + Zsi[it]);
                 Sink::put(p, gp, 4 * c, 4 * c, inv_div * (Aphi[it] + (Zr * Yi[it] - Zi * Yr[it])));
-                if (!Sink::kDirect) Sink::put(p, gp, hs + 4 * c, kp + 4 * c, f4zero());
             }
         }
     }
@@ -704,9 +698,10 @@ __device__ __forceinline__ float *gent_row(const TrainParams &p, int id)
 }
 
 // RESIDENT = one window and one group (decided on the host): the window/group machinery folds away.
-template <int MODEL, int NIT, class Sink, bool RESIDENT>
+template <int MODEL, int NIT, bool RESIDENT>
 __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kernel(const TrainParams p)
 {
+    using Sink = SinkRed;
     constexpr int HALVES = (MODEL == KGE_TRANSE || MODEL == KGE_DISTMULT) ? 1 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -802,20 +797,6 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
             bulk_commit();
         };
         const bool use_stash = !RESIDENT && p.stash != nullptr;
-        // push `cnt` gradient row windows from shared memory into the gradient table (bulk scatter mode)
-        auto scatter = [&](float *srcw, int cnt, int cb, auto dst) {
-            const int wch_t = min(wk, kp - cb * wk);
-            const uint32_t bytes = (n_cb == 1) ? (uint32_t)ld * 4u : (uint32_t)wch_t * 4u;
-            const int copies = (n_cb == 1) ? 1 : HALVES;
-            fence_proxy_async_smem();
-            __syncwarp();
-            for (int r = lane; r < cnt * copies; r += 32) {
-                const int row = (copies == 1) ? r : r / HALVES, h = (copies == 1) ? 0 : r - row * HALVES;
-                bulk_reduce_add_f32(dst(row) + h * kp + cb * wk, srcw + (size_t)row * lw + h * wk, bytes);
-            }
-            bulk_commit();
-        };
-
         Scorer<MODEL, NIT> S;
         if constexpr (HALVES == 2) { S.kp = kp; S.hs = wk; }
         float P = 0.f;
@@ -889,12 +870,10 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                 const bool top = (g == n_groups - 1);
                 const bool still_there = (cb == n_cb - 1 && top);  // left in place by pass A
                 if (top && !still_there) {  // first visit of this window: s, p, o come along, state is rebuilt
-                    if (!Sink::kDirect) bulk_wait_read_all();  // copy engine done reading what we overwrite
                     __syncwarp();
                     issue(buf, cb, true, j0, gsz, use_stash);
                 }
                 if (g > 0) {  // prefetch the next (lower) group into the other buffer
-                    if (!Sink::kDirect) bulk_wait_read_all();
                     __syncwarp();
                     issue(buf ^ 1, cb, false, j0 - G, G, use_stash);
                 }
@@ -913,153 +892,13 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                                                   gent_row(p, nid[j0 + a]) + gofs, gent_row(p, nid[j0 + b]) + gofs,
                                                   scale * sc[j0 + a], has_b ? scale * sc[j0 + b] : 0.f, has_b);
                     });
-                if (!Sink::kDirect) scatter(nrows, gsz, cb, [&](int r) { return gent_row(p, nid[j0 + r]); });
                 __syncwarp();
             }
             S.template finish<Sink>(srow, prow, orow, gs_row + gofs, gp_row + gofs, go_row + gofs, scale * dP, p.inv_div);
-            if (!Sink::kDirect) scatter(rows, 3, cb, [&](int r) { return r == 0 ? gs_row : r == 1 ? gp_row : go_row; });
         }
-        if (!Sink::kDirect) bulk_wait_read_all();  // slot is reused by the next positive's gather
         __syncwarp();
     }
-    if (!Sink::kDirect) bulk_wait_all();
     if (p.loss_out && p.mode == KGE_STEP_FUSED && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_out, loss_acc);
-}
-
-// --------------------------------------------------------------------------
-// Team variant of the resident kernel: TWO warps own one positive and split its columns (chunk
-// stride 64), sharing one shared-memory slot.  Shared memory (13 rows per positive for cfg2) is what
-// limits residency, so two warps per slot double the warps per SM at the same footprint (20 instead
-// of 11 for cfg2) and halve the per-lane register state.  Cost: partial scores are exchanged through
-// shared memory (one 64-thread named barrier) and the per-positive prologue / loss is executed by both
-// warps.  red.v4 scatter only.
-// --------------------------------------------------------------------------
-__device__ __forceinline__ void team_sync(int id, int threads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-template <int MODEL, int NIT>
-__global__ void __launch_bounds__(KGE_TEAM_THREADS) kge_train_team_kernel(const TrainParams p)
-{
-    constexpr int WPP = 2;
-    using Sink = SinkRed;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int team = warp / WPP, tw = warp % WPP, tlane = tw * 32 + lane;
-    const int n_teams = (blockDim.x >> 5) / WPP;
-    unsigned char *region = smem_raw + (size_t)team * p.region_bytes;
-    float *rows = reinterpret_cast<float *>(region);                          // (3+eta) rows, shared by the team
-    unsigned char *aux = region + p.rows_bytes + (size_t)tw * (3 * p.eta_pad * 4);
-    float *sc = reinterpret_cast<float *>(aux);                               // per warp: scores / dL/dscore
-    int *nid = reinterpret_cast<int *>(sc + p.eta_pad);
-    int *nside = nid + p.eta_pad;
-    float *part = reinterpret_cast<float *>(region + p.rows_bytes + (size_t)WPP * (3 * p.eta_pad * 4));  // [WPP][eta_pad+4]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(part + WPP * (p.eta_pad + 4));
-    const int pstride = p.eta_pad + 4;
-
-    if (tw == 0 && lane == 0) mbar_init(bar, 1);
-    fence_mbar_init();
-    fence_proxy_async_smem();
-    __syncthreads();
-
-    const int ld = p.ld, eta = p.eta, lw = p.slot_floats;
-    const uint32_t row_bytes = (uint32_t)ld * 4u;
-    float *srow = rows, *prow = rows + lw, *orow = rows + 2 * lw, *nrows = rows + 3 * lw;
-    const float scale = p.score_scale;
-    uint32_t phase = 0;
-    double loss_acc = 0.0;
-
-    const long long stride = (long long)gridDim.x * n_teams;
-    for (long long i = (long long)blockIdx.x * n_teams + team; i < p.B; i += stride) {
-        const int s_id = p.triples[3 * i], p_id = p.triples[3 * i + 1], o_id = p.triples[3 * i + 2];
-        for (int j = lane; j < eta; j += 32) {  // both warps draw the same corruptions into their own copies
-            int keep, repl;
-            const unsigned long long r = (unsigned long long)j * (unsigned long long)p.B + (unsigned long long)i;
-            if (p.neg_ent) { repl = p.neg_ent[r]; keep = p.neg_keep[r] ? 1 : 0; }
-            else draw_corruption(p.seed, p.step, r, p.n_ent, &keep, &repl);
-            nid[j] = repl;
-            nside[j] = keep;
-            if (tw == 0 && p.stamp_ent && p.mode != KGE_STEP_FORWARD_ONLY) stamp_ent_row(p, repl);
-        }
-        if (tw == 0 && p.stamp_ent && p.mode != KGE_STEP_FORWARD_ONLY) {
-            if (lane == 0) stamp_ent_row(p, s_id);
-            if (lane == 1) stamp_ent_row(p, o_id);
-            if (lane == 2 && p.stamp_rel) p.stamp_rel[p_id] = p.stamp;
-        }
-        __syncwarp();
-        team_sync(team + 1, WPP * 32);  // the whole team is done with the previous positive's rows
-        if (tw == 0) {
-            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(3 + eta) * row_bytes);
-            __syncwarp();
-            for (int r = lane; r < 3 + eta; r += 32) {
-                const float *src = r == 0 ? ent_row(p, s_id) : r == 1 ? p.rel + (size_t)p_id * ld : r == 2 ? ent_row(p, o_id)
-                                                                                                        : ent_row(p, nid[r - 3]);
-                bulk_load(rows + (size_t)r * lw, src, row_bytes, bar);
-            }
-        }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-
-        Scorer<MODEL, NIT> S;
-        S.nch = p.nch;
-        S.cs = 32 * WPP;
-        if constexpr (MODEL != KGE_TRANSE && MODEL != KGE_DISTMULT) { S.kp = p.kp; S.hs = p.kp; }
-        float *mine = part + tw * pstride;
-        {
-            const float pp = warp_sum(S.prep(srow, prow, orow, tlane));
-            if (lane == 0) mine[eta] = pp;
-        }
-        for_each_pair_by_side(
-            nside, eta, lane,
-            [&](int a, int b, bool has_b) {
-                float pa, pb;
-                S.template partial2<0>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
-                warp_sum2(pa, pb);
-                if (lane == 0) { mine[a] = pa; if (has_b) mine[b] = pb; }
-            },
-            [&](int a, int b, bool has_b) {
-                float pa, pb;
-                S.template partial2<1>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
-                warp_sum2(pa, pb);
-                if (lane == 0) { mine[a] = pa; if (has_b) mine[b] = pb; }
-            });
-        team_sync(team + 1, WPP * 32);  // partial scores of both column halves are in shared memory
-        const float P = part[eta] + part[pstride + eta];
-        for (int j = lane; j < eta; j += 32) sc[j] = scale * (part[j] + part[pstride + j]);
-        __syncwarp();
-
-        float dP;
-        if (p.mode != KGE_STEP_BACKWARD_EXT) {
-            if (tw == 0) {
-                if (p.scores_neg)
-                    for (int j = lane; j < eta; j += 32) p.scores_neg[(size_t)j * p.B + i] = sc[j];
-                if (p.scores_pos && lane == 0) p.scores_pos[i] = scale * P;
-            }
-            if (p.mode == KGE_STEP_FORWARD_ONLY) { __syncwarp(); continue; }
-            float li = loss_and_dscores(p, scale * P, sc, lane, &dP);
-            if (tw == 0 && lane == 0) loss_acc += (double)li;
-        } else {
-            for (int j = lane; j < eta; j += 32) sc[j] = p.dneg[(size_t)j * p.B + i];
-            dP = p.dpos[i];
-        }
-        __syncwarp();
-
-        for_each_pair_by_side(
-            nside, eta, lane,
-            [&](int a, int b, bool has_b) {
-                S.template grad2<0, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, gent_row(p, nid[a]), gent_row(p, nid[b]),
-                                          scale * sc[a], has_b ? scale * sc[b] : 0.f, has_b);
-            },
-            [&](int a, int b, bool has_b) {
-                S.template grad2<1, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, gent_row(p, nid[a]), gent_row(p, nid[b]),
-                                          scale * sc[a], has_b ? scale * sc[b] : 0.f, has_b);
-            });
-        S.template finish<Sink>(srow, prow, orow, gent_row(p, s_id), p.grad_rel + (size_t)p_id * ld, gent_row(p, o_id),
-                                scale * dP, p.inv_div);
-        __syncwarp();
-    }
-    if (p.loss_out && p.mode == KGE_STEP_FUSED && tw == 0 && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_out, loss_acc);
 }
 
 // --------------------------------------------------------------------------
@@ -1105,19 +944,7 @@ static cudaError_t launch_train_model(const TrainParams &p, int nit, int sm_coun
 {
 #define KGE_LAUNCH(N)                                                                                       \
     {                                                                                                       \
-        if (p.team) {                                                                                       \
-            auto tk = kge_train_team_kernel<MODEL, N>;                                                      \
-            cudaError_t e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                 \
-            long long want = (p.B + (threads / 64) - 1) / (threads / 64);                                   \
-            int grid = (int)(want < (long long)sm_count ? want : (long long)sm_count);                       \
-            tk<<<grid, threads, smem, st>>>(p);                                                             \
-            return cudaGetLastError();                                                                      \
-        }                                                                                                   \
-        const bool res = p.resident != 0;                                                                   \
-        auto kern = p.scatter_mode == KGE_SCATTER_RED_V4                                                    \
-                        ? (res ? kge_train_kernel<MODEL, N, SinkRed, true> : kge_train_kernel<MODEL, N, SinkRed, false>)   \
-                        : (res ? kge_train_kernel<MODEL, N, SinkSmem, true> : kge_train_kernel<MODEL, N, SinkSmem, false>); \
+        auto kern = p.resident ? kge_train_kernel<MODEL, N, true> : kge_train_kernel<MODEL, N, false>;      \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                                     \
         int occ = 0;                                                                                        \

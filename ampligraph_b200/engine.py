@@ -44,7 +44,11 @@ def _traced(name):
 class KGEEngine:
     def __init__(self, scoring_type, k, eta, n_ent, n_rel, loss="pairwise", loss_params=None,
                  optimizer="adam", optimizer_params=None, regularizer=None, device=0, neg_group=0,
-                 scatter=None, table_alloc=None, ent_rows=None):
+                 table_alloc=None, ent_rows=None, max_rel_size=None, rank_mode=None):
+        """regularizer: None | {"p":, "lambda": [, "p2":, "lambda2":]} | a pair [entities, relations] of those
+        (EmbeddingLookupLayer.py:131-155).  max_rel_size: RotatE phase normalisation when it differs from the
+        relation-table rows (RotatE.py:96).  rank_mode: 'auto' (tensor-core filter + exact refine for the bilinear
+        models) | 'exact' (FP32 canonical chain for every pair); env KGE_B200_RANK_MODE overrides the default."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("ampligraph_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -65,8 +69,8 @@ class KGEEngine:
         cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), _lib.SCORING[scoring_type], int(k), int(eta), int(n_ent),
                              int(n_rel), _lib.LOSSES[loss], _lib.REDUCTIONS[reduction],
                              float(lp.get("margin", default_margin)), float(lp.get("alpha", 0.5)), int(device),
-                             int(neg_group), _lib.SCATTER[scatter or os.environ.get("KGE_B200_SCATTER", "red_v4")],
-                             int(os.environ.get("KGE_B200_LAYOUT", "0")))
+                             int(neg_group), int(max_rel_size or 0),
+                             _lib.RANK_MODES[rank_mode or os.environ.get("KGE_B200_RANK_MODE", "auto")], 0)
         h = C.c_void_p()
         _lib.check(self.lib.kge_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -85,6 +89,7 @@ class KGEEngine:
             self.loss_acc = torch.zeros(2, dtype=torch.float64, device=self.device)  # [batch loss, reg loss]
         self.set_optimizer(optimizer, optimizer_params, regularizer)
         self.launches = 0  # kernels launched by this engine (bench.py reports it)
+        self._rank_ws = None  # caller-owned ranking workspace (kge_rank_workspace_bytes), grown on demand
 
     # -- lifetime ---------------------------------------------------------
     def close(self):
@@ -111,12 +116,19 @@ class KGEEngine:
         if name not in _lib.OPTIMIZERS:
             raise ValueError("Could not interpret optimizer identifier: %r" % (name,))
         p = dict(params or {})
-        reg = dict(regularizer or {})
-        self.opt_cfg = _lib.KgeOptimizerConfig(
-            C.sizeof(_lib.KgeOptimizerConfig), _lib.OPTIMIZERS[name], float(p.get("learning_rate", 0.001)),
-            float(p.get("beta_1", 0.9)), float(p.get("beta_2", 0.999)), float(p.get("epsilon", 1e-7)),
-            float(p.get("momentum", 0.0)), float(p.get("initial_accumulator_value", 0.1)),
-            int(reg.get("p", 2)) if regularizer else 0, float(reg.get("lambda", 1e-5)))
+        regs = list(regularizer) if isinstance(regularizer, (list, tuple)) else [regularizer, regularizer]
+        assert len(regs) == 2, "Incorrect length for regularizer. Expected 2, got {}".format(len(regs))
+
+        def cfg_for(reg):
+            reg = dict(reg or {})
+            return _lib.KgeOptimizerConfig(
+                C.sizeof(_lib.KgeOptimizerConfig), _lib.OPTIMIZERS[name], float(p.get("learning_rate", 0.001)),
+                float(p.get("beta_1", 0.9)), float(p.get("beta_2", 0.999)), float(p.get("epsilon", 1e-7)),
+                float(p.get("momentum", 0.0)), float(p.get("initial_accumulator_value", 0.1)),
+                int(reg.get("p", 2)) if reg else 0, float(reg.get("lambda", 1e-5)),
+                int(reg.get("p2", 0)) if reg else 0, float(reg.get("lambda2", 0.0)))
+        self.opt_cfgs = {"ent": cfg_for(regs[0]), "rel": cfg_for(regs[1])}
+        self.opt_cfg = self.opt_cfgs["ent"]  # hyper-parameters are common to both tables; only the regulariser differs
         self.opt_name = name
         self.t = 0
         mk = lambda rows, v=0.0: torch.full((rows, self.ld), v, dtype=torch.float32, device=self.device)
@@ -170,9 +182,18 @@ class KGEEngine:
             out.append(d)
         return out[0], out[1]
 
-    def init_glorot_uniform(self, seed=0):
-        _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.ent), self.ent_rows, int(seed) * 2 + 0, self._stream()))
-        _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.rel), self.n_rel, int(seed) * 2 + 1, self._stream()))
+    def init_glorot_uniform(self, seed=0, only=None):
+        if only in (None, "ent"):
+            _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.ent), self.ent_rows, int(seed) * 2 + 0, self._stream()))
+        if only in (None, "rel"):
+            _lib.check(self.lib.kge_init_glorot_uniform(self.h, _ptr(self.rel), self.n_rel, int(seed) * 2 + 1, self._stream()))
+
+    def init_table(self, which, kind, a=0.0, b=0.0, seed=0):
+        """kge_init_table on the 'ent' or 'rel' table: kind in _lib.INIT_KINDS (uniform [a,b) | normal (mean a, stddev b) |
+        truncated_normal | constant a)."""
+        table, rows = (self.ent, self.ent_rows) if which == "ent" else (self.rel, self.n_rel)
+        _lib.check(self.lib.kge_init_table(self.h, _ptr(table), rows, _lib.INIT_KINDS[kind], float(a), float(b),
+                                           int(seed) * 2 + (0 if which == "ent" else 1), self._stream()))
 
     # -- training ------------------------------------------------------------
     @_traced("kge.train_step")
@@ -202,12 +223,12 @@ class KGEEngine:
             s0, s1 = self.slots[key]
             if self.lazy:
                 _lib.check(self.lib.kge_optimizer_step_lazy(
-                    self.h, C.byref(self.opt_cfg), self.t, _ptr(table), _ptr(grad), _ptr(s0), _ptr(s1), rows,
+                    self.h, C.byref(self.opt_cfgs[key]), self.t, _ptr(table), _ptr(grad), _ptr(s0), _ptr(s1), rows,
                     _ptr(self.stamps[key]), self.lib.kge_step_stamp(self._last_step),
                     C.c_void_p(self.loss_acc.data_ptr() + 8), self._stream()))
                 continue
             _lib.check(self.lib.kge_optimizer_step(
-                self.h, C.byref(self.opt_cfg), self.t, _ptr(table), _ptr(grad), _ptr(s0), _ptr(s1), rows,
+                self.h, C.byref(self.opt_cfgs[key]), self.t, _ptr(table), _ptr(grad), _ptr(s0), _ptr(s1), rows,
                 C.c_void_p(self.loss_acc.data_ptr() + 8), self._stream()))
         self.launches += 2
 
@@ -239,19 +260,54 @@ class KGEEngine:
         self.launches += 2 if self.scoring_type == "RotatE" else 1
         return out
 
+    def rank_workspace(self, b, n_cand):
+        """The caller-owned scratch kge_rank needs (kge_rank_workspace_bytes): one cached torch buffer, grown on demand.
+        Growing frees the old buffer through torch's stream-ordered caching allocator, so no synchronisation is needed."""
+        need = int(self.lib.kge_rank_workspace_bytes(self.h, int(b), int(n_cand)))
+        if self._rank_ws is None or self._rank_ws.numel() < need:
+            self._rank_ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+        return self._rank_ws, need
+
     @_traced("kge.rank")
     def rank(self, triples, side, strategy="worst", filt_off=None, filt_idx=None, cand_ids=None, cand_begin=0,
-             n_cand=None, out=None):
-        """get_ranks for one side: returns/accumulates int32 counts (caller adds 1)."""
+             n_cand=None, out=None, counts=None):
+        """get_ranks for one side.  Default: returns/accumulates int32 rank counts in `out` (caller adds 1).
+        counts=[b,3] int32: accumulate the RAW counters {greater, equal, filtered} there instead (candidate
+        partitions must do this and call finalize_ranks once: 'middle' is not additive over partitions)."""
         assert triples.dtype == torch.int32 and triples.is_cuda and triples.is_contiguous()
         b = triples.shape[0]
-        if out is None:
+        if out is None and counts is None:
             out = torch.zeros(b, dtype=torch.int32, device=self.device)
         if n_cand is None:
             n_cand = cand_ids.numel() if cand_ids is not None else self.n_ent - cand_begin
         n_filt = int(filt_idx.numel()) if filt_idx is not None else 0
+        ws, ws_bytes = self.rank_workspace(b, n_cand)
         _lib.check(self.lib.kge_rank(self.h, _lib.SIDES[side], _lib.STRATEGIES[strategy], _ptr(self.ent), _ptr(self.rel),
                                      _ptr(triples), b, _ptr(cand_ids), int(cand_begin), int(n_cand), _ptr(filt_off),
-                                     _ptr(filt_idx), n_filt, _ptr(out), self._stream()))
+                                     _ptr(filt_idx), n_filt, _ptr(out) if counts is None else None, _ptr(counts),
+                                     _ptr(ws), ws_bytes, self._stream()))
         self.launches += 5
+        return out if counts is None else counts
+
+    def finalize_ranks(self, counts, strategy="worst", out=None):
+        """ranks += f_strategy(greater, equal) - filtered, once, from raw counters summed over candidate partitions."""
+        b = counts.shape[0]
+        if out is None:
+            out = torch.zeros(b, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.kge_rank_finalize(self.h, _ptr(counts), b, _lib.STRATEGIES[strategy], _ptr(out), self._stream()))
+        self.launches += 1
+        return out
+
+    def corruption_scores(self, triples, side, cand_ids=None, cand_begin=0, n_cand=None):
+        """_get_subject_corruption_scores / _get_object_corruption_scores: fp32 [b, n_cand], canonical summation order."""
+        assert triples.dtype == torch.int32 and triples.is_cuda and triples.is_contiguous()
+        b = triples.shape[0]
+        if n_cand is None:
+            n_cand = cand_ids.numel() if cand_ids is not None else self.n_ent - cand_begin
+        out = torch.empty((b, int(n_cand)), dtype=torch.float32, device=self.device)
+        ws, ws_bytes = self.rank_workspace(b, n_cand)
+        _lib.check(self.lib.kge_corruption_scores(self.h, _lib.SIDES[side], _ptr(self.ent), _ptr(self.rel), _ptr(triples), b,
+                                                  _ptr(cand_ids), int(cand_begin), int(n_cand), _ptr(out), _ptr(ws), ws_bytes,
+                                                  self._stream()))
+        self.launches += 3
         return out

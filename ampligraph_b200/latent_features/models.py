@@ -12,7 +12,7 @@ from .. import _lib
 from ..datasets import DataIndexer, FilterIndex, as_triple_array
 from ..engine import KGEEngine
 from ..evaluation import hits_at_n_score, mr_score, mrr_score
-from . import loss_functions, optimizers, regularizers
+from . import initializers, loss_functions, optimizers, regularizers
 from .layers.scoring import SCORING_LAYER_REGISTRY
 
 
@@ -85,17 +85,24 @@ class ScoringBasedEmbeddingModel:
     # ------------------------------------------------------------------ compile
     def compile(self, optimizer="adam", loss=None, entity_relation_initializer="glorot_uniform",
                 entity_relation_regularizer=None, **kwargs):
-        """compile (:1145-1318).  entity_relation_initializer: 'glorot_uniform' | ndarray |
-        callable(shape)->ndarray | list of two of those (entities, relations)."""
+        """compile (:1145-1318).  entity_relation_initializer: anything tf.keras.initializers.get takes in the reference
+        (a name such as 'glorot_uniform' / 'random_normal' / 'he_uniform', a {'class_name', 'config'} dict, an
+        initializers.Initializer instance), an ndarray, a callable(shape)->ndarray, or a list of two of those
+        [entities, relations] (EmbeddingLookupLayer.py:105-129).  entity_relation_regularizer: None | 'LP' | 'l3' |
+        'l1' | 'l2' | 'l1_l2' | regularizers.LPRegularizer, or a list of two [entities, relations] (:131-155)."""
         self.optimizer = optimizers.get(optimizer)
         self.compiled_loss = loss_functions.get(loss)
         init = entity_relation_initializer
-        self._initializer = list(init) if isinstance(init, (list, tuple)) else [init, init]
-        assert len(self._initializer) == 2, "Incorrect length for initializer. Assumed 2 got {}".format(len(self._initializer))
+        if isinstance(init, (list, tuple)):
+            assert len(init) == 2, "Incorrect length for initializer. Assumed 2 got {}".format(len(init))
+            self._initializer = [initializers.get(init[0]), initializers.get(init[1])]
+        else:
+            self._initializer = [initializers.get(init), initializers.get(init)]
         if self.scoring_type == "RotatE":  # :1312-1315
-            assert isinstance(self._initializer[1], str) and self._initializer[1] == "glorot_uniform", \
+            r = self._initializer[1]
+            assert isinstance(r, initializers.Initializer) and r.name == "glorot_uniform", \
                 "The relation initializer provided to a RotatE model must be glorot_uniform!"
-        self._regularizer = regularizers.get(entity_relation_regularizer)
+        self._regularizer = regularizers.get_pair(entity_relation_regularizer)
         self._loss_sum, self._loss_cnt = 0.0, 0
         self._is_compiled = True
         self.engine = None  # tables are (re)built lazily on the first fit, like EmbeddingLookupLayer.build
@@ -110,7 +117,9 @@ class ScoringBasedEmbeddingModel:
     # ------------------------------------------------------------------ engine
     def _build_engine(self):
         name, lp = self.compiled_loss.kernel_params()
-        reg = self._regularizer.kernel_params() if self._regularizer is not None else None
+        reg = [r.kernel_params() if r is not None else None for r in self._regularizer]
+        if self.scoring_type == "RotatE":
+            self.scoring_layer.max_rel_size = self.max_rel_size  # :338
         def make_engine(alloc=None):
             return KGEEngine(self.scoring_type, self.k, self.eta, self.max_ent_size, self.max_rel_size,
                              loss=name or "pairwise", loss_params=lp, optimizer=self.optimizer.name,
@@ -123,15 +132,18 @@ class ScoringBasedEmbeddingModel:
         else:
             self.engine = make_engine()
         dense = [None, None]
-        for n, (init, rows) in enumerate(zip(self._initializer, (self.max_ent_size, self.max_rel_size))):
-            if isinstance(init, str):
-                if init != "glorot_uniform":
-                    raise ValueError("Unknown initializer: %r (use 'glorot_uniform', an array or a callable)" % init)
+        for n, (init, rows, which) in enumerate(zip(self._initializer, (self.max_ent_size, self.max_rel_size), ("ent", "rel"))):
+            if isinstance(init, initializers.Initializer):  # drawn on the device (Philox), no host table
+                seed = init.seed if getattr(init, "seed", None) is not None else self.seed
+                if init.name == "glorot_uniform":
+                    self.engine.init_glorot_uniform(seed, only=which)
+                else:
+                    kind, a, b = init.spec(rows, self.internal_k)
+                    self.engine.init_table(which, kind, a, b, seed)
             elif callable(init):
                 dense[n] = np.asarray(init((rows, self.internal_k)), dtype=np.float32)
             else:
                 dense[n] = np.asarray(init, dtype=np.float32)
-        self.engine.init_glorot_uniform(self.seed)
         self.engine.set_embeddings(dense[0], dense[1])
         self._step = 0
 
@@ -144,7 +156,10 @@ class ScoringBasedEmbeddingModel:
         return dist.get_rank() if self._world() > 1 else 0
 
     def _to_dev(self, a, dtype):
-        return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).pin_memory().to(self.engine.device, non_blocking=True)
+        """host array -> device tensor.  Pageable source, synchronous copy: these are the small per-chunk id / filter
+        arrays of evaluate and the one-off upload of fit; pinning a fresh buffer per call (round 1) cost more than the
+        copy.  The per-step training path stages batches through ONE persistent pinned ring (train_on_batches)."""
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).to(self.engine.device)
 
     # ------------------------------------------------------------------ indexing
     def _index(self, x, fit=False):
@@ -233,8 +248,7 @@ class ScoringBasedEmbeddingModel:
             # per-batch losses accumulate on the device; one read-back per epoch (the logged value is
             # the reference's never-reset running mean of per-batch SUM losses)
             if world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(eng.loss_acc)
+                self._dp.reduce_loss_()
             self._loss_sum += eng.read_loss()
             logs = {"loss": self._loss_sum / max(self._loss_cnt, 1)}
             validate = (epoch >= (validation_burn_in - 1) and validation_data is not None
@@ -287,11 +301,107 @@ class ScoringBasedEmbeddingModel:
             self.engine.forward_backward(batch, None, seed=self.seed, step=self._step)
             self.engine.apply_gradients()
         self._step += 1
+        if self._world() > 1:
+            self._dp.reduce_loss_()  # the loss of the GLOBAL batch, identical on every rank
         loss = self.engine.read_loss()
         self._loss_sum += loss
         self._loss_cnt += 1
         self.is_fitted = True
         return loss
+
+    def train_on_batches(self, batches, prefetch=2):
+        """Streamed training from HOST memory: one train_step per batch of `batches` (an iterable of [B,3] int32 id
+        arrays, numpy or torch; the tf.data generator path of the reference's fit, graph_data_loader.py:472-523,:760-766
+        with its prefetch(2)).  Every step copies ITS batch host->device and reads ITS loss device->host, but nothing
+        blocks: batch i+1 travels on a copy stream through a persistent pinned ring while step i runs, and the 16-byte
+        loss record of step i is copied asynchronously and read one step later.  Returns the list of per-batch losses."""
+        self._assert_compile_was_called()
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return []
+        as_host = lambda x: x if torch.is_tensor(x) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.int32))
+        first = as_host(first)
+        if self.engine is None:
+            if self.max_ent_size is None or self.max_rel_size is None:
+                raise ValueError("train_on_batches needs max_ent_size/max_rel_size (ids are already indexed)")
+            self._build_engine()
+        eng = self.engine
+        dev = eng.device
+        user_loss = isinstance(self.compiled_loss, loss_functions.LossFunctionWrapper)
+        depth = max(2, int(prefetch))
+        cap = first.shape[0]
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_pipe", None) is None or self._pipe["cap"] < cap or self._pipe["depth"] != depth:
+            self._pipe = {"cap": cap, "depth": depth, "copy": torch.cuda.Stream(dev),
+                          "pin": [torch.empty((cap, 3), dtype=torch.int32).pin_memory() for _ in range(depth)],
+                          "dev": [torch.empty((cap, 3), dtype=torch.int32, device=dev) for _ in range(depth)],
+                          "ready": [torch.cuda.Event() for _ in range(depth)], "free": [torch.cuda.Event() for _ in range(depth)],
+                          "loss_pin": torch.zeros((depth, 2), dtype=torch.float64).pin_memory(),
+                          "loss_ev": [torch.cuda.Event() for _ in range(depth)]}
+            for e in self._pipe["free"]:
+                e.record(main)
+        P = self._pipe
+        copy = P["copy"]
+
+        def stage(i, hb):  # host batch -> (pinned ring slot ->) device ring slot, on the copy stream; never blocks on a STEP
+            s = i % depth
+            n = hb.shape[0]
+            if n > P["cap"]:
+                raise ValueError("batch of %d positives exceeds the first batch (%d) this pipeline was sized for" % (n, P["cap"]))
+            if hb.is_pinned():
+                src = hb
+            else:
+                P["ready"][s].synchronize()  # the previous H2D copy OUT of this pinned slot has finished (not the step)
+                P["pin"][s][:n].copy_(hb)
+                src = P["pin"][s][:n]
+            copy.wait_event(P["free"][s])    # stream-ordered: the step that read this device slot last is done
+            with torch.cuda.stream(copy):
+                P["dev"][s][:n].copy_(src, non_blocking=True)
+                P["ready"][s].record(copy)
+            return s, n
+
+        losses, pending = [], []  # pending: (slot, cumulative-loss record not yet read)
+        eng.loss_acc.zero_()  # the accumulator is cumulative from here on; per-step losses are differences of records
+        prev_total = 0.0
+        queued = [stage(0, first)]
+        i = 0
+        while queued:
+            nxt = next(it, None)
+            if nxt is not None:
+                queued.append(stage(i + 1, as_host(nxt)))  # overlaps step i
+            s, n = queued.pop(0)
+            main.wait_event(P["ready"][s])
+            batch = P["dev"][s][:n]
+            if self._world() > 1:
+                self._dp.train_step(batch, None, seed=self.seed + 7919 * self._rank(), step=self._step)
+            elif user_loss:
+                self._user_loss_step(batch)
+            else:
+                eng.forward_backward(batch, None, seed=self.seed, step=self._step)
+                eng.apply_gradients()
+            P["free"][s].record(main)
+            P["loss_pin"][s].copy_(eng.loss_acc, non_blocking=True)  # D2H of this step's (cumulative) loss record
+            P["loss_ev"][s].record(main)
+            pending.append(s)
+            if len(pending) >= depth:  # read the record of step i-depth+1 (long complete) before its slot is reused
+                ps = pending.pop(0)
+                P["loss_ev"][ps].synchronize()
+                tot = float(P["loss_pin"][ps].sum())
+                losses.append(tot - prev_total)
+                prev_total = tot
+            self._step += 1
+            self._loss_cnt += 1
+            i += 1
+        for ps in pending:
+            P["loss_ev"][ps].synchronize()
+            tot = float(P["loss_pin"][ps].sum())
+            losses.append(tot - prev_total)
+            prev_total = tot
+        eng.loss_acc.zero_()
+        self._loss_sum += sum(losses)
+        self.is_fitted = True
+        return losses
 
     def _user_loss_step(self, batch):
         self._two_phase_step(batch, None)
@@ -306,7 +416,8 @@ class ScoringBasedEmbeddingModel:
         repl = torch.where(keep.bool(), neg[:, 2], neg[:, 0]).contiguous()
         sp = torch.empty(B, dtype=torch.float32, device=eng.device)
         sn = torch.empty(B * self.eta, dtype=torch.float32, device=eng.device)
-        eng.forward_backward(batch, (repl, keep), mode=_lib.STEP_FORWARD_ONLY, scores_pos=sp, scores_neg=sn)
+        eng.forward_backward(batch, (repl, keep), seed=self.seed, step=self._step, mode=_lib.STEP_FORWARD_ONLY,
+                             scores_pos=sp, scores_neg=sn)
         spg, sng = sp.requires_grad_(True), sn.requires_grad_(True)
         fp, fn = spg, sng
         if weights is not None:  # compute_focusE_weights (:342-368) + score re-weighting (:396-406)
@@ -321,8 +432,8 @@ class ScoringBasedEmbeddingModel:
             name, lp = self.compiled_loss.kernel_params()
             loss = per_positive_loss(name, fp, fn.reshape(self.eta, -1), lp).sum()
         loss.backward()
-        eng.forward_backward(batch, (repl, keep), mode=_lib.STEP_BACKWARD_EXT, dpos=spg.grad.contiguous(),
-                             dneg=sng.grad.contiguous())
+        eng.forward_backward(batch, (repl, keep), seed=self.seed, step=self._step, mode=_lib.STEP_BACKWARD_EXT,
+                             dpos=spg.grad.contiguous(), dneg=sng.grad.contiguous())  # step: the lazy rule's row stamp
         eng.apply_gradients()
         eng.loss_acc[0] += loss.detach().double()
 
@@ -372,11 +483,15 @@ class ScoringBasedEmbeddingModel:
                 if findex is not None:
                     o_np, i_np = findex.lookup(tb, side, position_of)
                     off, idx = self._to_dev(o_np, np.int64), self._to_dev(i_np, np.int32)
-                if self._world() > 1 and cand_ids is None:  # row-sharded candidates, counts summed over ranks
+                if self._world() > 1 and cand_ids is None:
+                    # row-sharded candidates: RAW counters summed over ranks, tie strategy applied once ('middle' is not
+                    # additive over partitions, AbstractScoringLayer.py:232-244)
                     from ..parallel import allreduce_sum_, row_shard
                     lo, hi = row_shard(self.max_ent_size, self._world(), self._rank())
-                    r = eng.rank(td, side, ranking_strategy, off, idx, cand_begin=lo, n_cand=hi - lo)
-                    allreduce_sum_([r])
+                    cnt = torch.zeros((len(tb), 3), dtype=torch.int32, device=eng.device)
+                    eng.rank(td, side, ranking_strategy, off, idx, cand_begin=lo, n_cand=hi - lo, counts=cnt)
+                    allreduce_sum_([cnt])
+                    r = eng.finalize_ranks(cnt, ranking_strategy)
                 else:
                     r = eng.rank(td, side, ranking_strategy, off, idx, cand_ids=cand_ids)
                 out[start:start + len(tb), j] = r.cpu().numpy()
@@ -416,8 +531,8 @@ class ScoringBasedEmbeddingModel:
             for i in range(n_batches):
                 pb = pos[i * batch_size:(i + 1) * batch_size].contiguous()
                 sp = self.engine.score(pb)
-                if with_corruption:
-                    sn = self.engine.score(self.engine.generate_corruptions(pb, self.seed, step))
+                if with_corruption:  # ONE corruption per positive (eta=1, :1886): the j=0 block of the tile-ordered tensor
+                    sn = self.engine.score(self.engine.generate_corruptions(pb, self.seed, step)[:pb.shape[0]].contiguous())
                 else:
                     sn = self.engine.score(neg[i * nb_size:(i + 1) * nb_size].contiguous())
                 step += 1

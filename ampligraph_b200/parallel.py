@@ -1,11 +1,11 @@
-"""Multi-GPU host logic: one process per GPU (torch.distributed), data-parallel over positives.
+"""Multi-GPU host logic: one process per GPU (torch.distributed for the plumbing), peer memory for the data path.
 
 The training path shards naturally over positives: every rank runs the fused
 kernel on its own slice of the global batch into its own gradient tables, the tables are
-summed with ONE collective (the loss is a SUM over the batch, loss_functions.py:214, so the
-summed gradient equals the single-GPU gradient of the global batch), and every rank applies
-the identical dense optimizer step to its replica.  Ranking shards over entity rows: each rank
-counts against its row range and the int32 counts are summed (rank counts are additive over
+summed with ONE exchange (the loss is a SUM over the batch, loss_functions.py:214, so the
+summed gradient equals the single-GPU gradient of the global batch), and every rank ends up
+with the identical dense optimizer step.  Ranking shards over entity rows: each rank
+counts against its row range and the int32 raw counters are summed (rank counts are additive over
 entity partitions, ScoringBasedEmbeddingModel.py:1449-1452).
 """
 import os
@@ -36,15 +36,30 @@ def allreduce_sum_(tensors, group=None):
     return tensors
 
 
+def reject_lazy(optimizer_name, world):
+    """The lazy (touched-rows-only) optimizer is defined for ONE writer of the row stamps.  With replicated tables every
+    rank stamps only the rows of its own batch slice, so a lazy update after the gradient exchange would skip rows other
+    ranks touched: refuse instead of silently diverging.  Row-sharded tables (ShardedTrainer) do support it --
+    there every rank stamps the owner's shard through peer memory."""
+    if world > 1 and str(optimizer_name).lower().startswith("lazy_"):
+        raise NotImplementedError("optimizer %r with replicated tables on %d GPUs: the lazy rule needs row-sharded tables "
+                                  "(parallel.ShardedTrainer); use the dense optimizer for data-parallel training"
+                                  % (optimizer_name, world))
+
+
+_FLAG_WORDS = 64  # uint32 words reserved per rank for the in-kernel barriers (2 slots x up to 8 writers, padded)
+
+
 class DataParallelTrainer:
     """Replicated tables, one rank per GPU, the reference's train_step on the GLOBAL batch.
 
-    Each rank runs the fused kernel on its own slice of the batch into its own gradient table.
-    Then, preferred path ("p2p"): tables and gradient tables live in torch symmetric memory, so
-    every rank can address every peer's copy through NVLink; ONE kernel per table
-    (kge_optimizer_step_sharded) reduce-scatters the gradients by peer loads, runs the optimizer
-    on this rank's row shard (slots are sharded: 1/N of the Adam state per GPU) and all-gathers
-    the new rows by peer stores.  Two stream-ordered cross-rank barriers bracket it.
+    Each rank runs the fused kernel on its own slice of the batch into its own gradient block.
+    Preferred path ("p2p"): parameter block [ent|rel], two gradient blocks and a flag pad live in one torch
+    symmetric-memory buffer, so every rank can address every peer's copy through NVLink.  The whole tail of the step is
+    ONE kernel (kge_optimizer_step_exchange): flag barrier, gradient reduce-scatter by peer loads, the optimizer on this
+    rank's row shard (slots are sharded: 1/N of the Adam state per GPU), parameter all-gather by peer stores, flag
+    barrier.  Gradient blocks are double-buffered (step i scatters into block i&1 and the exchange zeroes the other
+    one), so there is no memset either: 2 launches per step (train kernel + exchange) at any N.
     Fallback ("nccl"): SUM all-reduce of the gradient tables + the full optimizer on every replica.
     Both equal the single-GPU step on the concatenated batch up to fp32 summation order, because
     the loss is a SUM over the batch (loss_functions.py:214).
@@ -59,11 +74,15 @@ class DataParallelTrainer:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.mode = "single" if self.world == 1 else mode
         self.hdl = None
+        self._k = 0  # exchanges done (gradient block parity, barrier token)
         if self.mode in ("auto", "p2p"):
             try:
                 self.eng = make_engine(self._symmetric_alloc)
+                reject_lazy("lazy_" if self.eng.lazy else "", self.world)
                 self._finish_p2p_setup()
                 self.mode = "p2p"
+            except NotImplementedError:
+                raise
             except Exception as e:  # no symmetric memory / no peer access: NCCL path
                 if mode == "p2p":
                     raise
@@ -73,38 +92,55 @@ class DataParallelTrainer:
                 self.eng = make_engine(None)
         else:
             self.eng = make_engine(None)
+        reject_lazy("lazy_" if self.eng.lazy else "", self.world)
 
     # ---- symmetric-memory plumbing ------------------------------------------------
     def _symmetric_alloc(self, n_ent, n_rel, ld, device):
-        """One symmetric buffer [ent | rel | g_ent | g_rel] so a single rendezvous maps all four."""
+        """One symmetric buffer [ent | rel | gA_ent | gA_rel | gB_ent | gB_rel | flags] so a single rendezvous maps it all."""
         import torch.distributed._symmetric_memory as symm_mem
-        rows = 2 * (n_ent + n_rel)
-        self._buf = symm_mem.empty((rows, ld), dtype=torch.float32, device=device)
+        blk = n_ent + n_rel
+        flag_rows = (_FLAG_WORDS + ld - 1) // ld
+        self._buf = symm_mem.empty((3 * blk + flag_rows, ld), dtype=torch.float32, device=device)
         self._buf.zero_()
         pg = self.group if self.group is not None else dist.group.WORLD
         self.hdl = symm_mem.rendezvous(self._buf, pg.group_name)
         b = self._buf
-        self._offsets = {"ent": 0, "rel": n_ent, "g_ent": n_ent + n_rel, "g_rel": 2 * n_ent + n_rel}
-        return (b[0:n_ent], b[n_ent:n_ent + n_rel], b[n_ent + n_rel:2 * n_ent + n_rel], b[2 * n_ent + n_rel:rows])
+        self._blk = blk
+        self._row_off = {"table": 0, "g0": blk, "g1": 2 * blk, "flags": 3 * blk}
+        self._gviews = [(b[blk:blk + n_ent], b[blk + n_ent:2 * blk]), (b[2 * blk:2 * blk + n_ent], b[2 * blk + n_ent:3 * blk])]
+        return b[0:n_ent], b[n_ent:blk], self._gviews[0][0], self._gviews[0][1]
 
     def _finish_p2p_setup(self):
         C, eng = self._C, self.eng
         ld = eng.ld
         base = [int(p) for p in self.hdl.buffer_ptrs]
         assert len(base) == self.world and base[self.rank] == self._buf.data_ptr()
-        mk = lambda key: (C.c_void_p * self.world)(*[b + self._offsets[key] * ld * 4 for b in base])
-        self._ptrs = {k: mk(k) for k in ("ent", "rel", "g_ent", "g_rel")}
-        self.shards = {"ent": row_shard(eng.n_ent, self.world, self.rank), "rel": row_shard(eng.n_rel, self.world, self.rank)}
-        # optimizer slots only for this rank's row shards
-        for key in ("ent", "rel"):
-            lo, hi = self.shards[key]
-            eng.slots[key] = [None if s is None else s[lo:hi].clone() for s in eng.slots[key]]
+        mk = lambda key: (C.c_void_p * self.world)(*[b + self._row_off[key] * ld * 4 for b in base])
+        self._ptrs = {k: mk(k) for k in ("table", "g0", "g1", "flags")}
+        self._local_g = [base[self.rank] + self._row_off[k] * ld * 4 for k in ("g0", "g1")]
+        self.shard = row_shard(self._blk, self.world, self.rank)  # over the concatenated [ent|rel] rows
+        lo, hi = self.shard
+        # optimizer slots only for this rank's row shard of the concatenated block
+        rows = hi - lo
+        mkslot = lambda v=0.0: torch.full((max(rows, 1), ld), v, dtype=torch.float32, device=eng.device)
+        if eng.opt_name == "adam":
+            self.slots = [mkslot(), mkslot()]
+        elif eng.opt_name == "adagrad":
+            self.slots = [mkslot(eng.opt_cfg.initial_accumulator_value), None]
+        elif eng.opt_cfg.momentum != 0.0:
+            self.slots = [mkslot(), None]
+        else:
+            self.slots = [None, None]
+        eng.slots = {"ent": [None, None], "rel": [None, None]}  # the full-size slots are not used on this path
         torch.cuda.synchronize()
-        self.hdl.barrier(channel=0)
+        self.hdl.barrier(channel=0)  # one-off: every rank's buffer (zeroed flags included) exists before the first step
 
     # ---- one global step ------------------------------------------------------------
     def train_step(self, batch, negatives=None, seed=0, step=0, kernel_done=None):
         eng = self.eng
+        if self.mode == "p2p":
+            blk = self._k & 1
+            eng.g_ent, eng.g_rel = self._gviews[blk]
         eng.forward_backward(batch, negatives, seed=seed, step=step)
         if kernel_done is not None:
             kernel_done.record()  # CUDA event: lets bench.py time the fused kernel alone
@@ -116,19 +152,24 @@ class DataParallelTrainer:
         else:
             C, _lib = self._C, self._lib
             eng.t += 1
-            st = eng._stream()
-            self.hdl.barrier(channel=0)  # every rank's gradient table is complete
-            for key, rows in (("ent", eng.n_ent), ("rel", eng.n_rel)):
-                lo, hi = self.shards[key]
-                s0, s1 = eng.slots[key]
-                _lib.check(eng.lib.kge_optimizer_step_sharded(
-                    eng.h, C.byref(eng.opt_cfg), eng.t, self.world, self.rank, self._ptrs[key], self._ptrs["g_" + key],
-                    C.c_void_p(s0.data_ptr() if s0 is not None else 0), C.c_void_p(s1.data_ptr() if s1 is not None else 0),
-                    lo, hi, C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
-            self.hdl.barrier(channel=1)  # all parameters delivered, all peers done reading my gradients
-            eng.g_ent.zero_()
-            eng.g_rel.zero_()
-            eng.launches += 4
+            self._k += 1
+            lo, hi = self.shard
+            s0, s1 = self.slots
+            p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+            _lib.check(eng.lib.kge_optimizer_step_exchange(
+                eng.h, C.byref(eng.opt_cfgs["ent"]), C.byref(eng.opt_cfgs["rel"]), eng.t, self.world, self.rank,
+                self._ptrs["table"], self._ptrs["g%d" % blk], C.c_void_p(self._local_g[blk ^ 1]), p(s0), p(s1), lo, hi,
+                self._ptrs["flags"], self._k, 3, C.c_void_p(eng.loss_acc.data_ptr() + 8), eng._stream()))
+            eng.launches += 1
+
+    def reduce_loss_(self):
+        """SUM the [batch loss, regulariser loss] accumulators over ranks (for logging).  p2p: every rank holds its shard of
+        the regulariser loss; nccl: every replica computed the FULL regulariser loss, so it is divided by world first."""
+        if self.world > 1:
+            if self.mode == "nccl":
+                self.eng.loss_acc[1] /= self.world
+            dist.all_reduce(self.eng.loss_acc, group=self.group)
+        return self.eng.loss_acc
 
     def close(self):
         self.eng.close()
@@ -143,9 +184,10 @@ class ShardedTrainer:
       1. kge_train_step_sharded: the fused kernel gathers the rows it needs from whichever rank owns
          them and scatter-adds gradient rows back, all over NVLink peer memory (the forward row
          all-to-all and backward gradient all-to-all of SURVEY.md 8e, fused into the kernel);
-      2. barrier; each rank runs the DENSE optimizer on its own shard (no exchange), and the
+      2. flag barrier (kge_peer_barrier); each rank runs the optimizer on its own shard (no exchange), and the
          replicated relation table goes through kge_optimizer_step_sharded (peer reduce + all-gather);
-      3. barrier.
+      3. flag barrier.
+    This replaces the reference's bucket partitioning through disk (datasets/partitioned_data_manager.py:573-955).
     """
 
     def __init__(self, scoring_type, k, eta, n_ent, n_rel, device, group=None, lazy=False, **engine_kw):
@@ -166,20 +208,28 @@ class ShardedTrainer:
 
         self.lazy = bool(lazy)
         self.use_stash = os.environ.get("KGE_B200_STASH", "1") != "0"
+        self._k = 0
 
         def alloc(rows, n_rel_, ld, dev):
             assert rows == self.rps
             self._stamp_rows = (rows + ld - 1) // ld  # int32 row stamps live in the same symmetric buffer
-            total = 2 * rows + 2 * n_rel_ + self._stamp_rows
+            flag_rows = (_FLAG_WORDS + ld - 1) // ld
+            total = 2 * rows + 2 * n_rel_ + self._stamp_rows + flag_rows
             self._buf = symm_mem.empty((total, ld), dtype=torch.float32, device=dev)
             self._buf.zero_()
             pg = group if group is not None else dist.group.WORLD
             self.hdl = symm_mem.rendezvous(self._buf, pg.group_name)
             self._off = {"ent": 0, "g_ent": rows, "rel": 2 * rows, "g_rel": 2 * rows + n_rel_,
-                         "stamp": 2 * rows + 2 * n_rel_}
+                         "stamp": 2 * rows + 2 * n_rel_, "flags": 2 * rows + 2 * n_rel_ + self._stamp_rows}
             b = self._buf
             return b[0:rows], b[2 * rows:2 * rows + n_rel_], b[rows:2 * rows], b[2 * rows + n_rel_:2 * rows + 2 * n_rel_]
 
+        # the engine itself runs the DENSE rule's bookkeeping (no engine-owned stamps): the entity stamps of a sharded run
+        # live in the symmetric buffer so that peers can stamp the owner's rows; optimizer="lazy_adam" implies lazy=True
+        opt_name = str(engine_kw.get("optimizer", "adam")).lower()
+        if opt_name.startswith("lazy_"):
+            self.lazy = True
+            engine_kw["optimizer"] = opt_name[len("lazy_"):]
         self.eng = KGEEngine(scoring_type, k, eta, n_ent, n_rel, device=device, table_alloc=alloc, ent_rows=self.rps,
                              **engine_kw)
         eng, ld = self.eng, self.eng.ld
@@ -194,11 +244,18 @@ class ShardedTrainer:
         self._stamps = self._buf[so:so + self._stamp_rows].view(torch.int32).reshape(-1)[:self.rps]
         self._rel_ptrs = (C.c_void_p * self.world)(*[ptr(q, "rel") for q in range(self.world)])
         self._grel_ptrs = (C.c_void_p * self.world)(*[ptr(q, "g_rel") for q in range(self.world)])
+        self._flag_ptrs = (C.c_void_p * self.world)(*[ptr(q, "flags") for q in range(self.world)])
         self.rel_shard = row_shard(self.n_rel, self.world, self.rank)
         lo, hi = self.rel_shard
         eng.slots["rel"] = [None if s is None else s[lo:hi].clone() for s in eng.slots["rel"]]
         torch.cuda.synchronize()
-        self.hdl.barrier(channel=0)
+        self.hdl.barrier(channel=0)  # one-off: all buffers exist and are zeroed before the first peer access
+
+    def barrier(self, slot=0):
+        """Stream-ordered cross-rank barrier over the flag pad (one 32-thread kernel)."""
+        self._k += 1
+        self._lib.check(self.eng.lib.kge_peer_barrier(self.eng.h, self.world, self.rank, self._flag_ptrs, int(slot), self._k,
+                                                      self.eng._stream()))
 
     def set_embeddings(self, ent_dense=None, rel_dense=None):
         """dense GLOBAL tables (numpy, identical on every rank): each rank keeps its row slice."""
@@ -209,8 +266,7 @@ class ShardedTrainer:
             self.eng.set_embeddings(loc, None)
         if rel_dense is not None:
             self.eng.set_embeddings(None, rel_dense)
-        torch.cuda.synchronize()
-        self.hdl.barrier(channel=0)
+        self.barrier(0)
 
     def get_embeddings(self):
         """-> (global entity table [n_ent, K] gathered from all shards, relation table), torch cpu."""
@@ -241,38 +297,43 @@ class ShardedTrainer:
             eng.h, _lib.STEP_FUSED, C.byref(self.map), p(eng.rel), p(eng.g_rel), p(batch), B, p(neg_ent), p(neg_keep),
             int(seed), int(step), p(eng.loss_acc), None, None, None, None, st))
         mark()
-        self.hdl.barrier(channel=0)  # every rank's scatters (into my shard too) and relation gradients are complete
+        self.barrier(0)  # every rank's scatters (into my shard too) and relation gradients are complete
         mark()
         eng.t += 1
         s0, s1 = eng.slots["ent"]
         if self.lazy:
-            _lib.check(eng.lib.kge_optimizer_step_lazy(eng.h, C.byref(eng.opt_cfg), eng.t, p(eng.ent), p(eng.g_ent), p(s0), p(s1),
+            _lib.check(eng.lib.kge_optimizer_step_lazy(eng.h, C.byref(eng.opt_cfgs["ent"]), eng.t, p(eng.ent), p(eng.g_ent), p(s0), p(s1),
                                                        self.rps, p(self._stamps), eng.lib.kge_step_stamp(int(step)),
                                                        C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
         else:
-            _lib.check(eng.lib.kge_optimizer_step(eng.h, C.byref(eng.opt_cfg), eng.t, p(eng.ent), p(eng.g_ent), p(s0), p(s1),
+            _lib.check(eng.lib.kge_optimizer_step(eng.h, C.byref(eng.opt_cfgs["ent"]), eng.t, p(eng.ent), p(eng.g_ent), p(s0), p(s1),
                                                   self.rps, C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
         lo, hi = self.rel_shard
         r0, r1 = eng.slots["rel"]
         _lib.check(eng.lib.kge_optimizer_step_sharded(
-            eng.h, C.byref(eng.opt_cfg), eng.t, self.world, self.rank, self._rel_ptrs, self._grel_ptrs, p(r0), p(r1),
+            eng.h, C.byref(eng.opt_cfgs["rel"]), eng.t, self.world, self.rank, self._rel_ptrs, self._grel_ptrs, p(r0), p(r1),
             lo, hi, C.c_void_p(eng.loss_acc.data_ptr() + 8), st))
         mark()
-        self.hdl.barrier(channel=1)  # all shards updated, relation rows delivered, my relation gradients consumed
+        self.barrier(1)  # all shards updated, relation rows delivered, my relation gradients consumed
         eng.g_rel.zero_()
         mark()
-        eng.launches += 4
+        eng.launches += 6
 
     def rank_counts(self, triples, side, strategy="worst", filt_off=None, filt_idx=None):
-        """full-table rank counts: each rank counts against its shard, int32 counts are summed."""
+        """full-table rank counts: each rank counts against its shard; the RAW counters {greater, equal, filtered} are
+        summed over ranks and the tie strategy is applied once ('middle' = greater + ceil(equal/2) is not additive over
+        shards, AbstractScoringLayer.py:232-244)."""
         C, _lib, eng = self._C, self._lib, self.eng
         b = triples.shape[0]
-        out = torch.zeros(b, dtype=torch.int32, device=eng.device)
+        counts = torch.zeros((b, 3), dtype=torch.int32, device=eng.device)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
         n_filt = int(filt_idx.numel()) if filt_idx is not None else 0
+        ws, ws_bytes = eng.rank_workspace(b, self.rps)
         _lib.check(eng.lib.kge_rank_sharded(eng.h, C.byref(self.map), self.rank, _lib.SIDES[side], _lib.STRATEGIES[strategy],
-                                            p(eng.rel), p(triples), b, p(filt_off), p(filt_idx), n_filt, p(out), eng._stream()))
-        return allreduce_sum_([out], self.group)[0]
+                                            p(eng.rel), p(triples), b, p(filt_off), p(filt_idx), n_filt, None, p(counts),
+                                            p(ws), ws_bytes, eng._stream()))
+        allreduce_sum_([counts], self.group)
+        return eng.finalize_ranks(counts, strategy)
 
     def close(self):
         self.eng.close()

@@ -5,15 +5,20 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference-semantics CPU path (oracle)
 
-Workload (BASELINE.json configs[1], "cfg2"): ComplEx k=200 (row = 400 fp32), eta=10,
+Headline workload (BASELINE.json configs[1], "cfg2"): ComplEx k=200 (row = 400 fp32), eta=10,
 self-adversarial loss (margin 3, alpha 0.5), Adam lr 1e-3, FB15K-237-shaped synthetic KG
 (14,505 entities / 237 relations / 272,115 triples), batch = 27,212 positives (10 batches
 per epoch).  A step = one reference train_step on one batch: fused forward+backward kernel
 + dense Adam on both tables.  Metric: training triples/sec counting positives + eta
 negatives = B*(1+eta)*steps / time.  N>1: weak scaling, tables replicated, each rank its
-own batch; the gradient exchange is fused with the optimizer (peer-memory reduce-scatter +
-sharded Adam + all-gather in one kernel per table, parallel.DataParallelTrainer), with the
-NCCL all-reduce + full optimizer as fallback (KGE_B200_DP_MODE=nccl).
+own batch; the whole tail of the step (cross-rank barrier, gradient reduce-scatter, sharded Adam,
+parameter all-gather, barrier) is ONE kernel over NVLink peer memory (parallel.DataParallelTrainer),
+with the NCCL all-reduce + full optimizer as fallback (KGE_B200_DP_MODE=nccl).
+
+Outside the headline timed region the same JSON line carries an `extra` block: the other
+BASELINE configs measured at their stated sizes (cfg3, cfg4, cfg5; row-sharded when N>1), full-entity ranking,
+and -- at every N>1 -- self-checks that the data-parallel / row-sharded step equals the single-GPU step on the
+concatenated batch (`dp_parity`, `sharded_parity`).
 """
 import argparse
 import json
@@ -27,9 +32,24 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(model="ComplEx", k=200, eta=10, loss="self_adversarial", loss_params={"margin": 3.0, "alpha": 0.5},
-           n_ent=14505, n_rel=237, n_triples=272115, batch=27212, optimizer="adam", lr=1e-3)
 METRIC = "training triples/sec (pos+eta negs)"
+SA = {"margin": 3.0, "alpha": 0.5}
+# BASELINE.json configs[1..4]; B = positives per GPU per step
+WORKLOADS = {
+    "cfg2": dict(model="ComplEx", k=200, eta=10, loss="self_adversarial", loss_params=SA, n_ent=14505, n_rel=237,
+                 n_triples=272115, batch=27212, optimizer="adam", lr=1e-3),
+    "cfg3": dict(model="DistMult", k=400, eta=20, loss="pairwise", loss_params={"margin": 1.0}, n_ent=40943, n_rel=11,
+                 n_triples=86835, batch=8684, optimizer="adam", lr=1e-3),
+    "cfg4": dict(model="RotatE", k=200, eta=30, loss="self_adversarial", loss_params=SA, n_ent=123182, n_rel=37,
+                 n_triples=1079040, batch=10791, optimizer="adam", lr=1e-3),
+    "cfg5": dict(model="ComplEx", k=1000, eta=50, loss="self_adversarial", loss_params=SA, n_ent=10_000_000, n_rel=1000,
+                 n_triples=None, batch=8192, optimizer="lazy_adam", lr=1e-3),
+}
+CFG = WORKLOADS["cfg2"]
+
+
+def internal_k(c):
+    return c["k"] if c["model"] in ("TransE", "DistMult") else 2 * c["k"]
 
 
 def synthetic_kg(n_ent, n_rel, n_triples, seed=1):
@@ -119,27 +139,42 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def workload_config(n_gpus):
+    """`config` of the JSON line: the same for both arms (the arm-specific prose lives under `arm`)."""
+    return {"workload": "cfg2: ComplEx k=200 eta=10 self_adversarial(margin 3, alpha 0.5), Adam lr 1e-3, "
+                        "FB15K-237-shaped synthetic KG (14505 ent / 237 rel / 272115 triples, Zipf(1.0) entities), "
+                        "batch 27212 positives per GPU",
+            "global_batch": CFG["batch"] * n_gpus,
+            "parallelism": ("dp%d, replicated tables" % n_gpus) if n_gpus > 1 else "single GPU",
+            "l2": "flushed between steps (256 MiB write outside the timed events); per-step CUDA events summed"}
+
+
 # ---------------------------------------------------------------------------
 # reference arm / cpu_baseline: the op-for-op CPU restatement of the reference step
 # ---------------------------------------------------------------------------
-def run_cpu_reference(steps, warmup, batch, threads=None):
+def run_cpu_reference(steps, warmup, batch, threads=None, budget_s=None):
+    """Times oracle/ref_step.py (torch-CPU fp32, the reference graph op for op) on cfg2 batches.  If `budget_s` is given
+    and (steps+warmup) full batches would exceed it, every step processes a bounded SAMPLE of the batch instead (the
+    first `sample` positives; the metric, triples/s, does not depend on the sample size to first order)."""
     import torch
-    from oracle import c_oracle, ref_step  # bench.py's cpu_baseline leg is allowed to execute oracle/
+    from oracle import c_oracle, ref_step  # bench.py's cpu_baseline / reference leg is allowed to execute oracle/
     rng = np.random.default_rng(0)
-    K = 2 * CFG["k"]
+    K = internal_k(CFG)
     ent, rel = glorot(CFG["n_ent"], K, rng), glorot(CFG["n_rel"], K, rng)
     data = synthetic_kg(CFG["n_ent"], CFG["n_rel"], CFG["n_triples"])
     rs = ref_step.RefStep(CFG["model"], K, ent, rel, CFG["eta"], loss=CFG["loss"], loss_params=CFG["loss_params"],
                           optimizer=CFG["optimizer"], optimizer_params={"learning_rate": CFG["lr"]})
     nb = (len(data) + batch - 1) // batch
+    sample = [batch]
 
     def one(i):
-        t = data[(i % nb) * batch:(i % nb + 1) * batch]
+        t = data[(i % nb) * batch:(i % nb + 1) * batch][:sample[0]]
         keep = rng.integers(0, 2, len(t) * CFG["eta"]).astype(np.uint8)
         repl = rng.integers(0, CFG["n_ent"], len(t) * CFG["eta"]).astype(np.int32)
         rs.train_step(t, c_oracle.corrupt(t, CFG["eta"], keep, repl))
         return len(t)
 
+    t_full = None
     if threads is None:
         # "all the host threads it can use": torch-CPU oversubscribes on many-core hosts (128 threads were 4x
         # slower than 8 on the first B200 box), so time one step per candidate count and keep the fastest
@@ -152,43 +187,304 @@ def run_cpu_reference(steps, warmup, batch, threads=None):
             dt = time.perf_counter() - t0
             if best is None or dt < best[0]:
                 best = (dt, th)
-        threads = best[1]
+        t_full, threads = best
     torch.set_num_threads(threads)
+    if budget_s is not None and t_full is not None and (steps + warmup) * t_full > budget_s:
+        sample[0] = int(max(1024, min(batch, batch * budget_s / ((steps + warmup) * t_full))))
     for i in range(warmup):
         one(i)
     t0, pos = time.perf_counter(), 0
     for i in range(steps):
         pos += one(warmup + i)
     dt = time.perf_counter() - t0
-    return pos * (1 + CFG["eta"]) / dt, dt, threads
+    return pos * (1 + CFG["eta"]) / dt, dt, threads, sample[0]
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded: the CPU step takes seconds, so cap the sample at 10 timed steps (3 warm-up)
-    steps, warmup = min(args.steps, 10), min(args.warmup, 3)
-    value, dt, threads = run_cpu_reference(steps, warmup, CFG["batch"])
+    steps, warmup = args.steps, args.warmup  # honoured exactly; a long request shrinks the per-step sample, not the count
+    value, dt, threads, sample = run_cpu_reference(steps, warmup, CFG["batch"], budget_s=150.0)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "triples/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(1), parallelism="host CPU, %d torch threads, rank 0 only" % threads,
-                           l2="n/a (CPU wall clock around a bounded sample of the same per-step batch)"),
+            "config": workload_config(args.gpus),
+            "arm": {"what": "reference-semantics CPU restatement (oracle/ref_step.py, torch-CPU fp32, op-for-op restatement "
+                            "of the TF graph; TensorFlow is not installable here), host cores of the GPU box, rank 0 only",
+                    "threads": threads, "positives_per_step": sample,
+                    "timing": "CPU wall clock around the timed steps"},
             "cpu_baseline": {"value": value, "unit": "triples/s", "cores": threads, "kind": "port",
-                             "sample": "%d steps of %d positives (oracle/ref_step.py, torch-CPU fp32, op-for-op "
-                                       "restatement of the TF graph; TensorFlow is not installable here)" % (steps, CFG["batch"])},
+                             "sample": "%d steps of %d positives each (of the %d-positive cfg2 batch)" % (steps, sample, CFG["batch"])},
             "e2e": {"value": value, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(n_gpus, dp_mode=""):
-    return {"workload": "cfg2: ComplEx k=200 eta=10 self_adversarial(margin 3, alpha 0.5), Adam lr 1e-3, "
-                        "FB15K-237-shaped synthetic KG (14505 ent / 237 rel / 272115 triples, Zipf(1.0) entities), "
-                        "batch 27212 positives per GPU",
-            "global_batch": CFG["batch"] * n_gpus,
-            "parallelism": ("dp%d, replicated tables, %s" % (n_gpus, dp_mode)) if n_gpus > 1 else "single GPU",
-            "l2": "flushed between steps (256 MiB write outside the timed events); per-step CUDA events summed"}
+# ---------------------------------------------------------------------------
+# helpers for the extra block
+# ---------------------------------------------------------------------------
+def _uniform_batches(c, E, n, rng, dev):
+    import torch
+    B, R = c["batch"], c["n_rel"]
+    return [torch.as_tensor(np.stack([rng.integers(0, E, B), rng.integers(0, R, B), rng.integers(0, E, B)], 1).astype(np.int32)).to(dev)
+            for _ in range(n)]
+
+
+def _time_steps(fn, steps, warmup, flush, world, dev):
+    """CUDA-event time of `steps` calls of fn(i) (max over ranks), L2 flushed between steps outside the events."""
+    import torch
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = []
+    for i in range(steps):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(warmup + i)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item() / steps
+
+
+def _step_entry(c, ms_step, ms_kernel, world, ld, peak, **more):
+    B, eta = c["batch"], c["eta"]
+    alg = 2 * (3 + eta) * ld * 4 * B  # algorithmic bytes per GPU per launch (SURVEY 8d)
+    d = {"triples_per_s": world * B * (1 + eta) / (ms_step / 1e3), "ms_per_step": ms_step, "kernel_ms": ms_kernel,
+         "positives_per_gpu": B, "n_gpus": world,
+         "roofline": {"bound": "hbm", "achieved": alg / (ms_kernel / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                      "frac": alg / (ms_kernel / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
+                      "kernel": "kge_train_kernel<%s>" % c["model"]}}
+    d.update(more)
+    return d
+
+
+def extra_single_step(name, dev, flush, peak, n_ent=None, steps=5, warmup=2):
+    """One BASELINE config on ONE GPU at its stated size: the fused kernel + the optimizer, resident inputs."""
+    import torch
+    from ampligraph_b200.engine import KGEEngine
+    c = WORKLOADS[name]
+    E = n_ent or c["n_ent"]
+    eng = KGEEngine(c["model"], c["k"], c["eta"], E, c["n_rel"], loss=c["loss"], loss_params=c["loss_params"],
+                    optimizer=c["optimizer"], optimizer_params={"learning_rate": c["lr"]}, device=dev.index)
+    eng.init_glorot_uniform(3)
+    rng = np.random.default_rng(11)
+    if c["n_triples"]:
+        data = torch.as_tensor(synthetic_kg(E, c["n_rel"], c["n_triples"], seed=5)).to(dev)
+        nb = data.shape[0] // c["batch"]
+        batches = [data[j * c["batch"]:(j + 1) * c["batch"]] for j in range(min(nb, 8))]
+    else:
+        batches = _uniform_batches(c, E, 4, rng, dev)
+    kev = []
+
+    def fn(i):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.forward_backward(batches[i % len(batches)], None, seed=9, step=i)
+        e1.record()
+        kev.append((e0, e1))
+        eng.apply_gradients()
+
+    ms = _time_steps(fn, steps, warmup, flush, 1, dev)
+    mk = float(np.mean([a.elapsed_time(b) for a, b in kev[warmup:]]))
+    out = _step_entry(c, ms, mk, 1, eng.ld, peak, entities=E, table_GB=round(E * eng.ld * 4 / 1e9, 3),
+                      optimizer=c["optimizer"], rows_resident=bool(eng.lib.kge_rows_resident(eng.h)),
+                      l2="flushed between steps", loss=eng.read_loss())
+    return out, eng, batches
+
+
+def extra_rank(eng, queries, n_ent, reps=3, flush=None, reduce=None, warm=True):
+    """Full-entity ranking of `queries` on both sides: ms for the two kge_rank calls (+ the counter all-reduce when sharded)."""
+    import torch
+    fn = reduce or (lambda side: eng.rank(queries, side, "worst"))
+    if warm:
+        for side in ("s", "o"):
+            fn(side)
+    torch.cuda.synchronize()
+    ms = []
+    for i in range(reps):
+        if flush is not None:
+            flush.fill_(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for side in ("s", "o"):
+            r = fn(side)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    med = float(np.median(ms))
+    b = queries.shape[0]
+    return {"queries": b, "sides": 2, "entities": n_ent, "ms": med, "G_candidate_scores_per_s": 2 * b * n_ent / (med / 1e3) / 1e9,
+            "TFLOPs_fma_equiv": 2.0 * 2 * b * n_ent * eng.ld / (med / 1e3) / 1e12,
+            "table_stream_GBps": 2 * n_ent * eng.ld * 4 / (med / 1e3) / 1e9, "mean_rank_side_o": float(r.float().mean().item()) + 1.0}
+
+
+def _global_negatives(c, E, B, world, steps, seed):
+    """Injected corruptions for `steps` GLOBAL batches of world*B positives, identical on every rank; per-rank slices."""
+    rng = np.random.default_rng(seed)
+    eta = c["eta"]
+    ne = rng.integers(0, E, (steps, world, eta, B)).astype(np.int32)
+    nk = rng.integers(0, 2, (steps, world, eta, B)).astype(np.uint8)
+    return ne, nk
+
+
+def extra_dp_parity(make_engine, dev, rank, world, ent0, rel0, data_np, steps=3):
+    """K data-parallel steps vs the same K steps on ONE GPU on the concatenated batch (rank 0 runs the single-GPU side)."""
+    import torch
+    import torch.distributed as dist
+    from ampligraph_b200.parallel import DataParallelTrainer
+    c, B = CFG, CFG["batch"]
+    eta = c["eta"]
+    dp = DataParallelTrainer(make_engine, mode=os.environ.get("KGE_B200_DP_MODE", "auto"))
+    dp.eng.set_embeddings(ent0, rel0)
+    ne, nk = _global_negatives(c, c["n_ent"], B, world, steps, 77)
+    to = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+    batch = lambda i, r: data_np[((i * world + r) % (len(data_np) // B)) * B:((i * world + r) % (len(data_np) // B) + 1) * B]
+    for i in range(steps):
+        dp.train_step(to(batch(i, rank)), (to(ne[i, rank].reshape(-1)), to(nk[i, rank].reshape(-1))))
+    torch.cuda.synchronize()
+    loss = dp.reduce_loss_().sum().item()
+    got_e, got_r = (x.cpu().numpy() for x in dp.eng.get_embeddings())
+    # replicas identical?
+    chk = torch.tensor([float(np.abs(got_e).sum()), float(np.abs(got_r).sum())], dtype=torch.float64, device=dev)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        ref = make_engine(None)
+        ref.set_embeddings(ent0, rel0)
+        for i in range(steps):
+            t = np.concatenate([batch(i, r) for r in range(world)])
+            g_ne = np.concatenate([ne[i, r] for r in range(world)], axis=1).reshape(-1)  # tile order of the global batch
+            g_nk = np.concatenate([nk[i, r] for r in range(world)], axis=1).reshape(-1)
+            ref.train_step(to(t), (to(g_ne), to(g_nk)))
+        ref_loss = ref.read_loss()
+        ref_e, ref_r = (x.cpu().numpy() for x in ref.get_embeddings())
+        err = max(np.abs(got_e - ref_e).max() / max(np.abs(ref_e).max(), 1e-30), np.abs(got_r - ref_r).max() / max(np.abs(ref_r).max(), 1e-30))
+        upd = max(np.abs(ref_e - ent0).max(), 1e-30)
+        ok = bool(np.allclose(got_e, ref_e, rtol=2e-4, atol=2e-6) and np.allclose(got_r, ref_r, rtol=2e-4, atol=2e-6)
+                  and abs(loss - ref_loss) <= 1e-4 * abs(ref_loss) and bool((lo == hi).all().item()))
+        out = {"steps": steps, "mode": dp.mode, "global_batch": world * B, "max_rel_err": float(err),
+               "max_abs_err_over_max_update": float(max(np.abs(got_e - ref_e).max(), np.abs(got_r - ref_r).max()) / upd),
+               "loss_rel_err": float(abs(loss - ref_loss) / abs(ref_loss)), "replicas_identical": bool((lo == hi).all().item()),
+               "ok": ok, "criterion": "tables allclose(rtol 2e-4, atol 2e-6) vs single-GPU on the concatenated batch, "
+                                      "summed loss within 1e-4, all replicas bit-identical"}
+        ref.close()
+    dp.close()
+    return out
+
+
+def extra_sharded(name, dev, rank, world, flush, peak, n_ent=None, steps=5, warmup=2, parity_steps=0, rank_queries=0):
+    """A BASELINE config with the entity table ROW-SHARDED over all ranks (cfg4 / cfg5): step time, phase attribution,
+    optional parity against the single-GPU step on the concatenated batch, optional full-entity ranking."""
+    import torch
+    import torch.distributed as dist
+    from ampligraph_b200.engine import KGEEngine
+    from ampligraph_b200.parallel import ShardedTrainer
+    c = WORKLOADS[name]
+    E = n_ent or c["n_ent"]
+    B, eta, R = c["batch"], c["eta"], c["n_rel"]
+    kw = dict(loss=c["loss"], loss_params=c["loss_params"], optimizer=c["optimizer"], optimizer_params={"learning_rate": c["lr"]})
+    out = {}
+    to = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+    if parity_steps:
+        K = internal_k(c)
+        rng0 = np.random.default_rng(5)
+        ent0, rel0 = glorot(E, K, rng0), glorot(R, K, rng0)
+        tr = ShardedTrainer(c["model"], c["k"], eta, E, R, dev.index, **kw)
+        tr.set_embeddings(ent0, rel0)
+        rngb = np.random.default_rng(6)
+        tb = np.stack([rngb.integers(0, E, (parity_steps, world, B)), rngb.integers(0, R, (parity_steps, world, B)),
+                       rngb.integers(0, E, (parity_steps, world, B))], -1).astype(np.int32)
+        ne, nk = _global_negatives(c, E, B, world, parity_steps, 78)
+        for i in range(parity_steps):
+            tr.train_step(to(tb[i, rank]), (to(ne[i, rank].reshape(-1)), to(nk[i, rank].reshape(-1))), step=i)
+        torch.cuda.synchronize()
+        got_e, got_r = (x.numpy() for x in tr.get_embeddings())
+        la = tr.eng.loss_acc.clone()
+        dist.all_reduce(la)
+        loss = la.sum().item()
+        if rank == 0:
+            ref = KGEEngine(c["model"], c["k"], eta, E, R, device=dev.index, **kw)
+            ref.set_embeddings(ent0, rel0)
+            for i in range(parity_steps):
+                t = tb[i].reshape(-1, 3)
+                g_ne = np.concatenate([ne[i, r] for r in range(world)], axis=1).reshape(-1)
+                g_nk = np.concatenate([nk[i, r] for r in range(world)], axis=1).reshape(-1)
+                ref.train_step(to(t), (to(g_ne), to(g_nk)), step=i)
+            ref_loss = ref.read_loss()
+            ref_e, ref_r = (x.cpu().numpy() for x in ref.get_embeddings())
+            err = max(np.abs(got_e - ref_e).max() / np.abs(ref_e).max(), np.abs(got_r - ref_r).max() / np.abs(ref_r).max())
+            ok = bool(np.allclose(got_e, ref_e, rtol=3e-4, atol=3e-6) and np.allclose(got_r, ref_r, rtol=3e-4, atol=3e-6)
+                      and abs(loss - ref_loss) <= 1e-4 * abs(ref_loss))
+            out["sharded_parity"] = {"steps": parity_steps, "global_batch": world * B, "max_rel_err": float(err),
+                                     "loss_rel_err": float(abs(loss - ref_loss) / abs(ref_loss)), "ok": ok,
+                                     "criterion": "gathered shards allclose(rtol 3e-4, atol 3e-6) vs single-GPU on the "
+                                                  "concatenated batch, summed loss within 1e-4"}
+            ref.close()
+        tr.close()
+        del tr
+        torch.cuda.empty_cache()
+    tr = ShardedTrainer(c["model"], c["k"], eta, E, R, dev.index, **kw)
+    tr.eng.init_glorot_uniform(1 + rank)  # each shard its own stream
+    tr.barrier(0)
+    rng = np.random.default_rng(100 + rank)
+    batches = _uniform_batches(c, E, 4, rng, dev)
+    ms = _time_steps(lambda i: tr.train_step(batches[i % 4], None, seed=7 + rank, step=i), steps, warmup, flush, world, dev)
+    # phase attribution of one step (separate passes, events between the phases; rank 0's view)
+    ph = []
+    for i in range(3):
+        evs = []
+        tr.train_step(batches[i % 4], None, seed=7 + rank, step=1000 + i, events=evs)
+        torch.cuda.synchronize()
+        ph.append([evs[j].elapsed_time(evs[j + 1]) for j in range(4)])
+    ph = np.median(np.array(ph), axis=0)
+    kt = torch.tensor([ph[0]], dtype=torch.float64, device=dev)
+    dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    ld = tr.eng.ld
+    out.update(_step_entry(c, ms, kt.item(), world, ld, peak, entities=E, table_GB=round(E * ld * 4 / 1e9, 2),
+                           as_stated=bool(E == c["n_ent"]), optimizer=c["optimizer"], sharding="entity rows over %d GPUs, "
+                           "gathers/scatters through NVLink peer memory inside the fused kernel" % world,
+                           phase_ms_rank0={"kernel": float(ph[0]), "barrier0": float(ph[1]), "optimizers": float(ph[2]), "barrier1": float(ph[3])},
+                           nvlink_GB_per_gpu_per_step_each_way=round((3 + eta) * B * ld * 4 * (world - 1) / world / 1e9, 3),
+                           l2="flushed between steps"))
+    if rank_queries:
+        q = batches[0][:rank_queries].contiguous()
+        r = extra_rank(tr.eng, q, E, reps=1, reduce=lambda side: tr.rank_counts(q, side), warm=False)
+        t = torch.tensor([r["ms"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        r["ms"] = t.item()
+        r["G_candidate_scores_per_s"] = 2 * q.shape[0] * E / (t.item() / 1e3) / 1e9
+        r["TFLOPs_fma_equiv"] = 2.0 * 2 * q.shape[0] * E * ld / (t.item() / 1e3) / 1e12
+        r["table_stream_GBps"] = 2 * E * ld * 4 / (t.item() / 1e3) / 1e9
+        out["full_entity_ranking"] = r
+    out["loss"] = tr.eng.read_loss()
+    tr.close()
+    del tr
+    torch.cuda.empty_cache()
+    return out
+
+
+def guarded(extra, key, fn):
+    try:
+        t0 = time.perf_counter()
+        v = fn()
+        if isinstance(v, dict):
+            v["wall_s"] = round(time.perf_counter() - t0, 2)
+        extra[key] = v
+    except Exception as e:  # an extra never takes the headline down
+        import traceback
+        extra[key] = {"error": repr(e), "trace": traceback.format_exc()[-600:]}
 
 
 # ---------------------------------------------------------------------------
@@ -207,7 +503,7 @@ def main_ours(args):
     torch.cuda.set_device(dev)
 
     rng = np.random.default_rng(0)
-    K = 2 * CFG["k"]
+    K = internal_k(CFG)
     B, eta = CFG["batch"], CFG["eta"]
     from ampligraph_b200.parallel import DataParallelTrainer, batch_slot
 
@@ -218,7 +514,8 @@ def main_ours(args):
 
     dp = DataParallelTrainer(make_engine, mode=os.environ.get("KGE_B200_DP_MODE", "auto"))
     eng = dp.eng
-    eng.set_embeddings(glorot(CFG["n_ent"], K, rng), glorot(CFG["n_rel"], K, rng))  # same tables on every rank
+    ent0, rel0 = glorot(CFG["n_ent"], K, rng), glorot(CFG["n_rel"], K, rng)
+    eng.set_embeddings(ent0, rel0)  # same tables on every rank
     data_np = synthetic_kg(CFG["n_ent"], CFG["n_rel"], CFG["n_triples"])
     nb = len(data_np) // B  # full batches only, so every step does identical work
     data = torch.as_tensor(data_np).to(dev)
@@ -231,16 +528,9 @@ def main_ours(args):
 
     def step(i, ev=None):
         b = batch_of(i)
-        if world == 1:
-            if ev: ev[0].record()
-            eng.forward_backward(b, None, seed=1234, step=i)
-            if ev: ev[1].record()
-            eng.apply_gradients()
-            if ev: ev[2].record()
-        else:
-            if ev: ev[0].record()
-            dp.train_step(b, None, seed=1234, step=i, kernel_done=ev[1] if ev else None)
-            if ev: ev[2].record()
+        if ev: ev[0].record()
+        dp.train_step(b, None, seed=1234, step=i, kernel_done=ev[1] if ev else None)
+        if ev: ev[2].record()
 
     def sync_all():
         if world > 1:
@@ -272,10 +562,13 @@ def main_ours(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_step = tt.item()
-    loss = eng.read_loss()
+    loss = float(dp.reduce_loss_().sum().item())
+    eng.loss_acc.zero_()
     value = world * B * (1 + eta) * args.steps / (t_step / 1e3)
 
-    # ---- e2e: same metric through the public API with HOST buffers, H2D + D2H inside the timed region ----
+    # ---- e2e: same metric through the public API with HOST buffers, H2D + D2H every step inside the timed region ----
+    # ScoringBasedEmbeddingModel.train_on_batches: batch i+1 is copied on a side stream while step i runs and the
+    # 16-byte loss record of step i is read one step later -- the copies are per step and inside the events, not blocking.
     from ampligraph_b200.latent_features import ScoringBasedEmbeddingModel
     model = ScoringBasedEmbeddingModel(eta=eta, k=CFG["k"], scoring_type=CFG["model"], seed=0,
                                        max_ent_size=CFG["n_ent"], max_rel_size=CFG["n_rel"])
@@ -286,22 +579,61 @@ def main_ours(args):
     model.compile(optimizer=optimizers.get("adam", {"learning_rate": CFG["lr"]}),
                   loss=loss_functions.get(CFG["loss"], CFG["loss_params"]))
     host_batches = [pinned[j * B:(j + 1) * B] for j in range(nb)]
-    for i in range(max(args.warmup, 3)):
-        model.train_on_batch(host_batches[(i * world + rank) % nb])
+    hb = lambda i: host_batches[(i * world + rank) % nb]
+    model.train_on_batches([hb(i) for i in range(max(args.warmup, 3))])
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        model.train_on_batch(host_batches[((args.warmup + i) * world + rank) % nb])  # H2D batch, step, D2H loss
+    e2e_losses = model.train_on_batches([hb(args.warmup + i) for i in range(args.steps)])  # H2D batch, step, D2H loss, every step
     e1.record()
     sync_all()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * (1 + eta) * args.steps / (te.item() / 1e3)
+    peak, peak_src = measured_hbm_peak()
+
+    # ---- extra: the other BASELINE configs at their stated sizes + N>1 self-checks (outside the headline region) ----
+    extra = {}
+    if not args.no_extra:
+        if world == 1:
+            def cfg2_rank():
+                q = data[:1024].contiguous()
+                r = extra_rank(eng, q, CFG["n_ent"], reps=5, flush=flush)
+                r["rank_mode"] = os.environ.get("KGE_B200_RANK_MODE", "auto")
+                return r
+            guarded(extra, "cfg2_full_entity_ranking", cfg2_rank)
+            guarded(extra, "cfg3", lambda: extra_single_step("cfg3", dev, flush, peak)[0])
+            guarded(extra, "cfg4_single_gpu", lambda: extra_single_step("cfg4", dev, flush, peak)[0])
+
+            def cfg5_one():
+                E = int(os.environ.get("KGE_BENCH_CFG5_ENT_PER_GPU", "1250000"))
+                out, e5, bt = extra_single_step("cfg5", dev, flush, peak, n_ent=E, steps=4, warmup=2)
+                out["as_stated"] = False
+                out["note"] = "cfg5 shape (k=1000, eta=50, B=8192, lazy Adam) with one GPU's share of the 10 M entities"
+                nq = int(os.environ.get("KGE_BENCH_CFG5_RANK_B", "64"))
+                out["full_entity_ranking"] = extra_rank(e5, bt[0][:nq].contiguous(), E, reps=1, warm=False)
+                e5.close()
+                return out
+            guarded(extra, "cfg5_shape_single_gpu", cfg5_one)
+        else:
+            res = {}
+            guarded(res, "v", lambda: extra_dp_parity(make_engine, dev, rank, world, ent0, rel0, data_np))
+            if rank == 0:
+                extra["dp_parity"] = res["v"]
+            res = {}
+            guarded(res, "v", lambda: extra_sharded("cfg4", dev, rank, world, flush, peak, parity_steps=3))
+            if rank == 0:
+                extra["cfg4_row_sharded"] = res["v"]
+            res = {}
+            per = int(os.environ.get("KGE_BENCH_CFG5_ENT_PER_GPU", "1250000"))
+            nq = int(os.environ.get("KGE_BENCH_CFG5_RANK_B", "64"))
+            guarded(res, "v", lambda: extra_sharded("cfg5", dev, rank, world, None, peak, n_ent=per * world, steps=4, warmup=2,
+                                                    rank_queries=nq))
+            if rank == 0:
+                extra["cfg5_row_sharded"] = res["v"]
 
     if rank == 0:
-        peak, peak_src = measured_hbm_peak()
         row_bytes = eng.ld * 4
         alg_bytes = 2 * (3 + eta) * row_bytes * B  # (3+eta) rows in + (3+eta) gradient rows out
         achieved = alg_bytes / (t_kern / 1e3) / 1e9
@@ -312,24 +644,32 @@ def main_ours(args):
         except Exception:
             pass
         cpu_steps = 3
-        cpu_value, cpu_dt, cpu_threads = run_cpu_reference(cpu_steps, 1, B) if world == 1 and not args.no_cpu else (None, None, None)
+        cpu = run_cpu_reference(cpu_steps, 1, B) if world == 1 and not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": "triples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_step / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(world, {"p2p": "gradient reduce-scatter + sharded Adam + parameter all-gather fused in one kernel over NVLink peer memory", "nccl": "NCCL all-reduce of gradient tables"}.get(dp.mode, dp.mode)), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": B * 3 * 4, "d2h_bytes_per_step": 16},
+                "config": workload_config(world), "clocks": clocks,
+                "arm": {"exchange": {"p2p": "barrier + gradient reduce-scatter + sharded Adam + parameter all-gather + barrier in ONE "
+                                            "kernel over NVLink peer memory (kge_optimizer_step_exchange)",
+                                     "nccl": "NCCL all-reduce of gradient tables + full optimizer", "single": "n/a"}.get(dp.mode, dp.mode),
+                        "launches_per_step": launches / max(args.steps, 1)},
+                "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": B * 3 * 4, "d2h_bytes_per_step": 16,
+                        "api": "ScoringBasedEmbeddingModel.train_on_batches (pinned host batches; copy stream prefetch; "
+                               "per-step loss read one step late)", "last_loss": e2e_losses[-1] if e2e_losses else None},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "kge_train_kernel<ComplEx,2>",
+                             "traffic": traffic, "kernel": "kge_train_kernel<ComplEx,2,resident>",
                              "kernel_ms": t_kern, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                             "note": "tables (23 MB) are L2-resident: achieved > HBM peak is possible"},
-                "final_loss": loss}
-        if cpu_value is not None:
-            line["cpu_baseline"] = {"value": cpu_value, "unit": "triples/s", "cores": cpu_threads, "kind": "port",
+                             "note": "cfg2's tables (23 MB) are L2-resident: this kernel is issue/latency bound, not HBM bound, "
+                                     "and `achieved` can exceed the HBM peak; extra.cfg5* / extra.cfg4* are the HBM-resident cases"},
+                "final_loss": loss, "extra": extra}
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu[0], "unit": "triples/s", "cores": cpu[2], "kind": "port",
                                     "sample": "%d steps of %d positives on the host (oracle/ref_step.py, torch-CPU "
-                                              "fp32 restatement of the reference graph)" % (cpu_steps, B)}
+                                              "fp32 restatement of the reference graph)" % (cpu_steps, cpu[3])}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -340,6 +680,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra block (profiling runs)")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

@@ -13,7 +13,11 @@
  *     library borrows it for the duration of the call and allocates nothing
  *     persistent except the small per-handle workspace created by kge_create.
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
- *     work is stream-ordered, no entry point synchronises the device.
+ *     work is stream-ordered; no entry point synchronises the device or allocates
+ *     device memory (scratch space is a caller-owned workspace, see kge_rank).
+ *   - every entry point that launches work first makes kge_config.device the
+ *     current device of the calling thread and restores the previous one on
+ *     return, so handles of different GPUs can be driven from one thread.
  *   - return value: 0 = ok, otherwise a kge_status; text via kge_last_error().
  *   - one caller thread per handle; different handles (one per GPU) may be
  *     driven from different threads.
@@ -36,7 +40,7 @@
 extern "C" {
 #endif
 
-#define KGE_B200_ABI_VERSION 1
+#define KGE_B200_ABI_VERSION 2
 
 typedef struct kge_handle kge_handle;
 
@@ -64,9 +68,17 @@ enum kge_reduction { KGE_REDUCE_SUM = 0, KGE_REDUCE_MEAN = 1 }; /* loss_function
 enum kge_optimizer { KGE_OPT_SGD = 0, KGE_OPT_ADAM = 1, KGE_OPT_ADAGRAD = 2 };
 enum kge_side { KGE_SIDE_S = 0, KGE_SIDE_O = 1 };
 enum kge_rank_strategy { KGE_RANK_WORST = 0, KGE_RANK_BEST = 1, KGE_RANK_MIDDLE = 2 };
-enum kge_scatter {
-    KGE_SCATTER_BULK = 0,   /* rows staged in shared memory, cp.reduce.async.bulk .add.f32 (copy engine) */
-    KGE_SCATTER_RED_V4 = 1  /* red.global.add.v4.f32 straight from registers */
+/* how kge_rank scores the candidates of DistMult / ComplEx / HolE (the bilinear models, a [b,K]x[K,E] contraction):
+ * AUTO = tensor cores (tcgen05, split-bf16 operands) decide every (query, candidate) pair whose approximate score is
+ * provably on one side of the positive's quantisation bin, the few remaining pairs are re-scored with the exact
+ * canonical FP32 chain -- ranks are bit-identical to EXACT, which runs that chain for every pair. */
+enum kge_rank_mode { KGE_RANK_MODE_AUTO = 0, KGE_RANK_MODE_EXACT = 1 };
+/* initialisers for kge_init_table (tf.keras.initializers the reference accepts, EmbeddingLookupLayer.py:105-129) */
+enum kge_init {
+    KGE_INIT_UNIFORM = 0,           /* U[a, b) */
+    KGE_INIT_NORMAL = 1,            /* N(mean a, stddev b) */
+    KGE_INIT_TRUNCATED_NORMAL = 2,  /* N(a, b) resampled until within 2 stddev (Keras TruncatedNormal) */
+    KGE_INIT_CONSTANT = 3           /* a */
 };
 enum kge_step_mode {
     KGE_STEP_FUSED = 0,         /* scores -> built-in loss -> gradients, one kernel */
@@ -89,8 +101,10 @@ typedef struct kge_config {
     float alpha;          /* self_adversarial temperature */
     int32_t device;       /* CUDA device ordinal */
     int32_t neg_group;    /* 0 = auto; >0 forces that many negatives resident per pass (testing) */
-    int32_t scatter_mode; /* enum kge_scatter: how gradient rows reach the gradient tables */
-    int32_t reserved;     /* 0; experiment switches: bit 0/1 pad row slots / warp regions to 128 B, bit 2 two-warps-per-positive kernel */
+    int64_t max_rel_size; /* RotatE phase normalisation sqrt(6/(internal_k*max_rel_size)) (RotatE.py:96,
+                             ScoringBasedEmbeddingModel.py:338); 0 = n_rel */
+    int32_t rank_mode;    /* enum kge_rank_mode */
+    int32_t reserved;     /* 0 */
 } kge_config;
 
 /* optimizers.get (optimizers.py:255-291) -> tf.keras.optimizers.legacy.{SGD,Adam,Adagrad};
@@ -103,8 +117,10 @@ typedef struct kge_optimizer_config {
     float epsilon;        /* 1e-7 */
     float momentum;       /* SGD: 0 */
     float initial_accumulator_value; /* Adagrad: 0.1 */
-    int32_t reg_p;        /* 0 = no regulariser, else p of LP (2, 3, ...) */
+    int32_t reg_p;        /* 0 = no regulariser, else p of LP (1, 2, 3, ...) */
     float reg_lambda;     /* LP lambda (default 1e-5) */
+    int32_t reg_p2;       /* optional second LP term (Keras 'l1_l2' = p 1 + p 2); 0 = none */
+    float reg_lambda2;
 } kge_optimizer_config;
 
 const char *kge_last_error(void);
@@ -126,6 +142,11 @@ int kge_unpack_rows(kge_handle *h, const float *table_dev, float *dense_dev, int
  * (EmbeddingLookupLayer.py:194-201): U(-l, l), l = sqrt(6/(rows+internal_k)),
  * from a Philox4x32-10 counter stream (TF's own stream is not reproducible). */
 int kge_init_glorot_uniform(kge_handle *h, float *table_dev, int64_t rows, uint64_t seed, void *stream);
+/* The other initialisers tf.keras.initializers.get resolves for entity_relation_initializer (random_normal,
+ * random_uniform, truncated_normal, glorot_normal, he_*, lecun_*, zeros, ones, constant; the fan-dependent ones
+ * are reduced to these four kinds by the caller): one Philox4x32-10 draw per element, pads stay 0. */
+int kge_init_table(kge_handle *h, float *table_dev, int64_t rows, int32_t kind, float a, float b, uint64_t seed,
+                   void *stream);
 
 /* predict_step (ScoringBasedEmbeddingModel.py:1694-1699): gather + _compute_scores. */
 int kge_score_triples(kge_handle *h, const float *ent_dev, const float *rel_dev,
@@ -246,6 +267,35 @@ int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_config *opt, i
                                float *slot0_shard_dev, float *slot1_shard_dev, int64_t row_begin,
                                int64_t row_end, double *reg_loss_dev, void *stream);
 
+/* ONE-LAUNCH data-parallel step tail: cross-rank flag barrier + gradient reduce-scatter + optimizer on this rank's
+ * row shard + parameter all-gather + cross-rank flag barrier, all inside one kernel over NVLink peer memory
+ * (replaces: barrier kernel, kge_optimizer_step_sharded x2, barrier kernel, two memsets).
+ *   peer_tables[q]  base of rank q's REPLICATED parameter block: rows [0,n_ent) entity table immediately followed by
+ *                   rows [n_ent, n_ent+n_rel) relation table (one contiguous [n_ent+n_rel, ld] buffer)
+ *   peer_grads[q]   base of rank q's gradient block of THIS step, same shape (its kge_train_step scattered into it)
+ *   zero_grads_dev  this rank's OTHER gradient block (gradient blocks are double-buffered: step i scatters into block
+ *                   i&1); it is zeroed here for the next step -- every peer finished reading it one step ago -- so
+ *                   nobody ever memsets a gradient table.  NULL: skip.
+ *   slot*_shard_dev optimizer slots of rows [row_begin, row_end) of the concatenated block only
+ *   opt_ent/opt_rel the two tables may carry different regularisers (EmbeddingLookupLayer.py:131-155)
+ *   peer_flags[q]   base of rank q's flag pad: 2*world uint32, zero-initialised once, peer-mapped like the tables
+ *   token           strictly increasing per call (e.g. the step count t): flags are never reset
+ *   phases          bit 0: wait until every rank entered this call (= finished its kge_train_step) before reading
+ *                   gradients; bit 1: before returning control to the stream, wait until every rank delivered its
+ *                   rows (so the next kernel on this stream may read the tables).  3 = both (the normal case).
+ * Stream order on each rank must be: kge_train_step(step i) -> this call.  No other synchronisation is needed. */
+int kge_optimizer_step_exchange(kge_handle *h, const kge_optimizer_config *opt_ent,
+                                const kge_optimizer_config *opt_rel, int64_t t, int32_t world, int32_t rank,
+                                float *const *peer_tables, float *const *peer_grads, float *zero_grads_dev,
+                                float *slot0_shard_dev, float *slot1_shard_dev, int64_t row_begin,
+                                int64_t row_end, uint32_t *const *peer_flags, uint32_t token, int32_t phases,
+                                double *reg_loss_dev, void *stream);
+
+/* The flag barrier alone (one tiny kernel): signal `token` into slot `slot` (0 or 1) of every rank's flag pad, then
+ * wait until all ranks signalled.  Used by the row-sharded trainer around its local optimizer. */
+int kge_peer_barrier(kge_handle *h, int32_t world, int32_t rank, uint32_t *const *peer_flags, int32_t slot,
+                     uint32_t token, void *stream);
+
 /* test_function / get_ranks (ScoringBasedEmbeddingModel.py:1387-1465,
  * layers/scoring/AbstractScoringLayer.py:156-422) for one corruption side.
  *   cand_ids_dev  NULL: candidates are entity rows [cand_begin, cand_begin+n_cand) of
@@ -256,26 +306,48 @@ int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_config *opt, i
  *                 otherwise) of the known-true entities; positions outside
  *                 [cand_begin, cand_begin+n_cand) are ignored (:280-288);
  *                 n_filt = total number of filter entries (= filt_off[b], known to the host)
- *   ranks_dev     [b] int32, += count (so shards/sides can accumulate); the caller
- *                 adds 1 (ScoringBasedEmbeddingModel.py:1684) */
+ *   ranks_dev     [b] int32, += count (so sides can accumulate); the caller adds 1
+ *                 (ScoringBasedEmbeddingModel.py:1684).  May be NULL when counts_dev is given.
+ *   counts_dev    NULL, or [b,3] int32 raw counters, += {#(q_pos < q_c), #(q_pos == q_c), #filtered}.
+ *                 Candidate partitions (row shards, cand_begin chunks) must accumulate THESE and call
+ *                 kge_rank_finalize once: 'middle' is best + ceil(equal/2) (:232-244), which is not
+ *                 additive over partitions; 'worst'/'best' are, so ranks_dev may be accumulated directly.
+ *   workspace_dev caller-owned scratch of at least kge_rank_workspace_bytes(h, b, n_cand) bytes, 256-byte
+ *                 aligned; contents are undefined afterwards.  The library never allocates or synchronises. */
 int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const float *ent_dev,
              const float *rel_dev, const int32_t *triples_dev, int64_t b,
              const int32_t *cand_ids_dev, int64_t cand_begin, int64_t n_cand,
              const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
-             int32_t *ranks_dev, void *stream);
+             int32_t *ranks_dev, int32_t *counts_dev, void *workspace_dev, int64_t workspace_bytes,
+             void *stream);
 
 /* kge_rank against THIS rank's row shard of a sharded table: query rows are fetched from whichever
  * rank owns them, candidates are the local shard's rows, filter ids are GLOBAL entity ids (those
- * outside the shard are ignored, AbstractScoringLayer.py:280-288).  Sum ranks_dev over ranks
- * (int32 all-reduce) for the full count (ScoringBasedEmbeddingModel.py:1449-1452). */
+ * outside the shard are ignored, AbstractScoringLayer.py:280-288).  Sum counts_dev over ranks
+ * (int32 all-reduce) and finalize once (ScoringBasedEmbeddingModel.py:1449-1452). */
 int kge_rank_sharded(kge_handle *h, const kge_shard_map *map, int32_t rank, int32_t side, int32_t strategy,
                      const float *rel_dev, const int32_t *triples_dev, int64_t b,
                      const int64_t *filt_off_dev, const int32_t *filt_idx_dev, int64_t n_filt,
-                     int32_t *ranks_dev, void *stream);
+                     int32_t *ranks_dev, int32_t *counts_dev, void *workspace_dev, int64_t workspace_bytes,
+                     void *stream);
 
-/* size in bytes of the device workspace kge_rank needs for b queries (allocated
- * internally and cached on the handle; exposed so callers can budget HBM). */
-int64_t kge_rank_workspace_bytes(const kge_handle *h, int64_t b);
+/* ranks[i] += f_strategy(counts[i]) - filtered[i]  (AbstractScoringLayer.py:218-258, :304-307) */
+int kge_rank_finalize(kge_handle *h, const int32_t *counts_dev /*[b,3]*/, int64_t b, int32_t strategy,
+                      int32_t *ranks_dev, void *stream);
+
+/* _get_subject_corruption_scores / _get_object_corruption_scores (TransE.py:56-114, DistMult.py:51-99,
+ * ComplEx.py:65-151, HolE.py:47-89, RotatE.py:107-217): the [b, n_cand] fp32 score matrix of every candidate
+ * substituted on `side`, canonical summation order (the scores kge_rank quantises).  Same candidate
+ * addressing and workspace contract as kge_rank. */
+int kge_corruption_scores(kge_handle *h, int32_t side, const float *ent_dev, const float *rel_dev,
+                          const int32_t *triples_dev, int64_t b, const int32_t *cand_ids_dev,
+                          int64_t cand_begin, int64_t n_cand, float *scores_dev /*[b, n_cand]*/,
+                          void *workspace_dev, int64_t workspace_bytes, void *stream);
+
+/* bytes of caller-owned scratch kge_rank / kge_rank_sharded / kge_corruption_scores need for b queries
+ * against n_cand candidates (query vectors, counters and -- in KGE_RANK_MODE_AUTO for the bilinear models --
+ * the split-bf16 copies of the candidate rows and query vectors the tensor-core pass reads). */
+int64_t kge_rank_workspace_bytes(const kge_handle *h, int64_t b, int64_t n_cand);
 
 #ifdef __cplusplus
 }

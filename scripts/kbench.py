@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel micro-benchmark (development aid): times kge_train_step alone for the BASELINE
-config shapes under different scatter modes / residency groups.  CUDA events, L2 flushed
+config shapes under different residency groups.  CUDA events, L2 flushed
 between iterations.  Usage: python scripts/kbench.py [cfg2 cfg3 cfg4 ...]"""
 import os
 import sys
@@ -34,10 +34,10 @@ def triples(c, rng):
     return np.stack([s, rng.integers(0, R, B), o], 1).astype(np.int32)
 
 
-def run(name, scatter, neg_group=0, iters=20):
+def run(name, neg_group=0, iters=20):
     c = CFGS[name]
     rng = np.random.default_rng(0)
-    eng = KGEEngine(c["model"], c["k"], c["eta"], c["E"], c["R"], loss=c["loss"], scatter=scatter, neg_group=neg_group)
+    eng = KGEEngine(c["model"], c["k"], c["eta"], c["E"], c["R"], loss=c["loss"], neg_group=neg_group)
     eng.init_glorot_uniform(1)
     t = torch.as_tensor(triples(c, rng)).cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -57,24 +57,23 @@ def run(name, scatter, neg_group=0, iters=20):
     row_bytes = eng.ld * 4
     alg = 2 * (3 + c["eta"]) * row_bytes * c["B"]
     g = eng.g_ent.double().abs().sum().item()
-    print("%-6s %-7s G=%-2d  med %8.1f us  min %8.1f us  %7.1f GB/s alg  %6.2f Mpos/s  %8.1f Mtriples/s  |g|=%.6e"
-          % (name, scatter, neg_group, np.median(ms) * 1e3, ms.min() * 1e3, alg / np.median(ms) / 1e6,
+    print("%-6s %-9s G=%-2d  med %8.1f us  min %8.1f us  %7.1f GB/s alg  %6.2f Mpos/s  %8.1f Mtriples/s  |g|=%.6e"
+          % (name, os.path.basename(os.environ.get("KGE_B200_LIB", "main")).replace("libkge_", "").replace(".so", ""), neg_group, np.median(ms) * 1e3, ms.min() * 1e3, alg / np.median(ms) / 1e6,
              c["B"] / np.median(ms) / 1e3, c["B"] * (1 + c["eta"]) / np.median(ms) / 1e3, g), flush=True)
     eng.close()
 
 
 if __name__ == "__main__":
     args = sys.argv[1:]
-    if args and args[0] == "one":  # one <cfg> <scatter> <G>   (for ncu)
-        run(args[1], args[2], int(args[3]), iters=5)
+    if args and args[0] == "one":  # one <cfg> <G>   (for ncu)
+        run(args[1], int(args[2]), iters=5)
         sys.exit(0)
     if args and args[0] == "sweep":
         for n, gs in (("cfg4", (0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3)), ("cfg4c", (0, 15, 13, 11, 10, 9, 8, 7, 6, 5)),
                       ("cfg3", (0, 13, 11, 10, 9, 7, 5)), ("cfg5w", (0,))):
             for g in gs:
-                run(n, "red_v4", neg_group=g)
+                run(n, neg_group=g)
         sys.exit(0)
     names = args or ["cfg2", "cfg2u", "cfg3", "cfg4", "cfg1", "big"]
     for n in names:
-        for scatter in ("bulk", "red_v4"):
-            run(n, scatter)
+        run(n)

@@ -197,3 +197,46 @@ def test_calibration_and_early_stopping():
     assert m.is_calibrated and 0 < m.predict_proba(X[:5]).min()
     with pytest.raises(ValueError):
         m.calibrate(X[2600:], positive_base_rate=1.5)
+
+
+def test_train_on_batches_equals_train_on_batch():
+    """The streamed host path (copy-stream prefetch, loss read one step late) is the same sequence of train_steps as
+    calling train_on_batch per batch: identical tables, identical per-batch losses; pinned and pageable sources."""
+    from ampligraph_b200.latent_features import ScoringBasedEmbeddingModel
+    E, R, B = 300, 5, 256
+    t = _kg(E, R, 3000, labels=False).astype(np.int32)
+    batches = [np.ascontiguousarray(t[i:i + B]) for i in range(0, 5 * B, B)] + [np.ascontiguousarray(t[5 * B:5 * B + 100])]  # short last batch
+    out = []
+    for streamed in (False, True, "pinned"):
+        m = ScoringBasedEmbeddingModel(eta=4, k=16, scoring_type="ComplEx", seed=3, max_ent_size=E, max_rel_size=R)
+        m.data_indexer = False
+        m.compile(optimizer="adam", loss="self_adversarial")
+        if streamed is False:
+            losses = [m.train_on_batch(torch.as_tensor(b)) for b in batches]
+        elif streamed is True:
+            losses = m.train_on_batches(iter(batches))
+        else:
+            losses = m.train_on_batches([torch.as_tensor(b).pin_memory() for b in batches], prefetch=3)
+        out.append((losses, [x.cpu().numpy() for x in m.engine.get_embeddings()]))
+    for losses, (e, r) in out[1:]:
+        assert np.allclose(losses, out[0][0], rtol=1e-6) and len(losses) == len(batches)
+        assert np.array_equal(e, out[0][1][0]) and np.array_equal(r, out[0][1][1])
+
+
+def test_model_initializers_and_regularizer_pair():
+    """compile() takes the Keras initialiser names / a pair, and a pair of regularisers (EmbeddingLookupLayer.py:105-155);
+    the reference's own initialiser test: RandomNormal(mean=0.5, stddev=0.05) -> mean/std of the built tables."""
+    from ampligraph_b200.latent_features import ScoringBasedEmbeddingModel, initializers
+    X = _kg(500, 6, 4000)
+    m = ScoringBasedEmbeddingModel(eta=2, k=40, scoring_type="DistMult", seed=11)
+    m.compile(optimizer="sgd", loss="nll", entity_relation_initializer=[initializers.RandomNormal(mean=0.5, stddev=0.05), "he_uniform"],
+              entity_relation_regularizer=["l2", "l1_l2"])
+    m.fit(X, batch_size=1000, epochs=0, verbose=False)  # builds the tables, trains nothing
+    m.is_fitted = True
+    ent = m.get_embeddings(m.data_indexer.ent_labels, "e")
+    rel = m.get_embeddings(m.data_indexer.rel_labels, "r")
+    assert abs(ent.mean() - 0.5) < 5e-3 and abs(ent.std() - 0.05) < 5e-3  # test_initializers.py:48-49
+    lim = np.sqrt(6.0 / len(rel))
+    assert np.abs(rel).max() <= lim and np.abs(rel).max() > 0.9 * lim
+    h = m.fit(X, batch_size=1000, epochs=2, verbose=False)
+    assert np.isfinite(h.history["loss"]).all()

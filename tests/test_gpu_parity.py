@@ -59,7 +59,7 @@ def _close(a, b, rtol=RTOL):
 def test_library_loads_and_layout():
     from ampligraph_b200 import _lib
     lib = _lib.load()
-    assert lib.kge_abi_version() == 1
+    assert lib.kge_abi_version() == _lib.ABI_VERSION
     for model, k, ld in (("TransE", 50, 52), ("DistMult", 400, 400), ("ComplEx", 3, 8), ("RotatE", 200, 400)):
         eng = _engine(model, k, 2, 10, 3)
         assert eng.ld == ld and eng.internal_k == (k if model in ("TransE", "DistMult") else 2 * k)
@@ -400,9 +400,54 @@ def test_external_loss_two_phase():
     eng.close()
 
 
+def _zipf_triples(E, R, n, rng):
+    """s,o ~ truncated Zipf(1.0) over a random permutation: hot entities collide in the red.v4 scatter like real data."""
+    w = 1.0 / np.arange(1, E + 1)
+    cdf = np.cumsum(w / w.sum())
+    perm = rng.permutation(E)
+    s, o = perm[np.searchsorted(cdf, rng.random(n))], perm[np.searchsorted(cdf, rng.random(n))]
+    return np.stack([s, rng.integers(0, R, n), o], 1).astype(np.int32)
+
+
+@pytest.mark.parametrize("name,model,k,eta,E,R,B,loss", [
+    # BASELINE configs[1] and [2] at their FULL stated size (entities, batch), Zipf-distributed triples
+    ("cfg2", "ComplEx", 200, 10, 14505, 237, 27212, "self_adversarial"),
+    ("cfg3", "DistMult", 400, 20, 40943, 11, 8684, "pairwise"),
+    # configs[3] and [4]: exact (k, eta) and a table that does not fit the 126 MB L2 (197 MB / 800 MB); the batch is
+    # bounded so that the CPU oracle (which materialises [B*eta, K] tensors) finishes in seconds
+    ("cfg4", "RotatE", 200, 30, 123182, 37, 2048, "self_adversarial"),
+    ("cfg5", "ComplEx", 1000, 50, 100000, 1000, 512, "self_adversarial"),
+])
+def test_full_size_forward_backward_vs_oracle(name, model, k, eta, E, R, B, loss):
+    """The fused kernel against the INDEPENDENT oracle (oracle/ref_step.py: 6 gathers, broadcast scoring, autograd) at
+    BASELINE sizes: loss and both gradient tables within 1e-4 (replaces the self-referential
+    gradient-linearity check).  Zipf-heavy collisions in the red.v4 scatter, column windows (cfg5) and negative
+    groups (cfg4, cfg5) are all exercised against an answer the kernel did not produce."""
+    rng = np.random.default_rng(101)
+    ent, rel = _tables(model, E, R, k, rng)
+    t = _zipf_triples(E, R, B, rng)
+    neg_ent, neg_keep = _negatives(E, B, eta, rng)
+    lp = {"margin": 3.0, "alpha": 0.5} if loss == "self_adversarial" else {"margin": 1.0}
+    eng = _engine(model, k, eta, E, R, loss=loss, loss_params=lp)
+    eng.set_embeddings(ent, rel)
+    eng.forward_backward(_dev(t), (_dev(neg_ent), _dev(neg_keep)))
+    got_loss = eng.read_loss()
+    g_e, g_r = _dense(eng, eng.g_ent), _dense(eng, eng.g_rel)
+    pads_zero = bool((eng.g_ent[:, eng.k:eng.kp] == 0).all())
+    resident = eng.lib.kge_rows_resident(eng.h)
+    eng.close()
+    assert resident == (1 if name in ("cfg2", "cfg3") else 0)  # cfg4/cfg5 take the windowed / grouped path
+    rs = _ref(model, k, ent, rel, eta, loss, lp)
+    rl, _, _, r_e, r_r = rs.loss_and_grads(t, _corruption_tensor(t, neg_ent, neg_keep, eta))
+    assert abs(got_loss - float(rl)) <= RTOL * abs(float(rl)), (got_loss, float(rl))
+    assert _close(g_e, r_e.numpy()), np.abs(g_e - r_e.numpy()).max() / np.abs(r_e.numpy()).max()
+    assert _close(g_r, r_r.numpy()), np.abs(g_r - r_r.numpy()).max() / np.abs(r_r.numpy()).max()
+    assert pads_zero
+
+
 def test_gradient_linearity_full_size():
-    """cfg2 shape at full size (14.5k entities, B=27,212): grads(A u B) == grads(A) + grads(B),
-    loss additive -- a size-independent property the oracle cannot check in seconds."""
+    """cfg2 at full size: grads(A u B) == grads(A) + grads(B), loss additive (a size-independent property, kept beside
+    the oracle comparison above)."""
     rng = np.random.default_rng(23)
     model, E, R, k, eta, B = "ComplEx", 14505, 237, 200, 10, 27212
     eng = _engine(model, k, eta, E, R, loss="self_adversarial")
@@ -423,8 +468,104 @@ def test_gradient_linearity_full_size():
     scale = g_all.abs().max().item()
     assert (eng.g_ent - g_all).abs().max().item() <= 1e-4 * scale
     assert (eng.g_rel - gr_all).abs().max().item() <= 1e-4 * gr_all.abs().max().item()
-    assert (eng.g_ent[:, eng.k:eng.kp] == 0).all()
     eng.close()
+
+
+def test_initializers_bound_mean_std():
+    """The reference pins its initialisers by mean/std only (tests/ampligraph/latent_features/test_initializers.py:40-49:
+    RandomNormal(mean=0.5, stddev=0.05) -> |mean-0.5|, |std-0.05| small).  Same check through kge_init_table /
+    kge_init_glorot_uniform, plus the Glorot bound sqrt(6/(rows+K)) (EmbeddingLookupLayer.py:194-201), truncation at
+    2 stddev, zero pad columns, and seed dependence."""
+    E, R, k = 20000, 50, 37  # k not a multiple of 4: pad columns exist
+    eng = _engine("ComplEx", k, 1, E, R)
+    K = eng.internal_k
+    eng.init_glorot_uniform(seed=3)
+    ent = _dense(eng, eng.ent)
+    lim = np.sqrt(6.0 / (E + K))
+    assert np.abs(ent).max() <= lim and np.abs(ent).max() > 0.999 * lim
+    assert abs(ent.mean()) < 0.01 * lim and abs(ent.std() - lim / np.sqrt(3)) < 0.01 * lim
+    assert (eng.ent[:, k:eng.kp] == 0).all() and (eng.ent[:, eng.kp + k:] == 0).all()
+    rel = _dense(eng, eng.rel)
+    assert np.abs(rel).max() <= np.sqrt(6.0 / (R + K))
+    eng.init_glorot_uniform(seed=4)
+    assert (np.abs(_dense(eng, eng.ent) - ent) > 0).mean() > 0.99  # another seed, another table
+    eng.init_table("ent", "normal", 0.5, 0.05, seed=1)
+    x = _dense(eng, eng.ent)
+    assert abs(x.mean() - 0.5) < 1e-3 and abs(x.std() - 0.05) < 1e-3  # the reference's own test, 1e-1 there
+    assert (eng.ent[:, k:eng.kp] == 0).all()
+    eng.init_table("ent", "truncated_normal", 0.0, 1.0, seed=1)
+    x = _dense(eng, eng.ent)
+    assert np.abs(x).max() <= 2.0 and abs(x.std() - 0.87962566) < 5e-3 and abs(x.mean()) < 5e-3
+    eng.init_table("rel", "uniform", -0.25, 0.75, seed=2)
+    x = _dense(eng, eng.rel)
+    assert x.min() >= -0.25 and x.max() < 0.75 and abs(x.mean() - 0.25) < 0.02
+    eng.init_table("rel", "constant", 1.0)
+    assert (_dense(eng, eng.rel) == 1.0).all()
+    eng.close()
+
+
+def test_regulariser_pair_and_l1_l2():
+    """A [entities, relations] pair of regularisers (EmbeddingLookupLayer.py:131-155) and Keras' l1_l2 (two LP terms):
+    one optimizer step against the oracle, loss included."""
+    rng = np.random.default_rng(59)
+    model, E, R, k, eta, B = "DistMult", 60, 5, 8, 2, 30
+    ent, rel = _tables(model, E, R, k, rng, scale=0.5)
+    regs = [{"p": 1, "lambda": 1e-2, "p2": 2, "lambda2": 3e-2}, {"p": 3, "lambda": 2e-2}]
+    eng = _engine(model, k, eta, E, R, loss="nll", optimizer="sgd", optimizer_params={"learning_rate": 0.1}, regularizer=regs)
+    eng.set_embeddings(ent, rel)
+    t = _triples(E, R, B, rng)
+    neg_ent, neg_keep = _negatives(E, B, eta, rng)
+    eng.train_step(_dev(t), (_dev(neg_ent), _dev(neg_keep)))
+    rs = _ref(model, k, ent, rel, eta, "nll", {})
+    rl, _, _, g_e, g_r = rs.loss_and_grads(t, _corruption_tensor(t, neg_ent, neg_keep, eta))
+    g_e, g_r = g_e.numpy().astype(np.float64), g_r.numpy().astype(np.float64)
+    g_e += 1e-2 * np.sign(ent) + 3e-2 * 2 * ent
+    g_r += 2e-2 * 3 * np.abs(rel) ** 2 * np.sign(rel)
+    want_loss = float(rl) + 1e-2 * np.abs(ent).sum() + 3e-2 * (ent.astype(np.float64) ** 2).sum() + 2e-2 * (np.abs(rel).astype(np.float64) ** 3).sum()
+    assert abs(eng.read_loss() - want_loss) <= 2e-4 * abs(want_loss)
+    assert _close(_dense(eng, eng.ent), ent - 0.1 * g_e, rtol=2e-4) and _close(_dense(eng, eng.rel), rel - 0.1 * g_r, rtol=2e-4)
+    eng.close()
+
+
+def test_exchange_kernel_world1_equals_plain_optimizer():
+    """kge_optimizer_step_exchange with world = 1 (peer pointers = own pointers, in-kernel flag barriers against itself)
+    is the plain dense optimizer on the concatenated [ent|rel] block, zeroes the other gradient block and does not hang;
+    the 2-GPU version of this check is tests/test_gpu_multi.py."""
+    import ctypes as C
+    from ampligraph_b200 import _lib
+    rng = np.random.default_rng(61)
+    model, E, R, k, eta, B = "ComplEx", 300, 7, 10, 3, 64
+    ent, rel = _tables(model, E, R, k, rng, scale=0.5)
+    regs = [{"p": 2, "lambda": 1e-3}, {"p": 3, "lambda": 1e-3}]
+    kw = dict(loss="nll", optimizer="adam", optimizer_params={"learning_rate": 0.01}, regularizer=regs)
+    ref = _engine(model, k, eta, E, R, **kw)
+    ref.set_embeddings(ent, rel)
+    eng = _engine(model, k, eta, E, R, **kw)
+    ld, blk = eng.ld, E + R
+    buf = torch.zeros((3 * blk + 1, ld), device="cuda")  # [ent|rel | g0 | g1 | flags]
+    eng.ent, eng.rel = buf[0:E], buf[E:blk]
+    eng.set_embeddings(ent, rel)
+    gv = [(buf[blk:blk + E], buf[blk + E:2 * blk]), (buf[2 * blk:2 * blk + E], buf[2 * blk + E:3 * blk])]
+    s0, s1 = torch.zeros((blk, ld), device="cuda"), torch.zeros((blk, ld), device="cuda")
+    one = lambda ptr: (C.c_void_p * 1)(ptr)
+    for step in range(4):
+        t = _triples(E, R, B, rng)
+        ne, nk = _negatives(E, B, eta, rng)
+        b = step & 1
+        eng.g_ent, eng.g_rel = gv[b]
+        gv[b ^ 1][0].fill_(7.0)  # garbage in the OTHER block: the exchange must zero it
+        eng.forward_backward(_dev(t), (_dev(ne), _dev(nk)))
+        eng.t += 1
+        _lib.check(eng.lib.kge_optimizer_step_exchange(
+            eng.h, C.byref(eng.opt_cfgs["ent"]), C.byref(eng.opt_cfgs["rel"]), eng.t, 1, 0, one(buf.data_ptr()),
+            one(gv[b][0].data_ptr()), C.c_void_p(gv[b ^ 1][0].data_ptr()), C.c_void_p(s0.data_ptr()), C.c_void_p(s1.data_ptr()),
+            0, blk, one(buf[3 * blk:].data_ptr()), step + 1, 3, C.c_void_p(eng.loss_acc.data_ptr() + 8), eng._stream()))
+        ref.train_step(_dev(t), (_dev(ne), _dev(nk)))
+        torch.cuda.synchronize()
+        assert (gv[b ^ 1][0] == 0).all() and (gv[b ^ 1][1] == 0).all()
+    assert torch.equal(eng.ent, ref.ent) and torch.equal(eng.rel, ref.rel)  # same arithmetic, element for element
+    assert abs(eng.read_loss() - ref.read_loss()) <= 1e-6 * abs(ref.read_loss())
+    eng.close(); ref.close()
 
 
 # ---------------------------------------------------------------------------
@@ -536,6 +677,101 @@ def test_ranks_full_size_invariants():
     eng.close()
 
 
+def test_scoring_layer_plugin_methods_on_reference_kats(kats):
+    """SCORING_LAYER_REGISTRY[name](k) exposes the reference's plugin methods (AbstractScoringLayer.py:103-156) on
+    EMBEDDINGS: _compute_scores and the diagonal of both corruption-score matrices reproduce the reference's golden
+    vectors (test_TransE.py:15-46 etc.), get_ranks its rank KATs (test_AbstractScoringLayer.py:15-53)."""
+    from ampligraph_b200.latent_features import SCORING_LAYER_REGISTRY
+    for c in kats["scoring"]:
+        layer = SCORING_LAYER_REGISTRY[c["model"]](c["k"])
+        if c["model"] == "RotatE":
+            layer.max_rel_size = c["max_rel_size"]
+        e_s, e_p, e_o = (np.array(c[x], np.float32) for x in ("e_s", "e_p", "e_o"))
+        want = np.array(c["expected"], np.float32)
+        if c["form"] == "triple":
+            got = layer._compute_scores([e_s, e_p, e_o])
+        elif c["form"] == "sub_diag":
+            got = np.diag(layer._get_subject_corruption_scores([e_s, e_p, e_o], np.array(c["ent_matrix"], np.float32)))
+        else:
+            got = np.diag(layer._get_object_corruption_scores([e_s, e_p, e_o], np.array(c["ent_matrix"], np.float32)))
+        assert (np.around(got, c["round_decimals"]) == want).all(), (c["source"], got, want)
+    r = kats["ranks"]
+    layer = SCORING_LAYER_REGISTRY[r["model"]](r["k"])
+    e_s, e_p, e_o = (np.array(r[x], np.float32) for x in ("e_s", "e_p", "e_o"))
+    cand = np.array(r["ent_matrix"], np.float32)
+    for case in r["cases"]:
+        got = layer.get_ranks([e_s, e_p, e_o], cand, case["start_ent_id"], case["end_ent_id"], case["filters"] or [],
+                              None, case["corrupt_side"], case["comparison_type"])
+        assert (got == np.array(case["expected"], np.int32)).all(), (case, got)
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_corruption_scores_vs_oracle(model):
+    """kge_corruption_scores: the [b, n_cand] matrix, bit-identical to the oracle's canonical chain, subset and range forms."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(67)
+    E, R, k, b = 333, 5, 21, 37
+    ent, rel = _tables(model, E, R, k, rng, scale=0.5)
+    t = _triples(E, R, b, rng)
+    eng = _engine(model, k, 1, E, R)
+    eng.set_embeddings(ent, rel)
+    sub = np.sort(rng.choice(E, 50, replace=False)).astype(np.int32)
+    for side in ("s", "o"):
+        ref = c_oracle.corruption_scores(model, side, ent[t[:, 0]], rel[t[:, 1]], ent[t[:, 2]], ent, max_rel_size=R)
+        got = eng.corruption_scores(_dev(t), side).cpu().numpy()
+        assert got.shape == (b, E) and (got == ref).all(), np.abs(got - ref).max()
+        got = eng.corruption_scores(_dev(t), side, cand_begin=100, n_cand=77).cpu().numpy()
+        assert (got == ref[:, 100:177]).all()
+        got = eng.corruption_scores(_dev(t), side, cand_ids=_dev(sub)).cpu().numpy()
+        assert (got == ref[:, sub]).all()
+    eng.close()
+
+
+def test_middle_strategy_over_candidate_partitions():
+    """'middle' = greater + ceil(equal/2) is not additive over candidate partitions; accumulating the RAW
+    counters and finalizing once is (this is what the row-sharded paths do).  Coarse scores -> many ties."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(71)
+    model, E, R, k, b = "DistMult", 500, 3, 4, 64
+    ent = np.round(rng.uniform(-1, 1, (E, k)), 1).astype(np.float32)
+    rel = np.round(rng.uniform(-1, 1, (R, k)), 1).astype(np.float32)
+    t = _triples(E, R, b, rng)
+    lists, off, idx = _filters(E, b, rng)
+    eng = _engine(model, k, 1, E, R)
+    eng.set_embeddings(ent, rel)
+    for strategy in ("middle", "worst", "best"):
+        want = c_oracle.rank_triples(model, "o", strategy, ent, rel, t, filters=lists)
+        counts = torch.zeros((b, 3), dtype=torch.int32, device="cuda")
+        for lo, hi in ((0, 101), (101, 333), (333, E)):
+            eng.rank(_dev(t), "o", strategy, _dev(off), _dev(idx), cand_begin=lo, n_cand=hi - lo, counts=counts)
+        got = eng.finalize_ranks(counts, strategy).cpu().numpy()
+        assert (got == want).all(), strategy
+    # the naive accumulation really is wrong for 'middle' on this input (so the test above has teeth)
+    naive = torch.zeros(b, dtype=torch.int32, device="cuda")
+    for lo, hi in ((0, 101), (101, 333), (333, E)):
+        eng.rank(_dev(t), "o", "middle", _dev(off), _dev(idx), cand_begin=lo, n_cand=hi - lo, out=naive)
+    assert (naive.cpu().numpy() != c_oracle.rank_triples(model, "o", "middle", ent, rel, t, filters=lists)).any()
+    eng.close()
+
+
+def test_two_handles_two_streams_device_guard():
+    """Every entry point makes its handle's device current and restores the caller's: drive a handle
+    from a thread whose current device is changed underneath, on a non-default stream."""
+    rng = np.random.default_rng(73)
+    E, R, k = 50, 3, 6
+    ent, rel = _tables("TransE", E, R, k, rng, scale=0.5)
+    eng = _engine("TransE", k, 1, E, R)
+    eng.set_embeddings(ent, rel)
+    t = _dev(_triples(E, R, 20, rng))
+    want = eng.score(t).cpu()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        got = eng.score(t)
+    st.synchronize()
+    assert torch.equal(got.cpu(), want) and torch.cuda.current_device() == 0
+    eng.close()
+
+
 def test_error_convention():
     from ampligraph_b200 import _lib
     with pytest.raises(ValueError):
@@ -544,7 +780,14 @@ def test_error_convention():
         _engine("TransE", 4, 1, 10, 2, loss="nope")
     eng = _engine("TransE", 4, 1, 10, 2)
     with pytest.raises(ValueError):  # invalid corrupt side id
-        _lib.check(eng.lib.kge_rank(eng.h, 7, 0, None, None, None, 0, None, 0, 0, None, None, 0, None, None))
+        _lib.check(eng.lib.kge_rank(eng.h, 7, 0, None, None, None, 0, None, 0, 0, None, None, 0, None, None, None, 0, None))
+    with pytest.raises(ValueError):  # the workspace is the caller's: too small -> refused, never allocated behind its back
+        out = torch.zeros(4, dtype=torch.int32, device="cuda")
+        tr = torch.zeros((4, 3), dtype=torch.int32, device="cuda")
+        ws = torch.empty(256, dtype=torch.uint8, device="cuda")
+        _lib.check(eng.lib.kge_rank(eng.h, 0, 0, eng.ent.data_ptr(), eng.rel.data_ptr(), tr.data_ptr(), 4, None, 0, 10, None,
+                                    None, 0, out.data_ptr(), None, ws.data_ptr(), 8, None))
+    assert eng.lib.kge_rank_workspace_bytes(eng.h, 4, 10) > 8
     with pytest.raises(ValueError):  # gradient buffers are mandatory outside FORWARD_ONLY
         _lib.check(eng.lib.kge_train_step(eng.h, 0, eng.ent.data_ptr(), eng.rel.data_ptr(), None, None,
                                           eng.ent.data_ptr(), 1, None, None, 0, 0, None, None, None, None, None, None))

@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for name in declared:
         assert hasattr(lib, name), "missing export: " + name
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
-    assert lib.kge_abi_version() == 1
+    assert lib.kge_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_fails_loudly_without_gpu():
@@ -33,7 +33,7 @@ def test_library_fails_loudly_without_gpu():
     import ctypes as C
     from ampligraph_b200 import _lib
     lib = _lib.load()
-    cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0, 0, 0)
+    cfg = _lib.KgeConfig(C.sizeof(_lib.KgeConfig), 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0, 0, 0, 0)
     h = C.c_void_p()
     rc = lib.kge_create(C.byref(cfg), C.byref(h))
     assert rc == _lib.KGE_ERR_CUDA and b"no CPU path" in lib.kge_last_error()
@@ -45,9 +45,17 @@ def test_library_fails_loudly_without_gpu():
 def test_config_struct_matches_header():
     import ctypes as C
     from ampligraph_b200 import _lib
-    assert C.sizeof(_lib.KgeConfig) == 64 and C.sizeof(_lib.KgeOptimizerConfig) == 40
+    # sizeof() of the C structs, measured by compiling include/kge_b200.h with gcc (no hand-kept constants)
+    src = ('#include <stdio.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu\\n", sizeof(kge_config), '
+           'sizeof(kge_optimizer_config), sizeof(kge_shard_map)); return 0;}' % _lib.HEADER)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-o", os.path.join(d, "s"), os.path.join(d, "s.c")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert [C.sizeof(_lib.KgeConfig), C.sizeof(_lib.KgeOptimizerConfig), C.sizeof(_lib.KgeShardMap)] == sizes, sizes
     assert C.sizeof(_lib.KgeShardMap) == 16 + 3 * 8 * 8  # kge_shard_map: header + ent[8] + grad_ent[8] + stamp_ent[8]
-    bad = _lib.KgeConfig(12, 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0, 0, 0)
+    bad = _lib.KgeConfig(12, 0, 4, 1, 10, 2, 0, 0, 1.0, 0.5, 0, 0, 0, 0, 0)
     h = C.c_void_p()
     assert _lib.load().kge_create(C.byref(bad), C.byref(h)) == _lib.KGE_ERR_INVALID_ARGUMENT  # ABI guard first
 
@@ -69,6 +77,15 @@ def test_registries_and_error_convention():
         optimizers.get("lion")
     assert regularizers.get("l3", {"lambda": 1e-3}).kernel_params() == {"p": 3, "lambda": 1e-3}
     assert regularizers.get("LP").kernel_params() == {"p": 2, "lambda": 1e-5}
+    # Keras names and a [entities, relations] pair (EmbeddingLookupLayer.py:131-155)
+    assert regularizers.get("l1_l2").kernel_params() == {"p": 1, "lambda": 0.01, "p2": 2, "lambda2": 0.01}
+    assert regularizers.get({"class_name": "L2", "config": {"l2": 0.5}}).kernel_params() == {"p": 2, "lambda": 0.5}
+    pair = regularizers.get_pair(["l1", None])
+    assert pair[0].kernel_params() == {"p": 1, "lambda": 0.01} and pair[1] is None
+    with pytest.raises(AssertionError):
+        regularizers.get_pair(["l1", "l2", "l2"])
+    with pytest.raises(ValueError):
+        regularizers.get("dropout")
     from ampligraph_b200.latent_features import ScoringBasedEmbeddingModel
     m = ScoringBasedEmbeddingModel(eta=2, k=4, scoring_type="RotatE")
     with pytest.raises(AssertionError):  # ScoringBasedEmbeddingModel.py:1312-1315
@@ -79,6 +96,43 @@ def test_registries_and_error_convention():
         ScoringBasedEmbeddingModel(eta=2, k=4, scoring_type="Random")
     with pytest.raises(KeyError):
         ScoringBasedEmbeddingModel(eta=2, k=4, scoring_type="ConvE")
+
+
+def test_initializers_resolve_like_keras():
+    """tf.keras.initializers.get names -> the four device kinds of kge_init_table, Keras' fan conventions for a
+    [rows, internal_k] weight (EmbeddingLookupLayer.py:105-129)."""
+    from ampligraph_b200.latent_features import initializers as I
+    rows, cols = 1000, 200
+    assert I.get("glorot_uniform").spec(rows, cols) == ("uniform", -np.sqrt(6 / 1200), np.sqrt(6 / 1200))
+    assert I.get("random_normal").spec(rows, cols) == ("normal", 0.0, 0.05)
+    assert I.get({"class_name": "RandomNormal", "config": {"mean": 0.5, "stddev": 0.05}}).spec(rows, cols) == ("normal", 0.5, 0.05)
+    assert I.get("random_uniform").spec(rows, cols) == ("uniform", -0.05, 0.05)
+    kind, mean, std = I.get("glorot_normal").spec(rows, cols)
+    assert kind == "truncated_normal" and mean == 0.0 and abs(std - np.sqrt(2 / 1200) / 0.87962566103423978) < 1e-12
+    kind, lo, hi = I.get("he_uniform").spec(rows, cols)
+    assert kind == "uniform" and abs(hi - np.sqrt(6 / rows)) < 1e-12 and lo == -hi
+    assert I.get("zeros").spec(rows, cols) == ("constant", 0.0, 0.0) and I.get("ones").spec(rows, cols)[1] == 1.0
+    assert isinstance(I.get(I.RandomUniform(-1, 1)), I.RandomUniform)
+    arr = np.zeros((3, 4), np.float32)
+    assert I.get(arr) is arr and callable(I.get(lambda shape: np.zeros(shape)))
+    with pytest.raises(ValueError):
+        I.get("orthogonal_ish")
+    from ampligraph_b200.latent_features import ScoringBasedEmbeddingModel
+    m = ScoringBasedEmbeddingModel(eta=2, k=4, scoring_type="ComplEx")
+    m.compile(loss="nll", entity_relation_initializer=["random_normal", "glorot_uniform"], entity_relation_regularizer=["l2", None])
+    assert m._initializer[0].name == "random_normal" and m._initializer[1].name == "glorot_uniform"
+    assert m._regularizer[0].kernel_params()["p"] == 2 and m._regularizer[1] is None
+    with pytest.raises(AssertionError):
+        m.compile(loss="nll", entity_relation_initializer=["zeros", "zeros", "zeros"])
+
+
+def test_lazy_optimizer_rejected_with_replicated_tables():
+    """lazy_* + data parallelism would skip rows other ranks touched; refuse it."""
+    from ampligraph_b200.parallel import reject_lazy
+    reject_lazy("lazy_adam", 1)
+    reject_lazy("adam", 8)
+    with pytest.raises(NotImplementedError):
+        reject_lazy("lazy_adam", 2)
 
 
 def test_data_indexer_first_seen_order():
