@@ -30,7 +30,7 @@ class KgeConfig(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("scoring", C.c_int32), ("k", C.c_int32), ("eta", C.c_int32),
                 ("n_ent", C.c_int64), ("n_rel", C.c_int64), ("loss", C.c_int32), ("reduction", C.c_int32),
                 ("margin", C.c_float), ("alpha", C.c_float), ("device", C.c_int32), ("neg_group", C.c_int32),
-                ("max_rel_size", C.c_int64), ("rank_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("max_rel_size", C.c_int64), ("rank_mode", C.c_int32), ("rank_pair_cap", C.c_int32)]
 
 
 class KgeOptimizerConfig(C.Structure):
@@ -87,6 +87,8 @@ PROTOTYPES = {
                            C.c_int64, _P, _P, _P, C.c_int64, _P]),
     "kge_rank_finalize": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
     "kge_corruption_scores": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P,
+                                        C.c_int64, _P]),
+    "kge_rank_filter_probe": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P, _P,
                                         C.c_int64, _P]),
     "kge_rank_workspace_bytes": (C.c_int64, [_P, C.c_int64, C.c_int64]),
 }

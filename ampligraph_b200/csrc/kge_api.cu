@@ -86,7 +86,7 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
         return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for reduction!");
     if (cfg->rank_mode != KGE_RANK_MODE_AUTO && cfg->rank_mode != KGE_RANK_MODE_EXACT)
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: unknown rank_mode %d", cfg->rank_mode);
-    if (cfg->max_rel_size < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: max_rel_size < 0");
+    if (cfg->max_rel_size < 0 || cfg->rank_pair_cap < 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: max_rel_size / rank_pair_cap < 0");
     if (cfg->k < 1 || cfg->eta < 1 || cfg->n_ent < 1 || cfg->n_rel < 1)
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_create: k, eta, n_ent, n_rel must be >= 1");
     if (cfg->n_ent > 0x7fffffffLL || cfg->n_rel > 0x7fffffffLL)
@@ -606,10 +606,13 @@ extern "C" int kge_peer_barrier(kge_handle *h, int32_t world, int32_t rank, uint
 struct RankWorkspace {
     float *qs, *qo, *qaux;   // [b, ld] query vectors (subject side / object side / RotatE object rows)
     int32_t *qpos, *cnt;     // [b], [b,3]
+    bool tc;                 // tensor-core filter region present (KGE_RANK_MODE_AUTO, bilinear model, large enough call)
+    RankTcLayout tcl;
+    void *tc_base;
     size_t bytes;
 };
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-static RankWorkspace carve_rank_workspace(const kge_handle *h, void *base, int64_t b, int64_t /*n_cand*/)
+static RankWorkspace carve_rank_workspace(const kge_handle *h, void *base, int64_t b, int64_t n_cand)
 {
     RankWorkspace w;
     char *p = (char *)base;
@@ -620,6 +623,14 @@ static RankWorkspace carve_rank_workspace(const kge_handle *h, void *base, int64
     w.qaux = (float *)(p + off); off += qbytes;
     w.qpos = (int32_t *)(p + off); off += align256((size_t)b * sizeof(int32_t));
     w.cnt = (int32_t *)(p + off); off += align256((size_t)3 * b * sizeof(int32_t));
+    w.tc = h->cfg.rank_mode == KGE_RANK_MODE_AUTO && rank_tc_applicable(h->L, 0, b, n_cand);
+    w.tc_base = nullptr;
+    if (w.tc) {
+        off = (off + 1023) & ~(size_t)1023;
+        w.tcl = rank_tc_layout(h->L, b, n_cand, h->cfg.rank_pair_cap);
+        w.tc_base = p + off;
+        off += w.tcl.bytes;
+    }
     w.bytes = off;
     return w;
 }
@@ -634,7 +645,8 @@ static int rank_impl(kge_handle *h, const kge_shard_map *map, int64_t filt_base,
                      const float *ent_dev, const float *rel_dev, const int32_t *triples_dev, int64_t b,
                      const int32_t *cand_ids_dev, int64_t cand_begin, int64_t n_cand, const int64_t *filt_off_dev,
                      const int32_t *filt_idx_dev, int64_t n_filt, int32_t *ranks_dev, int32_t *counts_dev,
-                     float *scores_dev, void *workspace_dev, int64_t workspace_bytes, void *stream)
+                     float *scores_dev, void *workspace_dev, int64_t workspace_bytes, void *stream,
+                     float *probe_delta_dev = nullptr)
 {
     KGE_CHECK_HANDLE(h, "kge_rank");
     if (side != KGE_SIDE_S && side != KGE_SIDE_O) return fail(KGE_ERR_INVALID_ARGUMENT, "Invalid value for corrupt_side");
@@ -654,7 +666,7 @@ static int rank_impl(kge_handle *h, const kge_shard_map *map, int64_t filt_base,
     if (!workspace_dev || workspace_bytes < need)
         return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: workspace of %lld bytes needed (kge_rank_workspace_bytes), got %lld",
                     (long long)need, (long long)(workspace_dev ? workspace_bytes : 0));
-    if (((uintptr_t)workspace_dev & 255u) != 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: workspace must be 256-byte aligned");
+    if (((uintptr_t)workspace_dev & 1023u) != 0) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank: workspace must be 1024-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const RankWorkspace w = carve_rank_workspace(h, workspace_dev, b, n_cand);
     if (int rc = refresh_rotation(h, rel_dev, st)) return rc;
@@ -668,9 +680,9 @@ static int rank_impl(kge_handle *h, const kge_shard_map *map, int64_t filt_base,
     KGE_CUDA(launch_rank_prepare(h->L, sv, ent_dev, rel_dev, h->rot, triples_dev, b, h->score_scale, w.qs, w.qo, w.qaux,
                                  w.qpos, st),
              "kge_rank: prepare");
-    // raw counters: the caller's accumulator, or a zeroed scratch that is finalized into ranks_dev below
-    int32_t *cnt = counts_dev ? counts_dev : w.cnt;
-    if (!counts_dev) KGE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)3 * b * sizeof(int32_t), st), "kge_rank: memset");
+    // raw counters of THIS call in a zeroed scratch; added to the caller's accumulator or finalized into ranks_dev below
+    int32_t *cnt = w.cnt;
+    KGE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)3 * b * sizeof(int32_t), st), "kge_rank: memset");
     RankParams p;
     memset(&p, 0, sizeof(p));
     p.L = h->L;
@@ -687,10 +699,20 @@ static int rank_impl(kge_handle *h, const kge_shard_map *map, int64_t filt_base,
     p.scale = h->score_scale;
     p.filt_base = filt_base;
     p.scores = scores_dev;
-    KGE_CUDA(launch_rank_count(p, cnt, st), "kge_rank: count");
+    if (probe_delta_dev) {  // kge_rank_filter_probe: approximate scores + assumed bound, nothing is counted
+        if (!w.tc || n_cand == 0) return fail(KGE_ERR_UNSUPPORTED, "kge_rank_filter_probe: the tensor-core filter does not apply to this call");
+        p.scores = nullptr;
+        KGE_CUDA(launch_rank_count_tc(p, w.tcl, w.tc_base, cnt, h->sm_count, st, scores_dev, probe_delta_dev), "kge_rank_filter_probe");
+        return KGE_OK;
+    }
+    if (w.tc && !scores_dev && n_cand > 0)  // tensor-core filter + exact refine: bit-identical counters (kge_rank_tc.cu)
+        KGE_CUDA(launch_rank_count_tc(p, w.tcl, w.tc_base, cnt, h->sm_count, st), "kge_rank: tensor-core count");
+    else
+        KGE_CUDA(launch_rank_count(p, cnt, st), "kge_rank: count");
     if (filt_off_dev && n_filt > 0)
         KGE_CUDA(launch_rank_filter_n(p, (const long long *)filt_off_dev, filt_idx_dev, n_filt, cnt, st), "kge_rank: filter");
-    if (!counts_dev && ranks_dev) KGE_CUDA(launch_rank_finalize(cnt, b, strategy, ranks_dev, st), "kge_rank: finalize");
+    if (counts_dev) KGE_CUDA(launch_rank_accumulate(cnt, b, counts_dev, st), "kge_rank: accumulate");
+    else if (ranks_dev) KGE_CUDA(launch_rank_finalize(cnt, b, strategy, ranks_dev, st), "kge_rank: finalize");
     return KGE_OK;
 }
 
@@ -741,4 +763,14 @@ extern "C" int kge_corruption_scores(kge_handle *h, int32_t side, const float *e
     if (b > 0 && n_cand > 0 && !scores_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_corruption_scores: null output");
     return rank_impl(h, nullptr, 0, side, KGE_RANK_WORST, ent_dev, rel_dev, triples_dev, b, cand_ids_dev, cand_begin, n_cand,
                      nullptr, nullptr, 0, nullptr, nullptr, scores_dev, workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" int kge_rank_filter_probe(kge_handle *h, int32_t side, const float *ent_dev, const float *rel_dev,
+                                     const int32_t *triples_dev, int64_t b, const int32_t *cand_ids_dev, int64_t cand_begin,
+                                     int64_t n_cand, float *approx_dev, float *delta_dev, void *workspace_dev,
+                                     int64_t workspace_bytes, void *stream)
+{
+    if (!approx_dev || !delta_dev) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_rank_filter_probe: null output");
+    return rank_impl(h, nullptr, 0, side, KGE_RANK_WORST, ent_dev, rel_dev, triples_dev, b, cand_ids_dev, cand_begin, n_cand,
+                     nullptr, nullptr, 0, nullptr, nullptr, approx_dev, workspace_dev, workspace_bytes, stream, delta_dev);
 }

@@ -115,6 +115,8 @@ struct RankParams {
     long long filt_base;   // subtracted from filter ids (global id of the local shard's first row)
     float scale;           // HolE
     float *scores;         // nullptr, or [b, n_cand] output of every candidate's score (kge_corruption_scores)
+    const unsigned *gate;  // nullptr, or device counter: kge_rank_dot_kernel only runs when *gate > gate_cap (overflow fallback
+    unsigned gate_cap;     // of the tensor-core filter, kge_rank_tc.cu)
 };
 cudaError_t launch_rank_prepare(const Layout &L, const ShardView &sv, const float *ent, const float *rel, const float *rot,
                                 const int32_t *triples, long long b, float scale, float *qvec_s, float *qvec_o,
@@ -124,5 +126,19 @@ cudaError_t launch_rank_count(const RankParams &p, int32_t *cnt, cudaStream_t st
 cudaError_t launch_rank_filter_n(const RankParams &p, const long long *filt_off, const int32_t *filt_idx,
                                  long long n_pairs, int32_t *cnt, cudaStream_t st);
 cudaError_t launch_rank_finalize(const int32_t *cnt, long long b, int strategy, int32_t *ranks, cudaStream_t st);
+cudaError_t launch_rank_accumulate(const int32_t *cnt, long long b, int32_t *counts, cudaStream_t st);  // counts += cnt
+
+// kge_rank_tc.cu: tensor-core filter + exact refine for the bilinear models
+struct RankTcLayout {  // carve-up of the tensor-core part of the caller's workspace
+    int nkb, ksteps, n_qb, n_ct;
+    unsigned pair_cap;
+    size_t off_a, off_b, off_thr, off_qnorm, off_tnorm, off_count, off_pairs, bytes;
+};
+bool rank_tc_applicable(const Layout &L, int side, long long b, long long n_cand);
+RankTcLayout rank_tc_layout(const Layout &L, long long b, long long n_cand, int pair_cap_override);
+// same contract as launch_rank_count (cnt[3q+0] += #greater, cnt[3q+1] += #equal), bit-identical results.
+// probe_a/probe_d != nullptr: diagnostic run -- write approximate scores and assumed error bounds [b, n_cand], count nothing
+cudaError_t launch_rank_count_tc(const RankParams &p, const RankTcLayout &w, void *ws, int32_t *cnt, int sm_count, cudaStream_t st,
+                                 float *probe_a = nullptr, float *probe_d = nullptr);
 
 }  // namespace kge

@@ -343,6 +343,7 @@ __device__ __forceinline__ unsigned long long rk_fma2(float e, unsigned long lon
 
 __global__ void __launch_bounds__(RD_THREADS, 2) kge_rank_dot_kernel(const RankParams p, int32_t *__restrict__ cnt)
 {
+    if (p.gate && *p.gate <= p.gate_cap) return;  // armed only as the overflow fallback of the tensor-core filter
     extern __shared__ __align__(128) float smem[];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int cg = warp & 1, qg = warp >> 1;  // 2 candidate groups of 128, 4 query groups of 16
@@ -541,6 +542,19 @@ __global__ void kge_rank_finalize_kernel(const int32_t *__restrict__ cnt, long l
     int gt = cnt[3 * i], eq = cnt[3 * i + 1], fl = cnt[3 * i + 2];
     int r = (strategy == KGE_RANK_BEST) ? gt : (strategy == KGE_RANK_MIDDLE) ? gt + (eq + 1) / 2 : gt + eq;
     ranks[i] += r - fl;
+}
+
+__global__ void kge_rank_accumulate_kernel(const int32_t *__restrict__ cnt, long long n, int32_t *__restrict__ counts)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counts[i] += cnt[i];
+}
+
+cudaError_t launch_rank_accumulate(const int32_t *cnt, long long b, int32_t *counts, cudaStream_t st)
+{
+    if (b == 0) return cudaSuccess;
+    kge_rank_accumulate_kernel<<<(unsigned)((3 * b + 255) / 256), 256, 0, st>>>(cnt, 3 * b, counts);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_rank_finalize(const int32_t *cnt, long long b, int strategy, int32_t *ranks, cudaStream_t st)

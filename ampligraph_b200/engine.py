@@ -44,7 +44,7 @@ def _traced(name):
 class KGEEngine:
     def __init__(self, scoring_type, k, eta, n_ent, n_rel, loss="pairwise", loss_params=None,
                  optimizer="adam", optimizer_params=None, regularizer=None, device=0, neg_group=0,
-                 table_alloc=None, ent_rows=None, max_rel_size=None, rank_mode=None):
+                 table_alloc=None, ent_rows=None, max_rel_size=None, rank_mode=None, rank_pair_cap=0):
         """regularizer: None | {"p":, "lambda": [, "p2":, "lambda2":]} | a pair [entities, relations] of those
         (EmbeddingLookupLayer.py:131-155).  max_rel_size: RotatE phase normalisation when it differs from the
         relation-table rows (RotatE.py:96).  rank_mode: 'auto' (tensor-core filter + exact refine for the bilinear
@@ -70,7 +70,7 @@ class KGEEngine:
                              int(n_rel), _lib.LOSSES[loss], _lib.REDUCTIONS[reduction],
                              float(lp.get("margin", default_margin)), float(lp.get("alpha", 0.5)), int(device),
                              int(neg_group), int(max_rel_size or 0),
-                             _lib.RANK_MODES[rank_mode or os.environ.get("KGE_B200_RANK_MODE", "auto")], 0)
+                             _lib.RANK_MODES[rank_mode or os.environ.get("KGE_B200_RANK_MODE", "auto")], int(rank_pair_cap))
         h = C.c_void_p()
         _lib.check(self.lib.kge_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -265,7 +265,7 @@ class KGEEngine:
         Growing frees the old buffer through torch's stream-ordered caching allocator, so no synchronisation is needed."""
         need = int(self.lib.kge_rank_workspace_bytes(self.h, int(b), int(n_cand)))
         if self._rank_ws is None or self._rank_ws.numel() < need:
-            self._rank_ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            self._rank_ws = torch.empty(max(need, 1024), dtype=torch.uint8, device=self.device)
         return self._rank_ws, need
 
     @_traced("kge.rank")
@@ -297,6 +297,19 @@ class KGEEngine:
         _lib.check(self.lib.kge_rank_finalize(self.h, _ptr(counts), b, _lib.STRATEGIES[strategy], _ptr(out), self._stream()))
         self.launches += 1
         return out
+
+    def rank_filter_probe(self, triples, side, cand_ids=None, cand_begin=0, n_cand=None):
+        """Diagnostic (kge_rank_filter_probe): (approximate tensor-core scores, assumed error bound), both [b, n_cand]."""
+        b = triples.shape[0]
+        if n_cand is None:
+            n_cand = cand_ids.numel() if cand_ids is not None else self.n_ent - cand_begin
+        approx = torch.empty((b, int(n_cand)), dtype=torch.float32, device=self.device)
+        delta = torch.empty_like(approx)
+        ws, ws_bytes = self.rank_workspace(b, n_cand)
+        _lib.check(self.lib.kge_rank_filter_probe(self.h, _lib.SIDES[side], _ptr(self.ent), _ptr(self.rel), _ptr(triples), b,
+                                                  _ptr(cand_ids), int(cand_begin), int(n_cand), _ptr(approx), _ptr(delta),
+                                                  _ptr(ws), ws_bytes, self._stream()))
+        return approx, delta
 
     def corruption_scores(self, triples, side, cand_ids=None, cand_begin=0, n_cand=None):
         """_get_subject_corruption_scores / _get_object_corruption_scores: fp32 [b, n_cand], canonical summation order."""

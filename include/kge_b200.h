@@ -104,7 +104,8 @@ typedef struct kge_config {
     int64_t max_rel_size; /* RotatE phase normalisation sqrt(6/(internal_k*max_rel_size)) (RotatE.py:96,
                              ScoringBasedEmbeddingModel.py:338); 0 = n_rel */
     int32_t rank_mode;    /* enum kge_rank_mode */
-    int32_t reserved;     /* 0 */
+    int32_t rank_pair_cap; /* 0 = auto (max(2^20, b*n_cand/16)); >0 caps the list of undecided pairs of the tensor-core
+                              filter -- a testing knob for its overflow fallback */
 } kge_config;
 
 /* optimizers.get (optimizers.py:255-291) -> tf.keras.optimizers.legacy.{SGD,Adam,Adagrad};
@@ -312,7 +313,7 @@ int kge_peer_barrier(kge_handle *h, int32_t world, int32_t rank, uint32_t *const
  *                 Candidate partitions (row shards, cand_begin chunks) must accumulate THESE and call
  *                 kge_rank_finalize once: 'middle' is best + ceil(equal/2) (:232-244), which is not
  *                 additive over partitions; 'worst'/'best' are, so ranks_dev may be accumulated directly.
- *   workspace_dev caller-owned scratch of at least kge_rank_workspace_bytes(h, b, n_cand) bytes, 256-byte
+ *   workspace_dev caller-owned scratch of at least kge_rank_workspace_bytes(h, b, n_cand) bytes, 1024-byte
  *                 aligned; contents are undefined afterwards.  The library never allocates or synchronises. */
 int kge_rank(kge_handle *h, int32_t side, int32_t strategy, const float *ent_dev,
              const float *rel_dev, const int32_t *triples_dev, int64_t b,
@@ -343,6 +344,15 @@ int kge_corruption_scores(kge_handle *h, int32_t side, const float *ent_dev, con
                           const int32_t *triples_dev, int64_t b, const int32_t *cand_ids_dev,
                           int64_t cand_begin, int64_t n_cand, float *scores_dev /*[b, n_cand]*/,
                           void *workspace_dev, int64_t workspace_bytes, void *stream);
+
+/* Diagnostic for KGE_RANK_MODE_AUTO (used by the tests that pin its error bound): the APPROXIMATE scores of the
+ * tensor-core filter pass and the error bound delta the filter assumes for each pair, both [b, n_cand] fp32, in the
+ * units of kge_corruption_scores.  The filter is sound iff |approx - kge_corruption_scores| <= delta everywhere.
+ * KGE_ERR_UNSUPPORTED when the filter does not apply (model, mode or size). */
+int kge_rank_filter_probe(kge_handle *h, int32_t side, const float *ent_dev, const float *rel_dev,
+                          const int32_t *triples_dev, int64_t b, const int32_t *cand_ids_dev, int64_t cand_begin,
+                          int64_t n_cand, float *approx_dev, float *delta_dev, void *workspace_dev,
+                          int64_t workspace_bytes, void *stream);
 
 /* bytes of caller-owned scratch kge_rank / kge_rank_sharded / kge_corruption_scores need for b queries
  * against n_cand candidates (query vectors, counters and -- in KGE_RANK_MODE_AUTO for the bilinear models --

@@ -772,6 +772,81 @@ def test_two_handles_two_streams_device_guard():
     eng.close()
 
 
+TC_MODELS = ["DistMult", "ComplEx", "HolE"]
+
+
+@pytest.mark.parametrize("model,k,E,b,scale", [("ComplEx", 200, 3000, 200, 0.05), ("DistMult", 400, 2100, 130, 0.3),
+                                               ("HolE", 37, 1500, 70, 0.5), ("ComplEx", 1000, 800, 257, 0.02),
+                                               ("DistMult", 50, 5000, 64, 1.0)])
+def test_tc_filter_error_bound(model, k, E, b, scale):
+    """The tensor-core filter pass (tcgen05, split-bf16 operands) is sound iff its approximate score is within the bound it
+    assumes of the canonical FP32 score for EVERY (query, candidate) pair (kge_rank_tc.cu header).  Measured through
+    kge_rank_filter_probe against kge_corruption_scores; the bound must also hold with a >= 4x margin, and the
+    approximation must be genuinely fine (3 bf16 products, not 1)."""
+    rng = np.random.default_rng(83)
+    R = 9
+    ent, rel = _tables(model, E, R, k, rng, scale=scale)
+    t = _triples(E, R, b, rng)
+    eng = _engine(model, k, 1, E, R, rank_mode="auto")
+    eng.set_embeddings(ent, rel)
+    for side in ("s", "o"):
+        exact = eng.corruption_scores(_dev(t), side)
+        approx, delta = eng.rank_filter_probe(_dev(t), side)
+        err = (approx.double() - exact.double()).abs()
+        assert bool((delta > 0).all()) and bool((err <= delta.double()).all()), float((err / delta.double()).max())
+        worst = float((err / delta.double()).max())
+        assert worst <= 0.25, worst
+        rel_err = float(err.max() / exact.abs().max())
+        assert rel_err < 2e-5, rel_err   # a single bf16 product would sit at ~4e-3
+    eng.close()
+
+
+@pytest.mark.parametrize("model", TC_MODELS)
+@pytest.mark.parametrize("E,b,k,coarse", [(5000, 300, 50, True), (1300, 129, 200, False), (20000, 1024, 24, True)])
+def test_ranks_tensor_core_filter_equals_exact_chain(model, E, b, k, coarse):
+    """KGE_RANK_MODE_AUTO (tensor-core filter + exact refine) == KGE_RANK_MODE_EXACT (canonical FP32 chain for every
+    pair), bit for bit: both sides, all three tie strategies, filtered and unfiltered, candidate ranges and subsets,
+    raw counters.  Coarse tables put thousands of candidates exactly ON the positive's bin (ties), fine ones next to it."""
+    rng = np.random.default_rng(89)
+    R = 7
+    ent, rel = _tables(model, E, R, k, rng, scale=0.6)
+    if coarse:
+        ent, rel = np.round(ent, 1), np.round(rel, 1)
+    t = _triples(E, R, b, rng)
+    lists, off, idx = _filters(E, b, rng, maxlen=12)
+    a = _engine(model, k, 1, E, R, rank_mode="auto")
+    x = _engine(model, k, 1, E, R, rank_mode="exact")
+    a.set_embeddings(ent, rel); x.set_embeddings(ent, rel)
+    td = _dev(t)
+    sub = _dev(np.sort(rng.choice(E, 777, replace=False)).astype(np.int32))
+    for side in ("s", "o"):
+        for strategy in ("worst", "best", "middle"):
+            assert torch.equal(a.rank(td, side, strategy), x.rank(td, side, strategy)), (side, strategy)
+        assert torch.equal(a.rank(td, side, "worst", _dev(off), _dev(idx)), x.rank(td, side, "worst", _dev(off), _dev(idx)))
+        assert torch.equal(a.rank(td, side, "worst", cand_begin=123, n_cand=E - 200), x.rank(td, side, "worst", cand_begin=123, n_cand=E - 200))
+        assert torch.equal(a.rank(td, side, "middle", cand_ids=sub), x.rank(td, side, "middle", cand_ids=sub))
+        ca = torch.zeros((b, 3), dtype=torch.int32, device="cuda"); cx = torch.zeros_like(ca)
+        a.rank(td, side, "worst", _dev(off), _dev(idx), counts=ca); x.rank(td, side, "worst", _dev(off), _dev(idx), counts=cx)
+        assert torch.equal(ca, cx)
+    a.close(); x.close()
+
+
+def test_tensor_core_filter_overflow_falls_back_to_exact():
+    """When more pairs are undecided than the list holds, the gated exact kernel recounts the whole call: same ranks."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(97)
+    model, E, R, k, b = "DistMult", 1500, 3, 8, 96
+    ent = np.round(rng.uniform(-1, 1, (E, k)), 1).astype(np.float32)
+    rel = np.round(rng.uniform(-1, 1, (R, k)), 1).astype(np.float32)
+    t = _triples(E, R, b, rng)
+    eng = _engine(model, k, 1, E, R, rank_mode="auto", rank_pair_cap=5)  # thousands of exact ties -> far more than 5 undecided pairs
+    eng.set_embeddings(ent, rel)
+    for side in ("s", "o"):
+        got = eng.rank(_dev(t), side, "middle").cpu().numpy()
+        assert (got == c_oracle.rank_triples(model, side, "middle", ent, rel, t)).all()
+    eng.close()
+
+
 def test_error_convention():
     from ampligraph_b200 import _lib
     with pytest.raises(ValueError):
