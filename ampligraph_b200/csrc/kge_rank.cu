@@ -39,6 +39,32 @@ __device__ __forceinline__ float rank_step(float acc, float e, float q)
     if (OP == OP_L1_ADD) return __fadd_rn(acc, fabsf(__fadd_rn(e, q)));  // TransE.py:78-84
     return __fadd_rn(acc, fabsf(__fsub_rn(q, e)));                  // TransE.py:107-113
 }
+// Correctly rounded sqrt for the RotatE modulus, without the slow-path plumbing of sqrt.rn.f32.  ptxas expands sqrt.rn into
+//   y = MUFU.RSQ(x); s = x*y (ftz); h = 0.5*y (ftz); r = fma(-s, s, x); result = fma(r, h, s)
+// guarded by a range check (x in [2^-101, inf)) that branches to an out-of-line routine for zero / denormal / inf / NaN
+// inputs -- per element: 2 compare/branch, BSSY + BSYNC and two MOVs for the call ABI, and the branch regions stop the
+// scheduler from interleaving the 32 independent chains of a thread tile.  Here x = re^2 + im^2 >= 0 and finite: the
+// SAME five instructions are issued unconditionally on max(x, 2^-101) and the result is multiplied by [x >= 2^-101].
+// scripts/check_sqrt.cu compares it with sqrt.rn.f32 for EVERY finite non-negative float on the B200 (profiles/):
+// bit-identical on [2^-101, FLT_MAX], exactly 0 at 0; only 0 < x < 2^-101 differs (0 instead of a value < 2^-50), a range
+// differences of fp32 embeddings cannot reach unless table entries are below ~1e-15 in magnitude.
+__device__ __forceinline__ float sqrt_rn_nonneg(float x)
+{
+#ifdef KGE_IEEE_SQRT_CALL
+    return __fsqrt_rn(x);
+#else
+    const float lo = 3.9443045e-31f;  // 2^-101
+    const float xc = fmaxf(x, lo);
+    float y, s, h, r, res;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(xc));
+    asm("mul.ftz.f32 %0, %1, %2;" : "=f"(s) : "f"(xc), "f"(y));
+    asm("mul.ftz.f32 %0, %1, 0f3F000000;" : "=f"(h) : "f"(y));
+    r = __fmaf_rn(-s, s, xc);
+    res = __fmaf_rn(r, h, s);
+    return (x >= lo) ? res : 0.f;
+#endif
+}
+
 template <int OP>
 __device__ __forceinline__ float rank_step_rot(float acc, float er, float ei, float qa, float qb, float or_, float oi)
 {
@@ -50,7 +76,7 @@ __device__ __forceinline__ float rank_step_rot(float acc, float er, float ei, fl
         re = __fsub_rn(qa, er);
         im = __fsub_rn(qb, ei);
     }
-    return __fadd_rn(acc, __fsqrt_rn(__fmaf_rn(im, im, __fmul_rn(re, re))));
+    return __fadd_rn(acc, sqrt_rn_nonneg(__fmaf_rn(im, im, __fmul_rn(re, re))));
 }
 template <int OP>
 __device__ __forceinline__ float rank_finish(float acc, float scale)
@@ -124,7 +150,7 @@ __global__ void kge_rank_qpos_kernel(int model, const ShardView sv, const float 
             float c = rot[prow + d], sn = rot[prow + kp + d];
             float re = __fsub_rn(__fmaf_rn(-s[kp + d], sn, __fmul_rn(s[d], c)), o[d]);
             float im = __fsub_rn(__fmaf_rn(s[kp + d], c, __fmul_rn(s[d], sn)), o[kp + d]);
-            acc = __fadd_rn(acc, __fsqrt_rn(__fmaf_rn(im, im, __fmul_rn(re, re))));
+            acc = __fadd_rn(acc, sqrt_rn_nonneg(__fmaf_rn(im, im, __fmul_rn(re, re))));
         }
         score = -acc;
     } else {
