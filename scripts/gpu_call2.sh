@@ -5,7 +5,7 @@ N=$(nvidia-smi -L | wc -l)
 mkdir -p gpurun_out
 echo "== $N GPUs"
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
-  echo "== multi-GPU tests"; timeout 900 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -30 | tee gpurun_out/c2_tests_multi_n$N.log
+  echo "== multi-GPU tests"; timeout 900 python -m pytest tests/test_gpu_z_multi.py -x -q 2>&1 | tail -30 | tee gpurun_out/c2_tests_multi_n$N.log
 fi
 echo "== bench N=$N"
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \

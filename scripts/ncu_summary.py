@@ -25,6 +25,10 @@ FULL_KEYS = [
     "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "smsp__inst_executed.sum",
     "lts__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_red.sum", "sm__cycles_elapsed.max",
     "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_uniform.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "nvlrx__bytes.sum", "nvltx__bytes.sum",
 ]
 STALL_PREFIX = "smsp__average_warps_issue_stalled_"
 

@@ -530,7 +530,7 @@ def test_regulariser_pair_and_l1_l2():
 def test_exchange_kernel_world1_equals_plain_optimizer():
     """kge_optimizer_step_exchange with world = 1 (peer pointers = own pointers, in-kernel flag barriers against itself)
     is the plain dense optimizer on the concatenated [ent|rel] block, zeroes the other gradient block and does not hang;
-    the 2-GPU version of this check is tests/test_gpu_multi.py."""
+    the 2-GPU version of this check is tests/test_gpu_z_multi.py."""
     import ctypes as C
     from ampligraph_b200 import _lib
     rng = np.random.default_rng(61)

@@ -311,3 +311,18 @@ def test_filter_index_and_indexer_properties():
 
     filters()
     indexer()
+
+
+def test_bench_arms_share_config_and_honour_steps():
+    """The driver compares the two arms' `config` and `steps` (BENCH_r01: same_config / same_steps were false): the
+    reference arm must print exactly the config the GPU arm prints, and take --steps/--warmup as given."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n in (1, 2, 8):
+        assert bench.workload_config(n) == bench.workload_config(n)
+        assert bench.workload_config(n)["global_batch"] == 27212 * n
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert "min(args.steps" not in src and "min(args.warmup" not in src
+    assert set(bench.WORKLOADS) == {"cfg2", "cfg3", "cfg4", "cfg5"} and bench.WORKLOADS["cfg5"]["n_ent"] == 10_000_000
