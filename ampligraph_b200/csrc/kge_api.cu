@@ -544,7 +544,8 @@ extern "C" int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_con
 
 extern "C" int kge_optimizer_step_exchange(kge_handle *h, const kge_optimizer_config *opt_ent,
                                            const kge_optimizer_config *opt_rel, int64_t t, int32_t world, int32_t rank,
-                                           float *const *peer_tables, float *const *peer_grads, float *zero_grads_dev,
+                                           float *const *peer_tables, float *const *peer_grads, float *table_mc_dev,
+                                           const float *grads_mc_dev, float *zero_grads_dev,
                                            float *slot0_shard_dev, float *slot1_shard_dev, int64_t row_begin,
                                            int64_t row_end, uint32_t *const *peer_flags, uint32_t token, int32_t phases,
                                            double *reg_loss_dev, void *stream)
@@ -573,6 +574,10 @@ extern "C" int kge_optimizer_step_exchange(kge_handle *h, const kge_optimizer_co
     memset(&x, 0, sizeof(x));
     x.world = world; x.rank = rank; x.phases = phases;
     for (int q = 0; q < world; ++q) { x.table[q] = peer_tables[q]; x.grad[q] = peer_grads[q]; x.flags[q] = phases ? peer_flags[q] : nullptr; }
+    if ((table_mc_dev == nullptr) != (grads_mc_dev == nullptr))
+        return fail(KGE_ERR_INVALID_ARGUMENT, "kge_optimizer_step_exchange: give both multicast mappings or neither");
+    x.table_mc = table_mc_dev;
+    x.grad_mc = grads_mc_dev;
     x.token = token;
     x.zero_grad = zero_grads_dev;
     const long long ld4 = h->L.ld / 4;

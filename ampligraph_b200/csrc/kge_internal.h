@@ -76,6 +76,8 @@ struct ExchangeParams {  // kge_optimizer_step_exchange
     float *table[KGE_MAX_PEERS];        // [ent|rel] parameter block of every rank
     const float *grad[KGE_MAX_PEERS];   // this step's gradient block of every rank
     unsigned *flags[KGE_MAX_PEERS];     // flag pad of every rank: 2*world uint32
+    float *table_mc;                    // NVLS: multicast mapping of the parameter block / this step's gradient block
+    const float *grad_mc;               // (both non-null: reduce and broadcast inside the switch), else nullptr
     unsigned token;
     float *zero_grad;                   // local: next step's gradient block, zeroed here (or nullptr)
     long long total4;                   // float4s in one block

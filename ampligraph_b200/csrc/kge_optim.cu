@@ -248,9 +248,31 @@ cudaError_t launch_peer_barrier(int world, int rank, unsigned *const *flags, int
 //            kernel open until all parameters destined for this rank have landed: the next kernel
 //            on the stream may read the tables.
 // --------------------------------------------------------------------------
+// NVLS variant (MC = true): the gradient shard is reduced INSIDE the NVSwitch (multimem.ld_reduce on the multicast
+// mapping of the gradient block: one load returns the sum over all ranks) and the updated rows are broadcast by the switch
+// (multimem.st on the multicast mapping of the parameter block): per rank 1/N of a block crosses its links each way
+// instead of (N-1)/N.  The switch fixes its own summation order, so results agree with the peer-load variant to fp32
+// rounding, not bit for bit; replicas stay identical because every element still has exactly one writer.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4 *mc)
+{
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float4 *mc, float4 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 struct ExchangeArgs {
     float4 *table[KGE_MAX_PEERS];
     const float4 *grad[KGE_MAX_PEERS];
+    float4 *table_mc;        // multicast mapping of the parameter block (MC instantiation) or nullptr
+    const float4 *grad_mc;   // multicast mapping of this step's gradient block
     FlagPtrs flags;
     float4 *zero_grad;
     float4 *s0, *s1;
@@ -262,7 +284,7 @@ struct ExchangeArgs {
     int world, rank, phases;
 };
 
-template <int KIND, bool REG, int WORLD>
+template <int KIND, bool REG, int WORLD, bool MC>
 __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeArgs x, const OptimParams o)
 {
     constexpr bool S0 = KIND != KGE_OPT_SGD, S1 = KIND == KGE_OPT_ADAM;
@@ -287,13 +309,17 @@ __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeA
 
     float racc = 0.f;
     for (long long base = tid; base < x.n4; base += nthreads * U) {
-        float4 gq[U][WORLD];
+        float4 gq[U][MC ? 1 : WORLD];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long long i = base + u * nthreads;
             if (i < x.n4) {
+                if (MC) {
+                    gq[u][0] = multimem_ld_reduce_add(x.grad_mc + x.off4 + i);
+                } else {
 #pragma unroll
-                for (int q = 0; q < WORLD; ++q) gq[u][q] = __ldcg(x.grad[q] + x.off4 + i);
+                    for (int q = 0; q < (MC ? 1 : WORLD); ++q) gq[u][q] = __ldcg(x.grad[q] + x.off4 + i);
+                }
             }
         }
 #pragma unroll
@@ -303,13 +329,17 @@ __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeA
             const long long gi = x.off4 + i;
             float4 g4 = gq[u][0];
 #pragma unroll
-            for (int q = 1; q < WORLD; ++q) { g4.x += gq[u][q].x; g4.y += gq[u][q].y; g4.z += gq[u][q].z; g4.w += gq[u][q].w; }
+            for (int q = 1; q < (MC ? 1 : WORLD); ++q) { g4.x += gq[u][q].x; g4.y += gq[u][q].y; g4.z += gq[u][q].z; g4.w += gq[u][q].w; }
             float4 x4 = x.table[rank][gi], a4 = z, b4 = z;
             if (S0 || mom) a4 = x.s0[i];
             if (S1) b4 = x.s1[i];
             const float4 xn = update4<KIND, REG>(x4, g4, a4, b4, o, gi < x.ent4 ? x.reg_ent : x.reg_rel, racc);
+            if (MC) {
+                multimem_st(x.table_mc + gi, xn);
+            } else {
 #pragma unroll
-            for (int q = 0; q < WORLD; ++q) __stcg(x.table[q] + gi, xn);
+                for (int q = 0; q < WORLD; ++q) __stcg(x.table[q] + gi, xn);
+            }
             if (S0 || mom) x.s0[i] = a4;
             if (S1) x.s1[i] = b4;
         }
@@ -339,6 +369,9 @@ cudaError_t launch_optimizer_exchange(const OptimParams &o, const ExchangeParams
         a.grad[q] = q < xp.world ? (const float4 *)xp.grad[q] : nullptr;
         a.flags.pad[q] = q < xp.world ? xp.flags[q] : nullptr;
     }
+    a.table_mc = (float4 *)xp.table_mc;
+    a.grad_mc = (const float4 *)xp.grad_mc;
+    const bool mc = xp.table_mc != nullptr && xp.grad_mc != nullptr;
     a.zero_grad = (float4 *)xp.zero_grad;
     a.s0 = (float4 *)xp.slot0;
     a.s1 = (float4 *)xp.slot1;
@@ -356,8 +389,11 @@ cudaError_t launch_optimizer_exchange(const OptimParams &o, const ExchangeParams
     int grid = (int)(want < (long long)sm_count * 4 ? want : (long long)sm_count * 4);
     const bool reg = xp.reg_ent.p > 0 || xp.reg_rel.p > 0;
 #define KGE_OPTX2(K, W)                                                                   \
-    if (reg) kge_optim_exchange_kernel<K, true, W><<<grid, 256, 0, st>>>(a, o);           \
-    else kge_optim_exchange_kernel<K, false, W><<<grid, 256, 0, st>>>(a, o);
+    if (mc) {                                                                             \
+        if (reg) kge_optim_exchange_kernel<K, true, W, true><<<grid, 256, 0, st>>>(a, o); \
+        else kge_optim_exchange_kernel<K, false, W, true><<<grid, 256, 0, st>>>(a, o);    \
+    } else if (reg) kge_optim_exchange_kernel<K, true, W, false><<<grid, 256, 0, st>>>(a, o); \
+    else kge_optim_exchange_kernel<K, false, W, false><<<grid, 256, 0, st>>>(a, o);
 #define KGE_OPTX(K)                                                                       \
     switch (xp.world) {                                                                   \
     case 1: KGE_OPTX2(K, 1) break;                                                        \

@@ -60,6 +60,8 @@ class DataParallelTrainer:
     rank's row shard (slots are sharded: 1/N of the Adam state per GPU), parameter all-gather by peer stores, flag
     barrier.  Gradient blocks are double-buffered (step i scatters into block i&1 and the exchange zeroes the other
     one), so there is no memset either: 2 launches per step (train kernel + exchange) at any N.
+    "nvls" (opt-in, KGE_B200_DP_MODE=nvls): the same kernel, but the gradient shard is reduced inside the NVSwitch
+    (multimem.ld_reduce on the multicast mapping) and the new rows are broadcast by it (multimem.st).
     Fallback ("nccl"): SUM all-reduce of the gradient tables + the full optimizer on every replica.
     Both equal the single-GPU step on the concatenated batch up to fp32 summation order, because
     the loss is a SUM over the batch (loss_functions.py:214).
@@ -75,16 +77,23 @@ class DataParallelTrainer:
         self.mode = "single" if self.world == 1 else mode
         self.hdl = None
         self._k = 0  # exchanges done (gradient block parity, barrier token)
-        if self.mode in ("auto", "p2p"):
+        self._mc = None
+        if self.mode in ("auto", "p2p", "nvls"):
             try:
                 self.eng = make_engine(self._symmetric_alloc)
                 reject_lazy("lazy_" if self.eng.lazy else "", self.world)
                 self._finish_p2p_setup()
-                self.mode = "p2p"
+                if mode == "nvls":
+                    mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+                    if not mc:
+                        raise RuntimeError("symmetric memory has no multicast mapping on this system (NVLS unavailable)")
+                    ld = self.eng.ld
+                    self._mc = {k: mc + self._row_off[k] * ld * 4 for k in ("table", "g0", "g1")}
+                self.mode = "nvls" if mode == "nvls" else "p2p"
             except NotImplementedError:
                 raise
             except Exception as e:  # no symmetric memory / no peer access: NCCL path
-                if mode == "p2p":
+                if mode in ("p2p", "nvls"):
                     raise
                 self.p2p_error = repr(e)
                 self.mode = "nccl"
@@ -138,7 +147,7 @@ class DataParallelTrainer:
     # ---- one global step ------------------------------------------------------------
     def train_step(self, batch, negatives=None, seed=0, step=0, kernel_done=None):
         eng = self.eng
-        if self.mode == "p2p":
+        if self.mode in ("p2p", "nvls"):
             blk = self._k & 1
             eng.g_ent, eng.g_rel = self._gviews[blk]
         eng.forward_backward(batch, negatives, seed=seed, step=step)
@@ -158,7 +167,9 @@ class DataParallelTrainer:
             p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
             _lib.check(eng.lib.kge_optimizer_step_exchange(
                 eng.h, C.byref(eng.opt_cfgs["ent"]), C.byref(eng.opt_cfgs["rel"]), eng.t, self.world, self.rank,
-                self._ptrs["table"], self._ptrs["g%d" % blk], C.c_void_p(self._local_g[blk ^ 1]), p(s0), p(s1), lo, hi,
+                self._ptrs["table"], self._ptrs["g%d" % blk],
+                C.c_void_p(self._mc["table"] if self._mc else 0), C.c_void_p(self._mc["g%d" % blk] if self._mc else 0),
+                C.c_void_p(self._local_g[blk ^ 1]), p(s0), p(s1), lo, hi,
                 self._ptrs["flags"], self._k, 3, C.c_void_p(eng.loss_acc.data_ptr() + 8), eng._stream()))
             eng.launches += 1
 

@@ -279,6 +279,11 @@ int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_config *opt, i
  *                   nobody ever memsets a gradient table.  NULL: skip.
  *   slot*_shard_dev optimizer slots of rows [row_begin, row_end) of the concatenated block only
  *   opt_ent/opt_rel the two tables may carry different regularisers (EmbeddingLookupLayer.py:131-155)
+ *   table_mc_dev / grads_mc_dev  NULL, or the NVLS MULTICAST mappings of the parameter block and of this step's gradient
+ *                   block (torch symmetric memory: multicast_ptr): the gradient shard is then reduced inside the NVSwitch
+ *                   (multimem.ld_reduce) and the updated rows are broadcast by it (multimem.st) -- 1/N of a block per
+ *                   rank per direction over the links instead of (N-1)/N; peer_tables/peer_grads are still required
+ *                   (local reads, fallback)
  *   peer_flags[q]   base of rank q's flag pad: 2*world uint32, zero-initialised once, peer-mapped like the tables
  *   token           strictly increasing per call (e.g. the step count t): flags are never reset
  *   phases          bit 0: wait until every rank entered this call (= finished its kge_train_step) before reading
@@ -287,7 +292,8 @@ int kge_optimizer_step_sharded(kge_handle *h, const kge_optimizer_config *opt, i
  * Stream order on each rank must be: kge_train_step(step i) -> this call.  No other synchronisation is needed. */
 int kge_optimizer_step_exchange(kge_handle *h, const kge_optimizer_config *opt_ent,
                                 const kge_optimizer_config *opt_rel, int64_t t, int32_t world, int32_t rank,
-                                float *const *peer_tables, float *const *peer_grads, float *zero_grads_dev,
+                                float *const *peer_tables, float *const *peer_grads, float *table_mc_dev,
+                                const float *grads_mc_dev, float *zero_grads_dev,
                                 float *slot0_shard_dev, float *slot1_shard_dev, int64_t row_begin,
                                 int64_t row_end, uint32_t *const *peer_flags, uint32_t token, int32_t phases,
                                 double *reg_loss_dev, void *stream);

@@ -558,7 +558,7 @@ def test_exchange_kernel_world1_equals_plain_optimizer():
         eng.t += 1
         _lib.check(eng.lib.kge_optimizer_step_exchange(
             eng.h, C.byref(eng.opt_cfgs["ent"]), C.byref(eng.opt_cfgs["rel"]), eng.t, 1, 0, one(buf.data_ptr()),
-            one(gv[b][0].data_ptr()), C.c_void_p(gv[b ^ 1][0].data_ptr()), C.c_void_p(s0.data_ptr()), C.c_void_p(s1.data_ptr()),
+            one(gv[b][0].data_ptr()), None, None, C.c_void_p(gv[b ^ 1][0].data_ptr()), C.c_void_p(s0.data_ptr()), C.c_void_p(s1.data_ptr()),
             0, blk, one(buf[3 * blk:].data_ptr()), step + 1, 3, C.c_void_p(eng.loss_acc.data_ptr() + 8), eng._stream()))
         ref.train_step(_dev(t), (_dev(ne), _dev(nk)))
         torch.cuda.synchronize()

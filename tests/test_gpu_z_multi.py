@@ -31,7 +31,12 @@ dev = lambda a: torch.as_tensor(a).cuda().contiguous()
 regs = [{"p": 2, "lambda": 1e-3}, {"p": 3, "lambda": 2e-3}]   # a different regulariser per table: the exchange kernel switches at the ent|rel boundary
 mk = lambda alloc: KGEEngine(model, k, eta, E, R, loss="self_adversarial", optimizer="adam",
                              optimizer_params={"learning_rate": 1e-2}, regularizer=regs, device=local, table_alloc=alloc)
-dp = DataParallelTrainer(mk, mode=mode)
+try:
+    dp = DataParallelTrainer(mk, mode=mode)
+except RuntimeError as e:
+    if mode == "nvls" and "multicast" in str(e):   # no NVLS on this box: nothing to test
+        print("rank", int(os.environ["RANK"]), mode, "ok (skipped: %s)" % e); dist.destroy_process_group(); raise SystemExit(0)
+    raise
 assert dp.mode == mode, (dp.mode, getattr(dp, "p2p_error", None))
 dp.eng.set_embeddings(ent, rel)
 for i in range(steps):
@@ -77,7 +82,7 @@ print("rank", rank, mode, "ok")
 '''
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "nvls"])
 def test_data_parallel_step_two_gpus(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
