@@ -134,7 +134,7 @@ cudaError_t launch_rank_accumulate(const int32_t *cnt, long long b, int32_t *cou
 struct RankTcLayout {  // carve-up of the tensor-core part of the caller's workspace
     int nkb, ksteps, n_qb, n_ct;
     unsigned pair_cap;
-    size_t off_a, off_b, off_thr, off_qnorm, off_tnorm, off_count, off_pairs, bytes;
+    size_t off_a, off_b, off_thr, off_tnorm, off_count, off_pairs, bytes;
 };
 bool rank_tc_applicable(const Layout &L, int side, long long b, long long n_cand);
 RankTcLayout rank_tc_layout(const Layout &L, long long b, long long n_cand, int pair_cap_override);

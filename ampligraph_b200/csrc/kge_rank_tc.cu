@@ -55,76 +55,65 @@ constexpr int TC_TMEM_COLS = 512;                  // two accumulator stages of 
 //    8-row group -> the canonical K-major SWIZZLE_NONE layout with LBO = 128 B (next k-chunk), SBO = 1024 B (next
 //    8-row group), so a whole tile is ONE contiguous bulk copy and needs no tensor map.
 // ---------------------------------------------------------------------------------------------------------------------
+// One WARP per row: lanes stride over the row's 8-column chunks (coalesced 32-byte reads), write the hi / lo core-matrix
+// rows (16 bytes each) and accumulate the row's sum of squares on the way, so the norms the error bound needs cost no
+// second pass.  Candidates (RB = 256): max |row| of each tile via atomicMax (positive floats order like their bit
+// patterns).  Queries (RB = 128): the warp's lane 0 also writes the query's bin edges {U, L} in SCORE units (unscaled
+// accumulator for HolE) and its error-bound factors.  qc >= n  <=>  trunc(x) >= n with x = fl(score*1000): x >= n for
+// n >= 1, x > n-1 for n <= 0.
 template <int RB>
 __global__ void __launch_bounds__(256) kge_rank_split_kernel(const float *__restrict__ src, const int32_t *__restrict__ ids,
                                                              long long row_begin, long long n_rows, long long rows_pad,
-                                                             int ld, int nkb, __nv_bfloat16 *__restrict__ out)
-{
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int chunks = nkb * 8;
-    if (idx >= rows_pad * chunks) return;
-    const long long r = idx / chunks;
-    const int c = (int)(idx - r * chunks), kb = c >> 3, kc = c & 7, col0 = c * 8;
-    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (r < n_rows) {
-        const float *row = src + (size_t)(ids ? (long long)ids[r] : row_begin + r) * ld;
-        if (col0 + 4 <= ld) { const float4 v = *reinterpret_cast<const float4 *>(row + col0); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
-        if (col0 + 8 <= ld) { const float4 v = *reinterpret_cast<const float4 *>(row + col0 + 4); x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w; }
-    }
-    __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        hi[e] = __float2bfloat16_rn(x[e]);
-        lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e]));  // x - hi is exact in fp32
-    }
-    const long long rb = r / RB;
-    const int rl = (int)(r - rb * RB);
-    const size_t tile = ((size_t)rb * nkb + kb) * (size_t)(2 * RB * TC_KB);
-    const size_t off = (size_t)(((rl >> 3) * 8 + kc) * 8 + (rl & 7)) * 8;
-    *reinterpret_cast<uint4 *>(out + tile + off) = *reinterpret_cast<const uint4 *>(hi);
-    *reinterpret_cast<uint4 *>(out + tile + (size_t)RB * TC_KB + off) = *reinterpret_cast<const uint4 *>(lo);
-}
-
-// |row|_2 (rounded up): per-row for the queries, max over each 256-row block for the candidates (positive floats order
-// like their bit patterns, so atomicMax on the uint view is a float max)
-__global__ void __launch_bounds__(256) kge_rank_norm_kernel(const float *__restrict__ src, const int32_t *__restrict__ ids,
-                                                            long long row_begin, long long n_rows, int ld,
-                                                            float *__restrict__ row_norm, unsigned *__restrict__ block_max)
+                                                             int ld, int nkb, __nv_bfloat16 *__restrict__ out,
+                                                             unsigned *__restrict__ tile_max, const int32_t *__restrict__ qpos,
+                                                             float scale, float eps_rel, float4 *__restrict__ thr)
 {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long r = warp0; r < n_rows; r += n_warps) {
-        const float *row = src + (size_t)(ids ? (long long)ids[r] : row_begin + r) * ld;
-        float acc = 0.f;
-        for (int c = lane * 4; c < ld; c += 128) {
-            const float4 v = *reinterpret_cast<const float4 *>(row + c);
-            acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    const int chunks = nkb * 8;
+    for (long long r = warp0; r < rows_pad; r += n_warps) {
+        const bool live = r < n_rows;
+        const float *row = live ? src + (size_t)(ids ? (long long)ids[r] : row_begin + r) * ld : nullptr;
+        const long long rb = r / RB;
+        const int rl = (int)(r - rb * RB);
+        float ss = 0.f;
+        for (int c = lane; c < chunks; c += 32) {
+            const int kb = c >> 3, kc = c & 7, col0 = c * 8;
+            float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (live) {
+                if (col0 + 4 <= ld) { const float4 v = *reinterpret_cast<const float4 *>(row + col0); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+                if (col0 + 8 <= ld) { const float4 v = *reinterpret_cast<const float4 *>(row + col0 + 4); x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w; }
+            }
+            __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                hi[e] = __float2bfloat16_rn(x[e]);
+                lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e]));  // x - hi is exact in fp32
+                ss = fmaf(x[e], x[e], ss);
+            }
+            const size_t tile = ((size_t)rb * nkb + kb) * (size_t)(2 * RB * TC_KB);
+            const size_t off = (size_t)(((rl >> 3) * 8 + kc) * 8 + (rl & 7)) * 8;
+            *reinterpret_cast<uint4 *>(out + tile + off) = *reinterpret_cast<const uint4 *>(hi);
+            *reinterpret_cast<uint4 *>(out + tile + (size_t)RB * TC_KB + off) = *reinterpret_cast<const uint4 *>(lo);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const float n = __fmul_ru(__fsqrt_ru(acc), 1.00001f);
-            if (row_norm) row_norm[r] = n;
-            if (block_max) atomicMax(block_max + r / TC_NC, __float_as_uint(n));
+        ss = warp_sum(ss);
+        if (lane != 0) continue;
+        const float norm = __fmul_ru(__fsqrt_ru(ss), 1.00001f);  // rounded up: the sum's own rounding error is << 1e-5
+        if (tile_max) {
+            if (live) atomicMax(tile_max + rb, __float_as_uint(norm));
+        } else if (!live) {
+            thr[r] = make_float4(INFINITY, INFINITY, 0.f, 0.f);  // padding queries never count, never push
+        } else {
+            const int n = qpos[r];
+            const double edge_hi = (n + 1 >= 1) ? (double)(n + 1) : (double)n;  // T(n+1)
+            const double edge_lo = (n >= 1) ? (double)n : (double)n - 1.0;      // T(n)
+            const float U = (float)(edge_hi / 1000.0 / (double)scale), L = (float)(edge_lo / 1000.0 / (double)scale);
+            // slack: rounding of U, L themselves, of fl(scale*acc) and of fl(score*1000), each <= 2^-24 relative (64x margin)
+            const float slack = fmaxf(fabsf(U), fabsf(L)) * 3.814697265625e-6f + 1e-37f;
+            thr[r] = make_float4(U, L, __fmul_ru(eps_rel, norm), slack);
         }
     }
-}
-
-// per-query bin edges in SCORE units (unscaled accumulator for HolE) + error-bound factors.
-// qc >= n  <=>  trunc(x) >= n with x = fl(score*1000): x >= n for n >= 1, x > n-1 for n <= 0.
-__global__ void kge_rank_thresholds_kernel(const int32_t *__restrict__ qpos, const float *__restrict__ qnorm, long long b,
-                                           long long b_pad, float scale, float eps_rel, float4 *__restrict__ thr)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b_pad) return;
-    if (i >= b) { thr[i] = make_float4(INFINITY, INFINITY, 0.f, 0.f); return; }  // padding lanes never count, never push
-    const int n = qpos[i];
-    const double edge_hi = (n + 1 >= 1) ? (double)(n + 1) : (double)n;        // T(n+1)
-    const double edge_lo = (n >= 1) ? (double)n : (double)n - 1.0;            // T(n)
-    const float U = (float)(edge_hi / 1000.0 / (double)scale), L = (float)(edge_lo / 1000.0 / (double)scale);
-    // slack: rounding of U, L themselves, of fl(scale*acc) and of fl(score*1000), each <= 2^-24 relative (64x margin)
-    const float slack = fmaxf(fabsf(U), fabsf(L)) * 3.814697265625e-6f + 1e-37f;
-    thr[i] = make_float4(U, L, __fmul_ru(eps_rel, qnorm[i]), slack);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -345,7 +334,13 @@ __global__ void __launch_bounds__(128) kge_rank_refine_kernel(const RankParams p
                                                               int32_t *__restrict__ cnt)
 {
     const unsigned n = *pair_count;
-    if (n > pair_cap) return;  // overflow: the gated exact kernel redoes everything
+    if (n > pair_cap) {  // overflow: forget what the filter counted; the gated exact kernel (next launch) recounts everything
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.b; i += (long long)gridDim.x * blockDim.x) {
+            cnt[3 * i] = 0;
+            cnt[3 * i + 1] = 0;
+        }
+        return;
+    }
     for (unsigned f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
         const int2 pr = pairs[f];
         const long long pos = pr.y;
@@ -359,15 +354,6 @@ __global__ void __launch_bounds__(128) kge_rank_refine_kernel(const RankParams p
         if (qp < qc) atomicAdd(cnt + 3 * pr.x + 0, 1);
         else if (qp == qc) atomicAdd(cnt + 3 * pr.x + 1, 1);
     }
-}
-
-// overflow only: forget what the filter counted; the gated exact kernel recounts
-__global__ void kge_rank_tc_reset_kernel(const unsigned *__restrict__ pair_count, unsigned pair_cap, int32_t *__restrict__ cnt,
-                                         long long b)
-{
-    if (*pair_count <= pair_cap) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < b) { cnt[3 * i] = 0; cnt[3 * i + 1] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -399,9 +385,8 @@ RankTcLayout rank_tc_layout(const Layout &L, long long b, long long n_cand, int 
     w.off_a = off; off += tc_align((size_t)w.n_qb * w.nkb * TC_A_BYTES);
     w.off_b = off; off += tc_align((size_t)w.n_ct * w.nkb * TC_B_BYTES);
     w.off_thr = off; off += tc_align((size_t)w.n_qb * TC_MQ * sizeof(float4));
-    w.off_qnorm = off; off += tc_align((size_t)b * sizeof(float));
+    w.off_count = off; off += 1024;                                       // pair counter, then the tile norms: one memset
     w.off_tnorm = off; off += tc_align((size_t)w.n_ct * sizeof(float));
-    w.off_count = off; off += 1024;
     w.off_pairs = off; off += tc_align((size_t)w.pair_cap * sizeof(int2));
     w.bytes = off;
     return w;
@@ -413,29 +398,23 @@ cudaError_t launch_rank_count_tc(const RankParams &p, const RankTcLayout &w, voi
     char *base = (char *)ws;
     __nv_bfloat16 *a_split = (__nv_bfloat16 *)(base + w.off_a), *b_split = (__nv_bfloat16 *)(base + w.off_b);
     float4 *thr = (float4 *)(base + w.off_thr);
-    float *qnorm = (float *)(base + w.off_qnorm), *tnorm = (float *)(base + w.off_tnorm);
+    float *tnorm = (float *)(base + w.off_tnorm);
     unsigned *count = (unsigned *)(base + w.off_count);
     int2 *pairs = (int2 *)(base + w.off_pairs);
     const int ld = p.L.ld;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(tnorm, 0, (size_t)w.n_ct * sizeof(float), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(count, 0, 16, st)) != cudaSuccess) return e;
-    // split + norms: candidates (256-row tiles) and this side's query vectors (128-row tiles)
+    if ((e = cudaMemsetAsync(count, 0, 1024 + (size_t)w.n_ct * sizeof(float), st)) != cudaSuccess) return e;
+    // split (+ norms, + per-query thresholds): candidates in 256-row tiles, this side's query vectors in 128-row tiles
+    const float eps_rel = (float)(ldexp(1.0, -14) + 4.0 * (double)ld * ldexp(1.0, -23));
     {
-        const long long rows_pad = (long long)w.n_ct * TC_NC, n = rows_pad * w.nkb * 8;
-        kge_rank_split_kernel<TC_NC><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ent, p.cand_ids, p.cand_begin, p.n_cand, rows_pad, ld,
-                                                                                  w.nkb, b_split);
-        long long want = (p.n_cand + 7) / 8;
-        kge_rank_norm_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, st>>>(p.ent, p.cand_ids, p.cand_begin, p.n_cand, ld,
-                                                                                            nullptr, (unsigned *)tnorm);
+        const long long rows_pad = (long long)w.n_ct * TC_NC, want = (rows_pad + 7) / 8;
+        kge_rank_split_kernel<TC_NC><<<(unsigned)(want < (long long)sm_count * 32 ? want : (long long)sm_count * 32), 256, 0, st>>>(
+            p.ent, p.cand_ids, p.cand_begin, p.n_cand, rows_pad, ld, w.nkb, b_split, (unsigned *)tnorm, nullptr, 1.f, 0.f, nullptr);
     }
     {
-        const long long rows_pad = (long long)w.n_qb * TC_MQ, n = rows_pad * w.nkb * 8;
-        kge_rank_split_kernel<TC_MQ><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.qvec, nullptr, 0, p.b, rows_pad, ld, w.nkb, a_split);
-        long long want = (p.b + 7) / 8;
-        kge_rank_norm_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, st>>>(p.qvec, nullptr, 0, p.b, ld, qnorm, nullptr);
-        const float eps_rel = (float)(ldexp(1.0, -14) + 4.0 * (double)ld * ldexp(1.0, -23));
-        kge_rank_thresholds_kernel<<<(unsigned)((rows_pad + 127) / 128), 128, 0, st>>>(p.qpos, qnorm, p.b, rows_pad, p.scale, eps_rel, thr);
+        const long long rows_pad = (long long)w.n_qb * TC_MQ, want = (rows_pad + 7) / 8;
+        kge_rank_split_kernel<TC_MQ><<<(unsigned)(want < (long long)sm_count * 32 ? want : (long long)sm_count * 32), 256, 0, st>>>(
+            p.qvec, nullptr, 0, p.b, rows_pad, ld, w.nkb, a_split, nullptr, p.qpos, p.scale, eps_rel, thr);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     TcParams t;
@@ -456,7 +435,6 @@ cudaError_t launch_rank_count_tc(const RankParams &p, const RankTcLayout &w, voi
     if ((e = cudaFuncSetAttribute(kge_rank_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     kge_rank_tc_kernel<false><<<(unsigned)(w.n_qb * per), TC_THREADS, smem, st>>>(t);
     kge_rank_refine_kernel<<<sm_count * 4, 128, 0, st>>>(p, pairs, count, w.pair_cap, cnt);
-    kge_rank_tc_reset_kernel<<<(unsigned)((p.b + 255) / 256), 256, 0, st>>>(count, w.pair_cap, cnt, p.b);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // overflow fallback: the exact FP32 kernel, every CTA of which returns at once unless the pair list overflowed
     RankParams g = p;

@@ -39,7 +39,7 @@ cap train_cfg5w kge_train_kernel 2 1 python scripts/kbench.py one cfg5w 0
 cap optim_lazy kge_optim_lazy_kernel 2 1 python -m pytest tests/test_gpu_parity.py -q -k "lazy_optimizer_matches_restatement and lazy_adam"
 cap optim_exchange kge_optim_exchange_kernel 1 1 python -m pytest tests/test_gpu_parity.py -q -k exchange_kernel_world1
 # ranking kernels: tensor-core filter + its helpers (ComplEx, auto mode), FFMA2 dot kernel (exact mode), generic tile kernel (TransE, RotatE)
-cap rank_tc 'kge_rank_tc_kernel|kge_rank_split_kernel|kge_rank_refine_kernel|kge_rank_norm_kernel' 0 8 python scripts/rbench.py one ComplEx 200 14505 1024
+cap rank_tc 'kge_rank_tc_kernel|kge_rank_split_kernel|kge_rank_refine_kernel' 0 8 python scripts/rbench.py one ComplEx 200 14505 1024
 KGE_B200_RANK_MODE=exact cap rank_dot 'kge_rank_dot_kernel|kge_rank_q|kge_rank_finalize' 0 4 python scripts/rbench.py one ComplEx 200 14505 1024
 cap rank_transe kge_rank_tile_kernel 0 1 python scripts/rbench.py one TransE 400 14505 1024
 cap rank_rotate kge_rank_tile_kernel 0 1 python scripts/rbench.py one RotatE 200 14505 1024
