@@ -76,7 +76,11 @@ __device__ __forceinline__ float rank_step_rot(float acc, float er, float ei, fl
         re = __fsub_rn(qa, er);
         im = __fsub_rn(qb, ei);
     }
-    return __fadd_rn(acc, sqrt_rn_nonneg(__fmaf_rn(im, im, __fmul_rn(re, re))));
+    // the inlined sqrt lets ptxas interleave all 32 chains of a thread tile: a win for the short object-side body (2.8 -> 2.46 ms,
+    // cfg2 table x 1,024 queries), a register blow-up for the longer subject-side one (128 -> 218 registers, 3.3 -> 4.7 ms), which
+    // therefore keeps the out-of-line sqrt.rn; the two are bit-identical (scripts/check_sqrt.cu)
+    const float x = __fmaf_rn(im, im, __fmul_rn(re, re));
+    return __fadd_rn(acc, OP == OP_ROT_S ? __fsqrt_rn(x) : sqrt_rn_nonneg(x));
 }
 template <int OP>
 __device__ __forceinline__ float rank_finish(float acc, float scale)

@@ -265,7 +265,9 @@ class KGEEngine:
         Growing frees the old buffer through torch's stream-ordered caching allocator, so no synchronisation is needed."""
         need = int(self.lib.kge_rank_workspace_bytes(self.h, int(b), int(n_cand)))
         if self._rank_ws is None or self._rank_ws.numel() < need:
-            self._rank_ws = torch.empty(max(need, 1024), dtype=torch.uint8, device=self.device)
+            raw = torch.empty(max(need, 1024) + 1024, dtype=torch.uint8, device=self.device)
+            off = (-raw.data_ptr()) % 1024  # the library wants a 1024-byte aligned base (operand tiles of the tensor-core pass)
+            self._rank_ws_raw, self._rank_ws = raw, raw[off:off + max(need, 1024)]
         return self._rank_ws, need
 
     @_traced("kge.rank")
