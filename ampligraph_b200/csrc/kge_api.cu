@@ -132,7 +132,7 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     h->wk = L.kp <= 512 ? L.kp : 512;
     h->n_cb = (L.kp + h->wk - 1) / h->wk;
     h->eta_pad = (cfg->eta + 3) / 4 * 4;
-    const int row_bytes = L.halves * h->wk * 4, aux = 3 * h->eta_pad * 4 + 16;
+    const int row_bytes = L.halves * h->wk * 4, aux = 4 * h->eta_pad * 4 + 16;  // sc | nid | nside | jorig, two mbarriers
     h->slot_floats = row_bytes / 4;
     const int max_warps = KGE_TRAIN_THREADS(cfg->scoring, h->nit) / 32;
     // Residency policy, tuned on B200 (scripts/kbench.py sweep, profiles/): keep all eta corruptions resident

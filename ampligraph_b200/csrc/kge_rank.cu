@@ -18,76 +18,9 @@
 // are exact no-ops in every chain (fma(0,0,a)=a, a+|0|=a, a+sqrt(0)=a).
 #include <math.h>
 
-#include "kge_internal.h"
+#include "kge_rank_common.cuh"
 
 namespace kge {
-
-enum { OP_DOT = 0, OP_L1_ADD = 1, OP_L1_SUB = 2, OP_ROT_S = 3, OP_ROT_O = 4 };
-
-__host__ __device__ inline int rank_op(int model, int side)
-{
-    if (model == KGE_TRANSE) return side == KGE_SIDE_S ? OP_L1_ADD : OP_L1_SUB;
-    if (model == KGE_ROTATE) return side == KGE_SIDE_S ? OP_ROT_S : OP_ROT_O;
-    return OP_DOT;
-}
-
-// one canonical accumulation step (shared by the tile kernel and the filter kernel)
-template <int OP>
-__device__ __forceinline__ float rank_step(float acc, float e, float q)
-{
-    if (OP == OP_DOT) return __fmaf_rn(e, q, acc);                  // DistMult.py:71 / ComplEx.py:95
-    if (OP == OP_L1_ADD) return __fadd_rn(acc, fabsf(__fadd_rn(e, q)));  // TransE.py:78-84
-    return __fadd_rn(acc, fabsf(__fsub_rn(q, e)));                  // TransE.py:107-113
-}
-// Correctly rounded sqrt for the RotatE modulus, without the slow-path plumbing of sqrt.rn.f32.  ptxas expands sqrt.rn into
-//   y = MUFU.RSQ(x); s = x*y (ftz); h = 0.5*y (ftz); r = fma(-s, s, x); result = fma(r, h, s)
-// guarded by a range check (x in [2^-101, inf)) that branches to an out-of-line routine for zero / denormal / inf / NaN
-// inputs -- per element: 2 compare/branch, BSSY + BSYNC and two MOVs for the call ABI, and the branch regions stop the
-// scheduler from interleaving the 32 independent chains of a thread tile.  Here x = re^2 + im^2 >= 0 and finite: the
-// SAME five instructions are issued unconditionally on max(x, 2^-101) and the result is multiplied by [x >= 2^-101].
-// scripts/check_sqrt.cu compares it with sqrt.rn.f32 for EVERY finite non-negative float on the B200 (profiles/):
-// bit-identical on [2^-101, FLT_MAX], exactly 0 at 0; only 0 < x < 2^-101 differs (0 instead of a value < 2^-50), a range
-// differences of fp32 embeddings cannot reach unless table entries are below ~1e-15 in magnitude.
-__device__ __forceinline__ float sqrt_rn_nonneg(float x)
-{
-#ifdef KGE_IEEE_SQRT_CALL
-    return __fsqrt_rn(x);
-#else
-    const float lo = 3.9443045e-31f;  // 2^-101
-    const float xc = fmaxf(x, lo);
-    float y, s, h, r, res;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(xc));
-    asm("mul.ftz.f32 %0, %1, %2;" : "=f"(s) : "f"(xc), "f"(y));
-    asm("mul.ftz.f32 %0, %1, 0f3F000000;" : "=f"(h) : "f"(y));
-    r = __fmaf_rn(-s, s, xc);
-    res = __fmaf_rn(r, h, s);
-    return (x >= lo) ? res : 0.f;
-#endif
-}
-
-template <int OP>
-__device__ __forceinline__ float rank_step_rot(float acc, float er, float ei, float qa, float qb, float or_, float oi)
-{
-    float re, im;
-    if (OP == OP_ROT_S) {  // RotatE.py:151-163: qa=cos, qb=sin
-        re = __fsub_rn(__fmaf_rn(-ei, qb, __fmul_rn(er, qa)), or_);
-        im = __fsub_rn(__fmaf_rn(ei, qa, __fmul_rn(er, qb)), oi);
-    } else {  // RotatE.py:208-216: (qa,qb) = rotated subject
-        re = __fsub_rn(qa, er);
-        im = __fsub_rn(qb, ei);
-    }
-    // the inlined sqrt lets ptxas interleave all 32 chains of a thread tile: a win for the short object-side body (2.8 -> 2.46 ms,
-    // cfg2 table x 1,024 queries), a register blow-up for the longer subject-side one (128 -> 218 registers, 3.3 -> 4.7 ms), which
-    // therefore keeps the out-of-line sqrt.rn; the two are bit-identical (scripts/check_sqrt.cu)
-    const float x = __fmaf_rn(im, im, __fmul_rn(re, re));
-    return __fadd_rn(acc, OP == OP_ROT_S ? __fsqrt_rn(x) : sqrt_rn_nonneg(x));
-}
-template <int OP>
-__device__ __forceinline__ float rank_finish(float acc, float scale)
-{
-    if (OP == OP_DOT) return (scale == 1.f) ? acc : __fmul_rn(scale, acc);  // HolE.py:67-69
-    return -acc;
-}
 
 // --------------------------------------------------------------------------
 // prepare: per-query vectors for both sides + quantised positive score
@@ -132,38 +65,26 @@ __global__ void kge_rank_qvec_kernel(int model, const ShardView sv, const float 
     }
 }
 
-// positive score, canonical order (one thread per query; b is small)
-__global__ void kge_rank_qpos_kernel(int model, const ShardView sv, const float *__restrict__ ent, const float *__restrict__ rel,
-                                     const float *__restrict__ rot, const int32_t *__restrict__ triples, long long b,
-                                     int kp, int ld, float scale, int32_t *__restrict__ qpos)
+// Positive score.  Its canonical chain (oracle: kgeo_score_triple) is, operation for operation, the corruption-score chain
+// of the triple's OWN entity on one side: TransE |(s+p) - o| and RotatE |R(s) - o| are the object-side chains with
+// candidate o (query vector s+p / R(s)); DistMult fma(s*p, o, acc) is the object-side chain with candidate o (query
+// vector s*p); ComplEx / HolE fma(s_re, p_re o_re + p_im o_im, acc), fma(s_im, ...) is the subject-side chain with candidate s.
+// So the positive is scored by the same warp-cooperative pair scorer as the filter entries, from the query vectors
+// kge_rank_qvec_kernel has just written.
+template <int OP>
+__global__ void kge_rank_qpos_kernel(const ShardView sv, const float *__restrict__ ent, const int32_t *__restrict__ triples,
+                                     long long b, int col, const float *__restrict__ qvec, const float *__restrict__ qaux, int kp,
+                                     int ld, float scale, int32_t *__restrict__ qpos)
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b) return;
-    const float *s = shard_row(sv, ent, triples[3 * i], ld);
-    const float *o = shard_row(sv, ent, triples[3 * i + 2], ld);
-    const size_t prow = (size_t)triples[3 * i + 1] * ld;
-    float acc = 0.f, score;
-    if (model == KGE_TRANSE) {
-        for (int d = 0; d < kp; ++d) acc = __fadd_rn(acc, fabsf(__fsub_rn(__fadd_rn(s[d], rel[prow + d]), o[d])));
-        score = -acc;
-    } else if (model == KGE_DISTMULT) {
-        for (int d = 0; d < kp; ++d) acc = __fmaf_rn(__fmul_rn(s[d], rel[prow + d]), o[d], acc);
-        score = acc;
-    } else if (model == KGE_ROTATE) {
-        for (int d = 0; d < kp; ++d) {
-            float c = rot[prow + d], sn = rot[prow + kp + d];
-            float re = __fsub_rn(__fmaf_rn(-s[kp + d], sn, __fmul_rn(s[d], c)), o[d]);
-            float im = __fsub_rn(__fmaf_rn(s[kp + d], c, __fmul_rn(s[d], sn)), o[kp + d]);
-            acc = __fadd_rn(acc, sqrt_rn_nonneg(__fmaf_rn(im, im, __fmul_rn(re, re))));
-        }
-        score = -acc;
-    } else {
-        const float *p = rel + prow;
-        for (int d = 0; d < kp; ++d) acc = __fmaf_rn(s[d], __fmaf_rn(p[kp + d], o[kp + d], __fmul_rn(p[d], o[d])), acc);
-        for (int d = 0; d < kp; ++d) acc = __fmaf_rn(s[kp + d], __fmaf_rn(-p[kp + d], o[d], __fmul_rn(p[d], o[kp + d])), acc);
-        score = (model == KGE_HOLE) ? __fmul_rn(scale, acc) : acc;
+    extern __shared__ __align__(16) float pair_sm[];
+    constexpr int ROWS = OP == OP_ROT_S ? 3 : 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    float *sm = pair_sm + (size_t)warp * ROWS * ld;
+    for (long long i = (long long)blockIdx.x * wpc + warp; i < b; i += (long long)gridDim.x * wpc) {
+        const float *e = shard_row(sv, ent, triples[3 * i + col], ld);
+        const float sc = pair_score_warp<OP>(e, qvec + (size_t)i * ld, qaux ? qaux + (size_t)i * ld : nullptr, ld, kp, scale, sm, lane);
+        if (lane == 0) qpos[i] = quantise(sc);
     }
-    qpos[i] = quantise(score);
 }
 
 cudaError_t launch_rank_prepare(const Layout &L, const ShardView &sv, const float *ent, const float *rel, const float *rot,
@@ -174,8 +95,22 @@ cudaError_t launch_rank_prepare(const Layout &L, const ShardView &sv, const floa
     long long n = b * L.kp;
     kge_rank_qvec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.model, sv, ent, rel, rot, triples, b, L.kp, L.ld,
                                                                        qvec_s, qvec_o, qaux);
-    kge_rank_qpos_kernel<<<(unsigned)((b + 127) / 128), 128, 0, st>>>(L.model, sv, ent, rel, rot, triples, b, L.kp, L.ld,
-                                                                      scale, qpos);
+    const int wpc = pair_score_warps(L.ld, 2);
+    const size_t sm = (size_t)wpc * 2 * L.ld * sizeof(float);
+    const unsigned grid = (unsigned)((b + wpc - 1) / wpc);
+#define KGE_QPOS(OP, COL, QV)                                                                                        \
+    {                                                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(kge_rank_qpos_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        if (e != cudaSuccess) return e;                                                                              \
+        kge_rank_qpos_kernel<OP><<<grid, wpc * 32, sm, st>>>(sv, ent, triples, b, COL, QV, nullptr, L.kp, L.ld, scale, qpos); \
+    }
+    switch (L.model) {
+    case KGE_TRANSE: KGE_QPOS(OP_L1_SUB, 2, qvec_o) break;
+    case KGE_ROTATE: KGE_QPOS(OP_ROT_O, 2, qvec_o) break;
+    case KGE_DISTMULT: KGE_QPOS(OP_DOT, 2, qvec_o) break;
+    default: KGE_QPOS(OP_DOT, 0, qvec_s) break;  // ComplEx, HolE
+    }
+#undef KGE_QPOS
     return cudaGetLastError();
 }
 
@@ -520,46 +455,51 @@ template <int OP>
 __global__ void kge_rank_filter_kernel(const RankParams p, const long long *__restrict__ off,
                                        const int32_t *__restrict__ idx, int32_t *__restrict__ cnt)
 {
-    constexpr bool ROT = (OP == OP_ROT_S || OP == OP_ROT_O);
+    extern __shared__ __align__(16) float pair_sm[];
+    constexpr int ROWS = OP == OP_ROT_S ? 3 : 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    float *sm = pair_sm + (size_t)warp * ROWS * p.L.ld;
     const long long total = off[p.b];
-    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= total) return;
-    long long lo = 0, hi = p.b;  // largest i with off[i] <= f
-    while (hi - lo > 1) {
-        long long mid = (lo + hi) >> 1;
-        if (off[mid] <= f) lo = mid; else hi = mid;
+    for (long long f = (long long)blockIdx.x * wpc + warp; f < total; f += (long long)gridDim.x * wpc) {
+        long long lo = 0, hi = p.b;  // largest i with off[i] <= f
+        while (hi - lo > 1) {
+            long long mid = (lo + hi) >> 1;
+            if (off[mid] <= f) lo = mid; else hi = mid;
+        }
+        const long long i = lo;
+        const long long pos = (long long)idx[f] - p.filt_base;  // filter ids are global; the shard's table is local
+        if (pos < p.cand_begin || pos >= p.cand_begin + p.n_cand) continue;  // :280-288 (warp-uniform)
+        const long long id = p.cand_ids ? (long long)p.cand_ids[pos] : pos;
+        const float sc = pair_score_warp<OP>(p.ent + (size_t)id * p.L.ld, p.qvec + (size_t)i * p.L.ld,
+                                             OP == OP_ROT_S ? p.qaux + (size_t)i * p.L.ld : nullptr, p.L.ld, p.L.kp, p.scale, sm, lane);
+        if (lane == 0 && p.qpos[i] <= quantise(sc)) atomicAdd(&cnt[3 * i + 2], 1);
     }
-    const long long i = lo;
-    const long long pos = (long long)idx[f] - p.filt_base;  // filter ids are global; the shard's table is local
-    if (pos < p.cand_begin || pos >= p.cand_begin + p.n_cand) return;  // :280-288
-    const long long id = p.cand_ids ? (long long)p.cand_ids[pos] : pos;
-    const float *e = p.ent + (size_t)id * p.L.ld;
-    const float *q = p.qvec + (size_t)i * p.L.ld;
-    float acc = 0.f;
-    if (!ROT) {
-        for (int d = 0; d < p.L.ld; ++d) acc = rank_step<OP>(acc, e[d], q[d]);
-    } else {
-        const int kp = p.L.kp;
-        const float *a = p.qaux + (size_t)i * p.L.ld;
-        for (int d = 0; d < kp; ++d)
-            acc = rank_step_rot<OP>(acc, e[d], e[kp + d], q[d], q[kp + d], OP == OP_ROT_S ? a[d] : 0.f,
-                                    OP == OP_ROT_S ? a[kp + d] : 0.f);
-    }
-    if (p.qpos[i] <= quantise(rank_finish<OP>(acc, p.scale))) atomicAdd(&cnt[3 * i + 2], 1);
 }
 
 cudaError_t launch_rank_filter_n(const RankParams &p, const long long *filt_off, const int32_t *filt_idx,
                                  long long n_pairs, int32_t *cnt, cudaStream_t st)
 {
     if (n_pairs == 0 || p.b == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((n_pairs + 127) / 128);
-    switch (rank_op(p.L.model, p.side)) {
-    case OP_DOT: kge_rank_filter_kernel<OP_DOT><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
-    case OP_L1_ADD: kge_rank_filter_kernel<OP_L1_ADD><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
-    case OP_L1_SUB: kge_rank_filter_kernel<OP_L1_SUB><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
-    case OP_ROT_S: kge_rank_filter_kernel<OP_ROT_S><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
-    case OP_ROT_O: kge_rank_filter_kernel<OP_ROT_O><<<grid, 128, 0, st>>>(p, filt_off, filt_idx, cnt); break;
+    const int op = rank_op(p.L.model, p.side);
+    const int wpc = pair_score_warps(p.L.ld, op == OP_ROT_S ? 3 : 2);
+    const size_t sm = (size_t)wpc * (op == OP_ROT_S ? 3 : 2) * p.L.ld * sizeof(float);
+    long long want = (n_pairs + wpc - 1) / wpc;
+    const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+#define KGE_FILT(OP)                                                                                                  \
+    {                                                                                                                 \
+        cudaError_t e = cudaFuncSetAttribute(kge_rank_filter_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        if (e != cudaSuccess) return e;                                                                               \
+        kge_rank_filter_kernel<OP><<<grid, wpc * 32, sm, st>>>(p, filt_off, filt_idx, cnt);                           \
+        break;                                                                                                        \
     }
+    switch (op) {
+    case OP_DOT: KGE_FILT(OP_DOT)
+    case OP_L1_ADD: KGE_FILT(OP_L1_ADD)
+    case OP_L1_SUB: KGE_FILT(OP_L1_SUB)
+    case OP_ROT_S: KGE_FILT(OP_ROT_S)
+    case OP_ROT_O: KGE_FILT(OP_ROT_O)
+    }
+#undef KGE_FILT
     return cudaGetLastError();
 }
 

@@ -30,7 +30,7 @@
 #include <cuda_bf16.h>
 #include <math.h>
 
-#include "kge_internal.h"
+#include "kge_rank_common.cuh"
 
 namespace kge {
 
@@ -39,21 +39,26 @@ namespace kge {
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TC_MQ = 128;                         // queries per A tile    (UMMA M, one TMEM lane per query)
 constexpr int TC_NC = 256;                         // candidates per B tile (UMMA N, one TMEM column per candidate)
-constexpr int TC_KB = 64;                          // columns per k-block (4 MMA k-steps of 16)
+constexpr int TC_KB = 32;                          // columns per k-block (2 MMA k-steps of 16)
+constexpr int TC_KC = TC_KB / 8;                   // 8-column chunks (core-matrix columns) per k-block
+constexpr int TC_KSTEPS = TC_KB / 16;              // MMA k-steps per k-block
 constexpr int TC_A_ELEMS = TC_MQ * TC_KB;          // bf16 elements of one part (hi or lo) of an A tile
 constexpr int TC_B_ELEMS = TC_NC * TC_KB;
-constexpr int TC_A_BYTES = 2 * TC_A_ELEMS * 2;     // hi + lo, contiguous in HBM and in shared memory: 32 KB
-constexpr int TC_B_BYTES = 2 * TC_B_ELEMS * 2;     // 64 KB
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;  // 96 KB per pipeline stage, 2 stages
+constexpr int TC_A_BYTES = 2 * TC_A_ELEMS * 2;     // hi + lo, contiguous in HBM and in shared memory: 16 KB
+constexpr int TC_B_BYTES = 2 * TC_B_ELEMS * 2;     // 32 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;  // 48 KB per pipeline stage
+constexpr int TC_STAGES = 4;                       // operand ring depth: the loop is bound by the latency of the bulk copies (a 96 KB
+                                                   // stage x 2 measured 15 us per 7-k-block tile against 4.9 us of MMAs), so more,
+                                                   // smaller stages in flight beat fewer, larger ones
 constexpr int TC_THREADS = 192;                    // warp 0 producer, warp 1 MMA issuer, warps 2..5 epilogue
 constexpr int TC_TMEM_COLS = 512;                  // two accumulator stages of 256 fp32 columns
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 1. split: fp32 rows -> blocked bf16 hi/lo operand tiles.
-//    tile (rb, kb) of a matrix with RB rows per block: [hi: RB x 64][lo: RB x 64]; inside a part, element (r, c) lives at
-//    ((r/8 * 8 + c/8) * 8 + r%8) * 8 + c%8: 8x8 core matrices of 128 contiguous bytes, 8 of them (one k-block) per
-//    8-row group -> the canonical K-major SWIZZLE_NONE layout with LBO = 128 B (next k-chunk), SBO = 1024 B (next
-//    8-row group), so a whole tile is ONE contiguous bulk copy and needs no tensor map.
+//    tile (rb, kb) of a matrix with RB rows per block: [hi: RB x TC_KB][lo: RB x TC_KB]; inside a part, element (r, c) lives
+//    at ((r/8 * TC_KC + c/8) * 8 + r%8) * 8 + c%8: 8x8 core matrices of 128 contiguous bytes, TC_KC of them (one k-block)
+//    per 8-row group -> the canonical K-major SWIZZLE_NONE layout with LBO = 128 B (next k-chunk), SBO = TC_KC*128 B
+//    (next 8-row group), so a whole tile is ONE contiguous bulk copy and needs no tensor map.
 // ---------------------------------------------------------------------------------------------------------------------
 // One WARP per row: lanes stride over the row's 8-column chunks (coalesced 32-byte reads), write the hi / lo core-matrix
 // rows (16 bytes each) and accumulate the row's sum of squares on the way, so the norms the error bound needs cost no
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(256) kge_rank_split_kernel(const float *__rest
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int chunks = nkb * 8;
+    const int chunks = nkb * TC_KC;
     for (long long r = warp0; r < rows_pad; r += n_warps) {
         const bool live = r < n_rows;
         const float *row = live ? src + (size_t)(ids ? (long long)ids[r] : row_begin + r) * ld : nullptr;
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(256) kge_rank_split_kernel(const float *__rest
         const int rl = (int)(r - rb * RB);
         float ss = 0.f;
         for (int c = lane; c < chunks; c += 32) {
-            const int kb = c >> 3, kc = c & 7, col0 = c * 8;
+            const int kb = c / TC_KC, kc = c - kb * TC_KC, col0 = c * 8;
             float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (live) {
                 if (col0 + 4 <= ld) { const float4 v = *reinterpret_cast<const float4 *>(row + col0); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(256) kge_rank_split_kernel(const float *__rest
                 ss = fmaf(x[e], x[e], ss);
             }
             const size_t tile = ((size_t)rb * nkb + kb) * (size_t)(2 * RB * TC_KB);
-            const size_t off = (size_t)(((rl >> 3) * 8 + kc) * 8 + (rl & 7)) * 8;
+            const size_t off = (size_t)(((rl >> 3) * TC_KC + kc) * 8 + (rl & 7)) * 8;
             *reinterpret_cast<uint4 *>(out + tile + off) = *reinterpret_cast<const uint4 *>(hi);
             *reinterpret_cast<uint4 *>(out + tile + (size_t)RB * TC_KB + off) = *reinterpret_cast<const uint4 *>(lo);
         }
@@ -172,10 +177,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, mma_sm100_desc.hpp): K-major, SWIZZLE_NONE,
-// leading byte offset (next 8-column chunk along K) 128 B, stride byte offset (next 8-row group) 1024 B, version 1 (sm_100)
+// leading byte offset (next 8-column chunk along K) 128 B, stride byte offset (next 8-row group) TC_KC*128 B, version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr)
 {
-    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) |
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)((TC_KC * 128u) >> 4) << 32) |
            ((uint64_t)1 << 46);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, N = 256, M = 128, dense
@@ -198,7 +203,7 @@ struct TcParams {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 2. the filter kernel.  CTA (qb, j): query block qb, candidate tiles j, j + ctas_per_qb, ...; one CTA per SM.
-//    Per tile: nkb pipeline trips {cp.async.bulk A tile + B tile -> 3 MMAs per k-step}, then 128x256 accumulators are
+//    Per tile: nkb trips of a TC_STAGES-deep ring {cp.async.bulk A tile + B tile -> 3 MMAs per k-step}, then 128x256 accumulators are
 //    read back by four warps (one query per thread) while the next tile's MMAs fill the other accumulator stage.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool PROBE>
@@ -206,17 +211,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kge_rank_tc_kernel(const TcPara
 {
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 2 * TC_STAGE_BYTES);  // [2] operands landed
-    uint64_t *empty = full + 2;                                                // [2] operands consumed
-    uint64_t *tfull = full + 4;                                                // [2] accumulator stage complete
-    uint64_t *tempty = full + 6;                                               // [2] accumulator stage drained
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(full + 8);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);  // [TC_STAGES] operands landed
+    uint64_t *empty = full + TC_STAGES;                                        // [TC_STAGES] operands consumed
+    uint64_t *tfull = empty + TC_STAGES;                                       // [2] accumulator stage complete
+    uint64_t *tempty = tfull + 2;                                              // [2] accumulator stage drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x % p.n_qb, first = blockIdx.x / p.n_qb;
     const int n_items = first < p.n_ct ? (p.n_ct - first + p.ctas_per_qb - 1) / p.ctas_per_qb : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
@@ -232,8 +238,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kge_rank_tc_kernel(const TcPara
             for (int i = 0; i < n_items; ++i) {
                 const int ct = first + i * p.ctas_per_qb;
                 for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-                    const int s = it & 1;
-                    mbar_wait(empty + s, ((it >> 1) & 1u) ^ 1u);
+                    const int s = it % TC_STAGES;
+                    mbar_wait(empty + s, ((it / TC_STAGES) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(full + s, (uint32_t)TC_STAGE_BYTES);
                     unsigned char *st = smem + (size_t)s * TC_STAGE_BYTES;
                     bulk_load(st, p.a_split + ((size_t)qb * p.nkb + kb) * (size_t)(2 * TC_A_ELEMS), TC_A_BYTES, full + s);
@@ -250,13 +256,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kge_rank_tc_kernel(const TcPara
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_NC);
             for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-                const int s = it & 1;
-                mbar_wait(full + s, (it >> 1) & 1u);
+                const int s = it % TC_STAGES;
+                mbar_wait(full + s, (it / TC_STAGES) & 1u);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * TC_STAGE_BYTES), a_lo = a_hi + TC_A_ELEMS * 2;
                     const uint32_t b_hi = a_hi + TC_A_BYTES, b_lo = b_hi + TC_B_ELEMS * 2;
-                    const int ks_n = min(4, p.ksteps - kb * 4);
+                    const int ks_n = min(TC_KSTEPS, p.ksteps - kb * TC_KSTEPS);
                     for (int ks = 0; ks < ks_n; ++ks) {
                         const uint32_t o = (uint32_t)ks * 256u;  // two 128-byte k-chunks per k-step of 16
                         const uint64_t da_hi = umma_smem_desc(a_hi + o), da_lo = umma_smem_desc(a_lo + o);
@@ -329,10 +335,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kge_rank_tc_kernel(const TcPara
 // 3. refine: the exact canonical chain (same arithmetic as kge_rank_dot_kernel / the filter kernel of kge_rank.cu) for the
 //    undecided pairs; one thread per pair.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) kge_rank_refine_kernel(const RankParams p, const int2 *__restrict__ pairs,
-                                                              const unsigned *__restrict__ pair_count, unsigned pair_cap,
-                                                              int32_t *__restrict__ cnt)
+__global__ void kge_rank_refine_kernel(const RankParams p, const int2 *__restrict__ pairs, const unsigned *__restrict__ pair_count,
+                                       unsigned pair_cap, int32_t *__restrict__ cnt)
 {
+    extern __shared__ __align__(16) float pair_sm[];
     const unsigned n = *pair_count;
     if (n > pair_cap) {  // overflow: forget what the filter counted; the gated exact kernel (next launch) recounts everything
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.b; i += (long long)gridDim.x * blockDim.x) {
@@ -341,18 +347,19 @@ __global__ void __launch_bounds__(128) kge_rank_refine_kernel(const RankParams p
         }
         return;
     }
-    for (unsigned f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    float *sm = pair_sm + (size_t)warp * 2 * p.L.ld;
+    for (unsigned f = blockIdx.x * wpc + warp; f < n; f += gridDim.x * wpc) {  // one warp per undecided pair
         const int2 pr = pairs[f];
         const long long pos = pr.y;
         const long long id = p.cand_ids ? (long long)p.cand_ids[pos] : p.cand_begin + pos;
-        const float *e = p.ent + (size_t)id * p.L.ld;
-        const float *qv = p.qvec + (size_t)pr.x * p.L.ld;
-        float acc = 0.f;
-        for (int d = 0; d < p.L.ld; ++d) acc = __fmaf_rn(e[d], qv[d], acc);
-        const float sc = (p.scale == 1.f) ? acc : __fmul_rn(p.scale, acc);
-        const int qc = quantise(sc), qp = p.qpos[pr.x];
-        if (qp < qc) atomicAdd(cnt + 3 * pr.x + 0, 1);
-        else if (qp == qc) atomicAdd(cnt + 3 * pr.x + 1, 1);
+        const float sc = pair_score_warp<OP_DOT>(p.ent + (size_t)id * p.L.ld, p.qvec + (size_t)pr.x * p.L.ld, nullptr, p.L.ld, p.L.kp,
+                                                 p.scale, sm, lane);
+        if (lane == 0) {
+            const int qc = quantise(sc), qp = p.qpos[pr.x];
+            if (qp < qc) atomicAdd(cnt + 3 * pr.x + 0, 1);
+            else if (qp == qc) atomicAdd(cnt + 3 * pr.x + 1, 1);
+        }
     }
 }
 
@@ -426,7 +433,7 @@ cudaError_t launch_rank_count_tc(const RankParams &p, const RankTcLayout &w, voi
     if (per > w.n_ct) per = w.n_ct;
     t.ctas_per_qb = per;
     t.probe_a = probe_a; t.probe_d = probe_d; t.scale = p.scale;
-    const size_t smem = 2 * (size_t)TC_STAGE_BYTES + 1024 /*alignment*/ + 128 /*barriers + TMEM slot*/;
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment*/ + 128 /*barriers + TMEM slot*/;
     if (probe_a) {
         if ((e = cudaFuncSetAttribute(kge_rank_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         kge_rank_tc_kernel<true><<<(unsigned)(w.n_qb * per), TC_THREADS, smem, st>>>(t);
@@ -434,7 +441,12 @@ cudaError_t launch_rank_count_tc(const RankParams &p, const RankTcLayout &w, voi
     }
     if ((e = cudaFuncSetAttribute(kge_rank_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     kge_rank_tc_kernel<false><<<(unsigned)(w.n_qb * per), TC_THREADS, smem, st>>>(t);
-    kge_rank_refine_kernel<<<sm_count * 4, 128, 0, st>>>(p, pairs, count, w.pair_cap, cnt);
+    {
+        const int wpc = pair_score_warps(ld, 2);
+        const size_t rsm = (size_t)wpc * 2 * ld * sizeof(float);
+        if ((e = cudaFuncSetAttribute(kge_rank_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm)) != cudaSuccess) return e;
+        kge_rank_refine_kernel<<<sm_count * 2, wpc * 32, rsm, st>>>(p, pairs, count, w.pair_cap, cnt);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // overflow fallback: the exact FP32 kernel, every CTA of which returns at once unless the pair list overflowed
     RankParams g = p;

@@ -23,6 +23,8 @@
 // per positive.
 #include <math.h>
 
+#include <type_traits>
+
 #include "kge_internal.h"
 
 namespace kge {
@@ -184,6 +186,23 @@ struct Scorer<KGE_DISTMULT, NIT> {
         pa = f4hsum(a);
         pb = f4hsum(b);
     }
+    static constexpr bool kQuad = true;  // has partial4: four corruptions of one side per call
+    template <int SIDE>
+    __device__ __forceinline__ void partial4(const float *r0, const float *r1, const float *r2, const float *r3, float &p0,
+                                             float &p1, float &p2, float &p3) const
+    {
+        float4 a = f4zero(), b = f4zero(), c4 = f4zero(), d = f4zero();
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int c = chunk(it);
+            const float4 q = SIDE ? C[it] : A[it];
+            a = f4fma(f4ld(r0 + 4 * c), q, a);
+            b = f4fma(f4ld(r1 + 4 * c), q, b);
+            c4 = f4fma(f4ld(r2 + 4 * c), q, c4);
+            d = f4fma(f4ld(r3 + 4 * c), q, d);
+        }
+        p0 = f4hsum(a); p1 = f4hsum(b); p2 = f4hsum(c4); p3 = f4hsum(d);
+    }
     template <int SIDE, class Sink>
     __device__ __forceinline__ void grad2(float *ra, float *rb, float *ga_row, float *gb_row, float ga, float gb,
                                           bool has_b)
@@ -268,6 +287,27 @@ struct ComplexScorer {
         pa = f4hsum(a);
         pb = f4hsum(b);
     }
+    static constexpr bool kQuad = true;
+    template <int SIDE>
+    __device__ __forceinline__ void partial4(const float *r0, const float *r1, const float *r2, const float *r3, float &p0,
+                                             float &p1, float &p2, float &p3) const
+    {
+        float4 a = f4zero(), b = f4zero(), c4 = f4zero(), d = f4zero();
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int c = chunk(it);
+            const float4 qr = SIDE ? C[it] : A[it], qi = SIDE ? D[it] : Bv[it];
+            a = f4fma(f4ld(r0 + 4 * c), qr, a);
+            b = f4fma(f4ld(r1 + 4 * c), qr, b);
+            c4 = f4fma(f4ld(r2 + 4 * c), qr, c4);
+            d = f4fma(f4ld(r3 + 4 * c), qr, d);
+            a = f4fma(f4ld(r0 + hs + 4 * c), qi, a);
+            b = f4fma(f4ld(r1 + hs + 4 * c), qi, b);
+            c4 = f4fma(f4ld(r2 + hs + 4 * c), qi, c4);
+            d = f4fma(f4ld(r3 + hs + 4 * c), qi, d);
+        }
+        p0 = f4hsum(a); p1 = f4hsum(b); p2 = f4hsum(c4); p3 = f4hsum(d);
+    }
     template <int SIDE, class Sink>
     __device__ __forceinline__ void grad2(float *ra, float *rb, float *ga_row, float *gb_row, float ga, float gb,
                                           bool has_b)
@@ -325,6 +365,7 @@ template <int NIT> struct Scorer<KGE_HOLE, NIT> : ComplexScorer<NIT> {};
 // ---- TransE: f = -sum |s+p-o| (TransE.py:51-53) ---------------------------
 template <int NIT>
 struct Scorer<KGE_TRANSE, NIT> {
+    static constexpr bool kQuad = false;
     float4 Qs[NIT], Qo[NIT], Vs[NIT], Vo[NIT];  // p-o, s+p, sum g*sign per side
     int lane, nch, cs = 32;  // cs: chunk stride = lanes cooperating on one positive
     __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
@@ -404,6 +445,7 @@ struct Scorer<KGE_TRANSE, NIT> {
 // The reference's gradient is NaN at an exactly-zero residual; here it is 0.
 template <int NIT>
 struct Scorer<KGE_ROTATE, NIT> {
+    static constexpr bool kQuad = false;
     float4 Cs[NIT], Sn[NIT], Yr[NIT], Yi[NIT], Or_[NIT], Oi[NIT];
     float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], Aphi[NIT];
     int lane, nch, cs = 32, kp, hs;  // cs: chunk stride = lanes on one positive; kp: half stride in HBM rows, hs: half stride of the staged row window
@@ -522,6 +564,23 @@ __device__ __forceinline__ void warp_sum2(float &a, float &b)
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
     }
+}
+
+// Four warp sums for the price of six shuffles: a transposed butterfly.  After the xor-16 step the lower half-warp
+// carries v0, v1 and the upper one v2, v3; after the xor-8 step each quarter-warp carries ONE value; three more
+// steps finish the sum inside the quarter.  On return lanes [8q, 8q+8) hold the full sum of value q.
+__device__ __forceinline__ float warp_sum4t(float v0, float v1, float v2, float v3, int lane)
+{
+    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+    float k0 = hi16 ? v2 : v0, k1 = hi16 ? v3 : v1;
+    k0 += __shfl_xor_sync(0xffffffffu, hi16 ? v0 : v2, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, hi16 ? v1 : v3, 16);
+    float k = hi8 ? k1 : k0;
+    k += __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
 }
 
 // --------------------------------------------------------------------------
@@ -709,8 +768,9 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
     float *rows = reinterpret_cast<float *>(region);  // (3+G) windows of lw floats
     float *sc = reinterpret_cast<float *>(region + p.rows_bytes);
     int *nid = reinterpret_cast<int *>(sc + p.eta_pad);
-    int *nside = nid + p.eta_pad;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(nside + p.eta_pad);
+    int *nside = nid + p.eta_pad;   // scratch while the corruptions are being sorted
+    int *jorig = nside + p.eta_pad; // sorted slot -> index j of the corruption in the reference's tile order
+    uint64_t *bar = reinterpret_cast<uint64_t *>(jorig + p.eta_pad);
 
     if (lane == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
     fence_mbar_init();
@@ -735,17 +795,44 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B; i += n_warps) {
         const int s_id = p.triples[3 * i], p_id = p.triples[3 * i + 1], o_id = p.triples[3 * i + 2];
-        // ---- corruptions of this positive (A3) ----
-        for (int j = lane; j < eta; j += 32) {
-            int keep, repl;
-            const unsigned long long r = (unsigned long long)j * (unsigned long long)p.B + (unsigned long long)i;
-            if (p.neg_ent) { repl = p.neg_ent[r]; keep = p.neg_keep[r] ? 1 : 0; }
-            else draw_corruption(p.seed, p.step, r, p.n_ent, &keep, &repl);
-            nid[j] = repl;
-            nside[j] = keep;  // keep_subj = 1 -> object replaced -> side 1
-            if (!resident) sc[j] = 0.f;
-            if (p.stamp_ent && p.mode != KGE_STEP_FORWARD_ONLY) stamp_ent_row(p, repl);  // lazy optimizer: row touched
+        // ---- corruptions of this positive (A3), SORTED BY SIDE as they are drawn ----
+        // Slot t of the warp's arrays (nid, sc, the gathered rows, the stash) holds corruption jorig[t]; slots [0, n0)
+        // replaced the subject, slots [n0, eta) the object.  Both passes then walk two plain index ranges with the side
+        // as a template argument -- no ballot / find-first-set bookkeeping per pair of corruptions.
+        int n0 = 0;
+        for (int base = 0; base < eta; base += 32) {
+            const int j = base + lane;
+            int keep = 1, repl = 0;
+            if (j < eta) {
+                const unsigned long long r = (unsigned long long)j * (unsigned long long)p.B + (unsigned long long)i;
+                if (p.neg_ent) { repl = p.neg_ent[r]; keep = p.neg_keep[r] ? 1 : 0; }
+                else draw_corruption(p.seed, p.step, r, p.n_ent, &keep, &repl);
+                nside[j] = keep;  // keep_subj = 1 -> object replaced -> side 1
+                sc[j] = __int_as_float(repl);
+                if (p.stamp_ent && p.mode != KGE_STEP_FORWARD_ONLY) stamp_ent_row(p, repl);  // lazy optimizer: row touched
+            }
+            n0 += __popc(__ballot_sync(0xffffffffu, j < eta && keep == 0));
         }
+        __syncwarp();
+        {
+            int c0 = 0, c1 = n0;
+            const unsigned lt = (1u << lane) - 1u;
+            for (int base = 0; base < eta; base += 32) {
+                const int j = base + lane;
+                const int keep = (j < eta) ? nside[j] : -1;
+                const unsigned m0 = __ballot_sync(0xffffffffu, keep == 0), m1 = __ballot_sync(0xffffffffu, keep == 1);
+                if (j < eta) {
+                    const int t = keep ? c1 + __popc(m1 & lt) : c0 + __popc(m0 & lt);
+                    nid[t] = __float_as_int(sc[j]);
+                    jorig[t] = j;
+                }
+                c0 += __popc(m0);
+                c1 += __popc(m1);
+            }
+        }
+        __syncwarp();
+        if (!resident)
+            for (int j = lane; j < eta; j += 32) sc[j] = 0.f;
         if (p.stamp_ent && p.mode != KGE_STEP_FORWARD_ONLY) {
             if (lane == 0) stamp_ent_row(p, s_id);
             if (lane == 1) stamp_ent_row(p, o_id);
@@ -823,20 +910,61 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                         else { sc[j0 + a] += pa; if (has_b) sc[j0 + b] += pb; }
                     }
                 };
-                for_each_pair_by_side(
-                    nside + j0, gsz, lane,
-                    [&](int a, int b, bool has_b) {
+                // slots [j0, j0+gsz) of this group: the part below n0 replaced the subject, the rest the object
+                const int e0 = min(n0, j0 + gsz), b1 = max(n0, j0);
+                if constexpr (Scorer<MODEL, NIT>::kQuad) {
+                    // four corruptions per trip; slots past the end of the range alias the last valid one and are dropped
+                    auto quad = [&](int t, int end, auto side_tag) {
+                        constexpr int SIDE = decltype(side_tag)::value;
+                        const int last = end - 1 - j0, a0 = t - j0;
+                        const float *r0 = nrows + (size_t)a0 * lw, *r1 = nrows + (size_t)min(a0 + 1, last) * lw;
+                        const float *r2 = nrows + (size_t)min(a0 + 2, last) * lw, *r3 = nrows + (size_t)min(a0 + 3, last) * lw;
+                        float v0, v1, v2, v3;
+                        S.template partial4<SIDE>(r0, r1, r2, r3, v0, v1, v2, v3);
+                        const float v = warp_sum4t(v0, v1, v2, v3, lane);
+                        const int q = lane >> 3;
+                        if ((lane & 7) == 0 && t + q < end) {
+                            if (resident) sc[t + q] = v; else sc[t + q] += v;
+                        }
+                    };
+                    // a tail of one or two corruptions takes the cheaper two-at-a-time path
+                    auto tail = [&](int t, int end, auto side_tag) {
+                        constexpr int SIDE = decltype(side_tag)::value;
+                        const int a = t - j0;
+                        const bool has_b = t + 1 < end;
+                        const int b = has_b ? a + 1 : a;
                         float pa, pb;
-                        S.template partial2<0>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
+                        S.template partial2<SIDE>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
                         warp_sum2(pa, pb);
                         store(a, b, has_b, pa, pb);
-                    },
-                    [&](int a, int b, bool has_b) {
-                        float pa, pb;
-                        S.template partial2<1>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
-                        warp_sum2(pa, pb);
-                        store(a, b, has_b, pa, pb);
-                    });
+                    };
+                    auto side_range = [&](int lo, int hi, auto side_tag) {
+                        int t = lo;
+                        for (; hi - t >= 3; t += 4) quad(t, hi, side_tag);
+                        if (t < hi) tail(t, hi, side_tag);
+                    };
+                    side_range(j0, e0, std::integral_constant<int, 0>{});
+                    side_range(b1, j0 + gsz, std::integral_constant<int, 1>{});
+                } else {
+                for (int t = j0; t < e0; t += 2) {
+                    const int a = t - j0;
+                    const bool has_b = t + 1 < e0;
+                    const int b = has_b ? a + 1 : a;
+                    float pa, pb;
+                    S.template partial2<0>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
+                    warp_sum2(pa, pb);
+                    store(a, b, has_b, pa, pb);
+                }
+                for (int t = b1; t < j0 + gsz; t += 2) {
+                    const int a = t - j0;
+                    const bool has_b = t + 1 < j0 + gsz;
+                    const int b = has_b ? a + 1 : a;
+                    float pa, pb;
+                    S.template partial2<1>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
+                    warp_sum2(pa, pb);
+                    store(a, b, has_b, pa, pb);
+                }
+                }
                 __syncwarp();
             }
         }
@@ -848,13 +976,13 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                 for (int j = lane; j < eta; j += 32) sc[j] *= scale;
             __syncwarp();
             if (p.scores_neg)
-                for (int j = lane; j < eta; j += 32) p.scores_neg[(size_t)j * p.B + i] = sc[j];
+                for (int t = lane; t < eta; t += 32) p.scores_neg[(size_t)jorig[t] * p.B + i] = sc[t];
             if (p.scores_pos && lane == 0) p.scores_pos[i] = scale * P;
             if (p.mode == KGE_STEP_FORWARD_ONLY) { __syncwarp(); continue; }
             float li = loss_and_dscores(p, scale * P, sc, lane, &dP);
             if (lane == 0) loss_acc += (double)li;
         } else {
-            for (int j = lane; j < eta; j += 32) sc[j] = p.dneg[(size_t)j * p.B + i];
+            for (int t = lane; t < eta; t += 32) sc[t] = p.dneg[(size_t)jorig[t] * p.B + i];
             dP = p.dpos[i];
         }
         __syncwarp();
@@ -880,18 +1008,23 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                 if (!still_there) wait(buf);
                 if (top && !still_there) (void)S.prep(srow, prow, orow, lane);
                 float *const nrows = nbuf(buf);
-                for_each_pair_by_side(
-                    nside + j0, gsz, lane,
-                    [&](int a, int b, bool has_b) {
-                        S.template grad2<0, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw,
-                                                  gent_row(p, nid[j0 + a]) + gofs, gent_row(p, nid[j0 + b]) + gofs,
-                                                  scale * sc[j0 + a], has_b ? scale * sc[j0 + b] : 0.f, has_b);
-                    },
-                    [&](int a, int b, bool has_b) {
-                        S.template grad2<1, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw,
-                                                  gent_row(p, nid[j0 + a]) + gofs, gent_row(p, nid[j0 + b]) + gofs,
-                                                  scale * sc[j0 + a], has_b ? scale * sc[j0 + b] : 0.f, has_b);
-                    });
+                const int e0 = min(n0, j0 + gsz), b1 = max(n0, j0);
+                for (int t = j0; t < e0; t += 2) {
+                    const int a = t - j0;
+                    const bool has_b = t + 1 < e0;
+                    const int b = has_b ? a + 1 : a;
+                    S.template grad2<0, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, gent_row(p, nid[j0 + a]) + gofs,
+                                              gent_row(p, nid[j0 + b]) + gofs, scale * sc[j0 + a],
+                                              has_b ? scale * sc[j0 + b] : 0.f, has_b);
+                }
+                for (int t = b1; t < j0 + gsz; t += 2) {
+                    const int a = t - j0;
+                    const bool has_b = t + 1 < j0 + gsz;
+                    const int b = has_b ? a + 1 : a;
+                    S.template grad2<1, Sink>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, gent_row(p, nid[j0 + a]) + gofs,
+                                              gent_row(p, nid[j0 + b]) + gofs, scale * sc[j0 + a],
+                                              has_b ? scale * sc[j0 + b] : 0.f, has_b);
+                }
                 __syncwarp();
             }
             S.template finish<Sink>(srow, prow, orow, gs_row + gofs, gp_row + gofs, go_row + gofs, scale * dP, p.inv_div);

@@ -220,7 +220,8 @@ def test_train_on_batches_equals_train_on_batch():
         out.append((losses, [x.cpu().numpy() for x in m.engine.get_embeddings()]))
     for losses, (e, r) in out[1:]:
         assert np.allclose(losses, out[0][0], rtol=1e-6) and len(losses) == len(batches)
-        assert np.array_equal(e, out[0][1][0]) and np.array_equal(r, out[0][1][1])
+        # same steps, but fp32 atomics (red.v4) sum in a different order from run to run: equal to rounding, not bit for bit
+        assert np.allclose(e, out[0][1][0], rtol=1e-5, atol=1e-7) and np.allclose(r, out[0][1][1], rtol=1e-5, atol=1e-7)
 
 
 def test_model_initializers_and_regularizer_pair():
