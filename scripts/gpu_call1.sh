@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/c1_gpu.txt 2>&1
-echo "== sqrt check"; timeout 120 scripts/check_sqrt 2>&1 | tee gpurun_out/c1_check_sqrt.log
+echo "== sqrt check"; ([ -x scripts/check_sqrt ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/check_sqrt scripts/check_sqrt.cu) && timeout 120 scripts/check_sqrt 2>&1 | tee gpurun_out/c1_check_sqrt.log
 echo "== tests (main lib)"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/c1_tests_main.log
 echo "== tests (sorted variant)"; KGE_B200_LIB=$PWD/_variants/libkge_sorted.so timeout 900 python -m pytest tests/test_gpu_parity.py -q \
   -k "forward_backward or wide_rows or negative_groups or edge_shapes or philox or external or full_size or lazy or train_steps or linearity" 2>&1 | tail -8 | tee gpurun_out/c1_tests_sorted.log
