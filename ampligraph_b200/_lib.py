@@ -82,6 +82,7 @@ PROTOTYPES = {
     "kge_optimizer_step_exchange": (C.c_int, [_P, C.POINTER(KgeOptimizerConfig), C.POINTER(KgeOptimizerConfig), C.c_int64,
                                               C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _P, _P,
                                               C.c_int64, C.c_int64, C.POINTER(_P), C.c_uint32, C.c_int32, _P, _P]),
+    "kge_set_exchange_trace": (C.c_int, [_P, _P]),
     "kge_peer_barrier": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.c_int32, C.c_uint32, _P]),
     "kge_rank": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P,
                            C.c_int64, _P, _P, _P, C.c_int64, _P]),

@@ -19,6 +19,7 @@ struct kge_handle {
     // the only device memory the library owns (allocated once by kge_create, freed by kge_destroy):
     float *rot;              // [n_rel, ld] rotation table (RotatE only)
     unsigned *done_counter;  // last-CTA counter of kge_optimizer_step_exchange
+    unsigned long long *exchange_trace;  // caller-owned 8 x uint64 phase stamps of the next exchange launches, or nullptr
     // training launch geometry
     int nit, G, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats, resident;
     int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
@@ -590,7 +591,15 @@ extern "C" int kge_optimizer_step_exchange(kge_handle *h, const kge_optimizer_co
     x.slot0 = slot0_shard_dev; x.slot1 = slot1_shard_dev;
     x.reg_loss = reg_loss_dev;
     x.done_counter = h->done_counter;
+    x.trace = h->exchange_trace;
     KGE_CUDA(launch_optimizer_exchange(o, x, h->sm_count, (cudaStream_t)stream), "kge_optimizer_step_exchange");
+    return KGE_OK;
+}
+
+extern "C" int kge_set_exchange_trace(kge_handle *h, uint64_t *stamps_dev)
+{
+    KGE_CHECK_HANDLE(h, "kge_set_exchange_trace");
+    h->exchange_trace = reinterpret_cast<unsigned long long *>(stamps_dev);
     return KGE_OK;
 }
 

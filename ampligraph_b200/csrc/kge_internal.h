@@ -47,6 +47,9 @@ struct TrainParams {
 
 // grid = min(occupancy * sm_count, ceil(B / warps))
 cudaError_t launch_train(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st);
+// kge_train_res.cu: the resident trilinear fast path (DistMult / ComplEx / HolE, all rows of a positive resident, eta <= 32, one table)
+bool train_res_applicable(const TrainParams &p, int nit);
+cudaError_t launch_train_res(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_rotation_table(const float *rel, float *rot, long long n_rel, int kp, int ld, float div,
                                   cudaStream_t st);
 cudaError_t launch_corruptions(const int32_t *triples, long long B, int eta, unsigned long long seed,
@@ -87,6 +90,7 @@ struct ExchangeParams {  // kge_optimizer_step_exchange
     float *slot0, *slot1;
     double *reg_loss;
     unsigned *done_counter;             // handle-owned device counter (last-CTA detection), self-resetting
+    unsigned long long *trace;          // nullptr or 8 x uint64 phase stamps (kge_set_exchange_trace)
 };
 cudaError_t launch_optimizer(const OptimParams &o, float *table, float *grad, float *slot0, float *slot1,
                              long long n_floats, double *reg_loss, int sm_count, cudaStream_t st);

@@ -280,9 +280,21 @@ struct ExchangeArgs {
     RegParams reg_ent, reg_rel;
     double *reg_loss;
     unsigned *done_counter;
+    unsigned long long *trace;  // nullptr, or 8 x uint64 %globaltimer stamps of the phases (kge_set_exchange_trace)
     unsigned token;
     int world, rank, phases;
 };
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// phase stamp by CTA 0 (or whoever is told to): one store, only when tracing
+#define KGE_TRACE(slot, cond)                                                         \
+    do {                                                                              \
+        if (x.trace && (cond) && threadIdx.x == 0) x.trace[slot] = globaltimer_ns(); \
+    } while (0)
 
 template <int KIND, bool REG, int WORLD, bool MC>
 __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeArgs x, const OptimParams o)
@@ -295,9 +307,11 @@ __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeA
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
 
+    KGE_TRACE(0, blockIdx.x == 0);
     // zero the next step's local gradient block: independent of the peers, overlaps the barrier wait
     if (x.zero_grad)
         for (long long i = tid; i < x.total4; i += nthreads) __stcg(x.zero_grad + i, z);
+    KGE_TRACE(1, blockIdx.x == 0);
 
     if (x.phases & 1) {
         if (threadIdx.x < 32) {
@@ -306,6 +320,7 @@ __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeA
         }
         __syncthreads();
     }
+    KGE_TRACE(2, blockIdx.x == 0);
 
     float racc = 0.f;
     for (long long base = tid; base < x.n4; base += nthreads * U) {
@@ -346,17 +361,26 @@ __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeA
     }
     if (REG && x.reg_loss) flush_reg_loss(racc, x.reg_loss);
 
+    KGE_TRACE(3, blockIdx.x == 0);
     if (x.phases & 2) {
-        __threadfence_system();  // this thread's peer stores are performed before the CTA reports done
+        // Release pattern at CTA granularity: the CTA barrier orders every thread's peer stores before thread 0's
+        // system-scope fence (fences are cumulative), which orders them before its done-count; the last CTA fences again
+        // before it signals the peers.  One MEMBAR.SYS per CTA instead of one per thread.
         __syncthreads();
         __shared__ int last;
-        if (threadIdx.x == 0) last = (atomicAdd(x.done_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            last = (atomicAdd(x.done_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
         __syncthreads();
+        KGE_TRACE(4, blockIdx.x == 0);
         if (last && threadIdx.x < 32) {
             if (threadIdx.x == 0) *x.done_counter = 0u;  // self-reset for the next launch (stream-ordered)
             __threadfence_system();
+            KGE_TRACE(5, true);
             flags_signal(x.flags, WORLD, rank, 1, x.token, threadIdx.x);
             flags_wait(x.flags, WORLD, rank, 1, x.token, threadIdx.x);
+            KGE_TRACE(6, true);
         }
     }
 }
@@ -379,6 +403,7 @@ cudaError_t launch_optimizer_exchange(const OptimParams &o, const ExchangeParams
     a.reg_ent = xp.reg_ent; a.reg_rel = xp.reg_rel;
     a.reg_loss = xp.reg_loss;
     a.done_counter = xp.done_counter;
+    a.trace = xp.trace;
     a.token = xp.token;
     a.world = xp.world; a.rank = xp.rank; a.phases = xp.phases;
     // no CTA ever waits for another CTA of this grid (phase 1 is per CTA, phase 3 is the last finisher alone), so the

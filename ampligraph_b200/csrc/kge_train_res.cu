@@ -1,0 +1,382 @@
+// kge_train_res.cu -- the RESIDENT TRILINEAR fast path of the fused training step (sm_100a).
+//
+// Same contract as kge_train_kernel (kge_train.cu; reference: train_step ScoringBasedEmbeddingModel.py:370-429 ->
+// EmbeddingLookupLayer.call, CorruptionGenerationLayerTrain.call, DistMult/ComplEx/HolE _compute_scores, the five
+// losses, tape.gradient), specialised for the shape the headline workload has: DistMult / ComplEx / HolE, every row of
+// a positive resident in the warp's shared-memory slot (one column window, one group), eta <= 32 (one corruption per
+// lane), a single (not row-sharded) table.  What the specialisation buys (ncu source page of the general kernel,
+// profiles/r2b_train_cfg2_general_kernel_source_hot.txt: 2,344 instructions per positive, 135 per pair of the gradient loop of which
+// 56 are loads / FMAs / REDs): all shared-memory traffic goes through explicit 32-bit shared addresses (one IADD per
+// 128-bit load instead of 64-bit generic pointer arithmetic re-derived every trip), gradient rows are addressed as
+// one 64-bit base per row plus the lane's byte offset, the shard/window/group machinery does not exist, and the
+// corruption sort is one ballot pair.  Arithmetic per element is identical to the general kernel's (same f32x2 FMAs in
+// the same order), so both produce the same scores; gradients differ only in the order of the fp32 atomics.
+#include "kge_train_common.cuh"
+
+namespace kge {
+
+// ---- explicit shared-memory accessors (32-bit shared addresses) -------------------------------------------------------
+__device__ __forceinline__ float4 lds4(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_i(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_i(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void mbar_init_s(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RES_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RES_DONE;\n"
+        "bra RES_WAIT_LOOP;\n"
+        "RES_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_s(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// The front end rematerialises cheap values (kernel parameters, %tid-derived addresses) inside the long per-positive
+// loop instead of keeping them in registers -- a dozen ld.param / shift / mad per trip of the inner loops.  Passing a
+// value through an empty asm makes it opaque: it is computed once and stays in its register.
+#define KGE_KEEP32(x) asm volatile("" : "+r"(x))
+#define KGE_KEEP64(x) asm volatile("" : "+l"(x))
+#define KGE_KEEPF(x) asm volatile("" : "+f"(x))
+__device__ __forceinline__ void red4(char *row, uint32_t byte_off, float4 v) { red_add_v4(reinterpret_cast<float *>(row + byte_off), v); }
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------------
+// HALVES = 1: DistMult (f = sum s p o, DistMult.py:48); HALVES = 2: ComplEx / HolE (ComplEx.py:52-62; HolE.py:45 scales by
+// 2/k, folded into the gradient scalars).  Lane l owns float4 chunks c = l + 32*it (it < NIT) of every half-row; lanes past
+// the end of the row read its last chunk with zero query vectors (exact zeros in every sum) and never store.
+// Shared-memory slot of a warp (same carve-up as kge_train_kernel, computed by kge_create):
+//   [ s | p | o | eta replaced rows ] [ sc: eta_pad floats ] [ nid ] [ (unused) ] [ jorig ] [ mbarrier ]
+template <int HALVES, int NIT, int THREADS>
+__global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    KGE_KEEP32(warp);
+    KGE_KEEP32(lane);
+    uint32_t rows_s = smem_u32(smem_raw) + (uint32_t)warp * (uint32_t)p.region_bytes;
+    uint32_t sc_s = rows_s + (uint32_t)p.rows_bytes;
+    uint32_t nid_s = sc_s + 4u * (uint32_t)p.eta_pad;
+    uint32_t jor_s = nid_s + 8u * (uint32_t)p.eta_pad;
+    uint32_t bar_s = jor_s + 4u * (uint32_t)p.eta_pad;
+    KGE_KEEP32(rows_s); KGE_KEEP32(sc_s); KGE_KEEP32(nid_s); KGE_KEEP32(jor_s); KGE_KEEP32(bar_s);
+    float *const sc = reinterpret_cast<float *>(smem_raw + (size_t)warp * p.region_bytes + p.rows_bytes);  // for loss_and_dscores
+
+    if (lane == 0) mbar_init_s(bar_s, 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    int ld = p.ld, eta = p.eta;
+    const int nch = p.kp >> 2;
+    uint32_t lwB = (uint32_t)p.slot_floats * 4u;  // bytes between rows of the slot
+    uint32_t hsB = (uint32_t)p.kp * 4u;           // bytes between the real and the imaginary half of a row (slot and HBM alike)
+    uint32_t row_bytes = (uint32_t)ld * 4u;
+    KGE_KEEP32(ld); KGE_KEEP32(eta); KGE_KEEP32(lwB); KGE_KEEP32(hsB); KGE_KEEP32(row_bytes);
+    uint32_t off[NIT];  // this lane's byte offset inside a half, per chunk
+    int live_i[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int c = lane + 32 * it;
+        live_i[it] = c < nch ? 1 : 0;
+        off[it] = 16u * (uint32_t)min(c, nch - 1);
+        KGE_KEEP32(off[it]);
+        KGE_KEEP32(live_i[it]);
+    }
+    bool live[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) live[it] = live_i[it] != 0;
+    float scale = p.score_scale;  // HolE 2/k, else 1
+    KGE_KEEPF(scale);
+    unsigned lt = (1u << lane) - 1u;
+    KGE_KEEP32(lt);
+    float *grad_ent = p.grad_ent;
+    KGE_KEEP64(grad_ent);
+    const bool stamping = p.stamp_ent != nullptr && p.mode != KGE_STEP_FORWARD_ONLY;
+    uint32_t phase = 0u;
+    double loss_acc = 0.0;
+
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B; i += n_warps) {
+        // ---- the positive, and its corruptions sorted by side as they are drawn (A3) ----
+        int tv = 0;
+        if (lane < 3) tv = __ldg(p.triples + 3 * i + lane);
+        const int s_id = __shfl_sync(0xffffffffu, tv, 0), p_id = __shfl_sync(0xffffffffu, tv, 1), o_id = __shfl_sync(0xffffffffu, tv, 2);
+        int keep = -1, repl = 0;
+        if (lane < eta) {
+            const unsigned long long r = (unsigned long long)lane * (unsigned long long)p.B + (unsigned long long)i;  // tile order j*B+i
+            if (p.neg_ent) { repl = p.neg_ent[r]; keep = p.neg_keep[r] ? 1 : 0; }
+            else draw_corruption(p.seed, p.step, r, p.n_ent, &keep, &repl);
+        }
+        // slots [0, n0) replaced the subject (keep_subj == 0), slots [n0, eta) the object; jorig[slot] = j
+        const unsigned m0 = __ballot_sync(0xffffffffu, keep == 0), m1 = __ballot_sync(0xffffffffu, keep == 1);
+        const int n0 = __popc(m0);
+        if (lane < eta) {
+            const int t = keep ? n0 + __popc(m1 & lt) : __popc(m0 & lt);
+            sts_i(nid_s + 4u * (uint32_t)t, repl);
+            sts_i(jor_s + 4u * (uint32_t)t, lane);
+            if (stamping) p.stamp_ent[repl] = p.stamp;  // lazy optimizer: row touched
+        }
+        if (stamping) {
+            if (lane == 0) p.stamp_ent[s_id] = p.stamp;
+            if (lane == 1) p.stamp_ent[o_id] = p.stamp;
+            if (lane == 2 && p.stamp_rel) p.stamp_rel[p_id] = p.stamp;
+        }
+        __syncwarp();
+
+        // ---- gather (A2): one bulk copy per row, s | p | o | replaced rows in slot order ----
+        const int nrow = 3 + eta;
+        if (lane == 0) mbar_expect_tx_s(bar_s, (uint32_t)nrow * row_bytes);
+        __syncwarp();
+        for (int r = lane; r < nrow; r += 32) {
+            const int id = r == 0 ? s_id : r == 1 ? p_id : r == 2 ? o_id : lds_i(nid_s + 4u * (uint32_t)(r - 3));
+            const float *src = (r == 1 ? p.rel : p.ent) + (size_t)id * ld;
+            bulk_load_s(rows_s + (uint32_t)r * lwB, src, row_bytes, bar_s);
+        }
+        char *const gs_row = reinterpret_cast<char *>(grad_ent + (size_t)s_id * ld);
+        char *const gp_row = reinterpret_cast<char *>(p.grad_rel + (size_t)p_id * ld);
+        char *const go_row = reinterpret_cast<char *>(grad_ent + (size_t)o_id * ld);
+        mbar_wait_s(bar_s, phase);
+        phase ^= 1u;
+
+        // ---- per-positive query vectors and the positive's score (A4) ----
+        // side 0 (subject replaced): f = <r, Q0>;  side 1 (object replaced): f = <r, Q1>   (re / im parts for HALVES = 2)
+        float4 Q0r[NIT], Q0i[NIT], Q1r[NIT], Q1i[NIT];
+        float4 W0r[NIT], W0i[NIT], W1r[NIT], W1i[NIT];  // sum_j g_j r_j per side
+        float P;
+        {
+            float4 acc = f4zero();
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const uint32_t a = rows_s + off[it];
+                if constexpr (HALVES == 2) {
+                    const float4 sr = lds4(a), si = lds4(a + hsB);
+                    float4 pr = lds4(a + lwB), pi = lds4(a + lwB + hsB);
+                    const float4 orr = lds4(a + 2u * lwB), oi = lds4(a + 2u * lwB + hsB);
+                    if (!live[it]) { pr = f4zero(); pi = f4zero(); }  // every query vector carries a factor of p
+                    Q0r[it] = f4fma(pi, oi, pr * orr);
+                    Q0i[it] = pr * oi - pi * orr;
+                    Q1r[it] = sr * pr - si * pi;
+                    Q1i[it] = f4fma(sr, pi, si * pr);
+                    acc = f4fma(sr, Q0r[it], acc);
+                    acc = f4fma(si, Q0i[it], acc);
+                    W0i[it] = W1i[it] = f4zero();
+                } else {
+                    const float4 vs = lds4(a), vo = lds4(a + 2u * lwB);
+                    float4 vp = lds4(a + lwB);
+                    if (!live[it]) vp = f4zero();
+                    Q0r[it] = vp * vo;
+                    Q1r[it] = vs * vp;
+                    acc = f4fma(vs, Q0r[it], acc);
+                }
+                W0r[it] = W1r[it] = f4zero();
+            }
+            P = warp_sum(f4hsum(acc));
+        }
+
+        // ---- pass A: the eta corruption scores, four (then two) rows of one side per trip ----
+        auto score_side = [&](int lo, int hi, const float4(&qr)[NIT], const float4(&qi)[NIT]) {
+            int t = lo;
+            for (; hi - t >= 3; t += 4) {
+                const uint32_t r0 = rows_s + (uint32_t)(3 + t) * lwB, r1 = r0 + lwB, r2 = r1 + lwB;
+                const uint32_t r3 = (t + 3 < hi) ? r2 + lwB : r2;  // a trip of three: the fourth row aliases the third and is dropped
+                float4 a = f4zero(), b = f4zero(), c = f4zero(), d = f4zero();
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const uint32_t o = off[it];
+                    a = f4fma(lds4(r0 + o), qr[it], a);
+                    b = f4fma(lds4(r1 + o), qr[it], b);
+                    c = f4fma(lds4(r2 + o), qr[it], c);
+                    d = f4fma(lds4(r3 + o), qr[it], d);
+                    if constexpr (HALVES == 2) {
+                        a = f4fma(lds4(r0 + o + hsB), qi[it], a);
+                        b = f4fma(lds4(r1 + o + hsB), qi[it], b);
+                        c = f4fma(lds4(r2 + o + hsB), qi[it], c);
+                        d = f4fma(lds4(r3 + o + hsB), qi[it], d);
+                    }
+                }
+                const float v = warp_sum4t(f4hsum(a), f4hsum(b), f4hsum(c), f4hsum(d), lane);  // lanes [8q, 8q+8) hold row q's sum
+                const int q = lane >> 3;
+                if ((lane & 7) == 0 && t + q < hi) sts_f(sc_s + 4u * (uint32_t)(t + q), v);
+            }
+            if (t < hi) {  // one or two rows left
+                const bool has_b = t + 1 < hi;
+                const uint32_t ra = rows_s + (uint32_t)(3 + t) * lwB, rb = has_b ? ra + lwB : ra;
+                float4 a = f4zero(), b = f4zero();
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const uint32_t o = off[it];
+                    a = f4fma(lds4(ra + o), qr[it], a);
+                    b = f4fma(lds4(rb + o), qr[it], b);
+                    if constexpr (HALVES == 2) {
+                        a = f4fma(lds4(ra + o + hsB), qi[it], a);
+                        b = f4fma(lds4(rb + o + hsB), qi[it], b);
+                    }
+                }
+                float pa = f4hsum(a), pb = f4hsum(b);
+                warp_sum2(pa, pb);
+                if (lane == 0) {
+                    sts_f(sc_s + 4u * (uint32_t)t, pa);
+                    if (has_b) sts_f(sc_s + 4u * (uint32_t)(t + 1), pb);
+                }
+            }
+        };
+        score_side(0, n0, Q0r, Q0i);
+        score_side(n0, eta, Q1r, Q1i);
+        __syncwarp();
+
+        // ---- loss and dL/dscore (A5) ----
+        float dP;
+        if (p.mode != KGE_STEP_BACKWARD_EXT) {
+            if (scale != 1.f) {
+                if (lane < eta) sc[lane] *= scale;
+                __syncwarp();
+            }
+            if (p.scores_neg && lane < eta) p.scores_neg[(size_t)lds_i(jor_s + 4u * (uint32_t)lane) * p.B + i] = sc[lane];
+            if (p.scores_pos && lane == 0) p.scores_pos[i] = scale * P;
+            if (p.mode == KGE_STEP_FORWARD_ONLY) { __syncwarp(); continue; }
+            const float li = loss_and_dscores(p, scale * P, sc, lane, &dP);
+            if (lane == 0) loss_acc += (double)li;
+        } else {
+            if (lane < eta) sc[lane] = p.dneg[(size_t)lds_i(jor_s + 4u * (uint32_t)lane) * p.B + i];
+            dP = p.dpos[i];
+        }
+        __syncwarp();
+
+        // ---- pass B: gradient rows of the replaced entities, two rows of one side per trip; W += g * row ----
+        // gradient REDs of one replaced row: g * Q at the lane's chunks.  One 64-bit base per half; chunk it sits 512*it bytes
+        // further (off[it] = off[0] + 512*it wherever live[it]), which the RED takes as an immediate offset.
+        auto red_row = [&](int id, float g, const float4(&qr)[NIT], const float4(&qi)[NIT]) {
+            if (!live[0]) return;
+            char *const g0 = reinterpret_cast<char *>(grad_ent + (size_t)id * ld) + off[0];
+            char *const g1 = g0 + hsB;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                if (!live[it]) break;
+                red_add_v4(reinterpret_cast<float *>(g0 + 512 * it), g * qr[it]);
+                if constexpr (HALVES == 2) red_add_v4(reinterpret_cast<float *>(g1 + 512 * it), g * qi[it]);
+            }
+        };
+        auto grad_side = [&](int lo, int hi, const float4(&qr)[NIT], const float4(&qi)[NIT], float4(&Wr)[NIT], float4(&Wi)[NIT]) {
+            for (int t = lo; t < hi; t += 2) {
+                const bool has_b = t + 1 < hi;
+                const uint32_t tb = (uint32_t)(has_b ? t + 1 : t);
+                const uint32_t ra = rows_s + (uint32_t)(3 + t) * lwB, rb = rows_s + (3u + tb) * lwB;
+                const float ga = scale * lds_f(sc_s + 4u * (uint32_t)t);
+                const float gb = has_b ? scale * lds_f(sc_s + 4u * tb) : 0.f;
+                const int ida = lds_i(nid_s + 4u * (uint32_t)t), idb = lds_i(nid_s + 4u * tb);
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const uint32_t o = off[it];
+                    const float4 ar = lds4(ra + o), br = lds4(rb + o);
+                    Wr[it] = f4fma(ga, ar, Wr[it]);
+                    Wr[it] = f4fma(gb, br, Wr[it]);
+                    if constexpr (HALVES == 2) {
+                        const float4 ai = lds4(ra + o + hsB), bi = lds4(rb + o + hsB);
+                        Wi[it] = f4fma(ga, ai, Wi[it]);
+                        Wi[it] = f4fma(gb, bi, Wi[it]);
+                    }
+                }
+                red_row(ida, ga, qr, qi);
+                if (has_b) red_row(idb, gb, qr, qi);
+            }
+        };
+        grad_side(0, n0, Q0r, Q0i, W0r, W0i);
+        grad_side(n0, eta, Q1r, Q1i, W1r, W1i);
+
+        // ---- gradient rows of s, p, o: bilinearity folds every corruption's share into W ----
+        {
+            const float gP = scale * dP;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                if (!live[it]) continue;
+                const uint32_t o = off[it], a = rows_s + o;
+                if constexpr (HALVES == 2) {
+                    const float4 sr = lds4(a), si = lds4(a + hsB);
+                    const float4 pr = lds4(a + lwB), pi = lds4(a + lwB + hsB);
+                    const float4 orr = lds4(a + 2u * lwB), oi = lds4(a + 2u * lwB + hsB);
+                    const float4 Ur = f4fma(gP, sr, W0r[it]), Ui = f4fma(gP, si, W0i[it]);    // everything that sat in the subject slot
+                    const float4 Xr = f4fma(gP, orr, W1r[it]), Xi = f4fma(gP, oi, W1i[it]);   // everything that sat in the object slot
+                    red4(gs_row, o, f4fma(pi, Xi, pr * Xr));                                  // d/ds f(s,p,X)
+                    red4(gs_row, o + hsB, pr * Xi - pi * Xr);
+                    red4(go_row, o, Ur * pr - Ui * pi);                                       // d/do f(U,p,o)
+                    red4(go_row, o + hsB, f4fma(Ur, pi, Ui * pr));
+                    red4(gp_row, o, f4fma(Ur, orr, Ui * oi) + f4fma(sr, W1r[it], si * W1i[it]));   // d/dp [f(U,p,o) + f(s,p,W1)]
+                    red4(gp_row, o + hsB, (Ur * oi - Ui * orr) + (sr * W1i[it] - si * W1r[it]));
+                } else {
+                    const float4 vs = lds4(a), vp = lds4(a + lwB), vo = lds4(a + 2u * lwB);
+                    const float4 U = f4fma(gP, vs, W0r[it]), X = f4fma(gP, vo, W1r[it]);
+                    red4(gs_row, o, vp * X);
+                    red4(go_row, o, U * vp);
+                    red4(gp_row, o, f4fma(U, vo, vs * W1r[it]));
+                }
+            }
+        }
+        __syncwarp();  // every lane has read the slot before the next positive's gather overwrites it
+    }
+    if (p.loss_out && p.mode == KGE_STEP_FUSED && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_out, loss_acc);
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------------
+bool train_res_applicable(const TrainParams &p, int nit)
+{
+    const bool trilinear = p.model == KGE_DISTMULT || p.model == KGE_COMPLEX || p.model == KGE_HOLE;
+    return trilinear && p.resident && p.shard_world <= 1 && p.eta <= 32 && p.stash == nullptr && nit <= 2 && p.n_cb == 1;
+}
+
+template <int HALVES, int NIT>
+static cudaError_t launch_res(const TrainParams &p, int sm_count, int threads, size_t smem, cudaStream_t st)
+{
+    constexpr int THREADS = KGE_TRAIN_THREADS(KGE_COMPLEX, NIT);
+    auto kern = kge_train_res_kernel<HALVES, NIT, THREADS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    const long long want = (p.B + (threads / 32) - 1) / (threads / 32), cap = (long long)occ * sm_count;
+    kern<<<(int)(want < cap ? want : cap), threads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_train_res(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st)
+{
+    if (p.B == 0) return cudaSuccess;
+    const bool two = p.model != KGE_DISTMULT;
+    if (nit <= 1) return two ? launch_res<2, 1>(p, sm_count, threads, smem, st) : launch_res<1, 1>(p, sm_count, threads, smem, st);
+    return two ? launch_res<2, 2>(p, sm_count, threads, smem, st) : launch_res<1, 2>(p, sm_count, threads, smem, st);
+}
+
+}  // namespace kge

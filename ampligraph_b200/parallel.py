@@ -47,6 +47,19 @@ def reject_lazy(optimizer_name, world):
                                   % (optimizer_name, world))
 
 
+def tables_close(got, ref, init, rtol=3e-4, atol_of_update=2e-3):
+    """Parity criterion for two runs that sum the same fp32 gradient contributions in a different order (multi-GPU vs
+    single GPU): |got - ref| <= atol + rtol*|ref| with atol = atol_of_update * max|ref - init|.  Adam turns a relative
+    gradient difference d into an update difference of about lr*d whatever the size of the parameter, so the absolute
+    part of the tolerance is stated relative to how far the parameters MOVED; a lost or doubled contribution changes a
+    row by O(1) of its update and fails.  Returns (ok, max_abs_err / max_update)."""
+    import numpy as np
+    got, ref, init = (np.asarray(x, dtype=np.float64) for x in (got, ref, init))
+    upd = max(float(np.abs(ref - init).max()), 1e-30)
+    err = np.abs(got - ref)
+    return bool((err <= atol_of_update * upd + rtol * np.abs(ref)).all()), float(err.max() / upd)
+
+
 _FLAG_WORDS = 64  # uint32 words reserved per rank for the in-kernel barriers (2 slots x up to 8 writers, padded)
 
 
@@ -172,6 +185,20 @@ class DataParallelTrainer:
                 C.c_void_p(self._local_g[blk ^ 1]), p(s0), p(s1), lo, hi,
                 self._ptrs["flags"], self._k, 3, C.c_void_p(eng.loss_acc.data_ptr() + 8), eng._stream()))
             eng.launches += 1
+
+    def trace_exchange(self, on=True):
+        """Switch the phase stamps of the exchange kernel on/off (kge_set_exchange_trace); read them with
+        exchange_phases_us() after a synchronised step."""
+        C = self._C
+        self._trace = torch.zeros(8, dtype=torch.int64, device=self.eng.device) if on else None
+        self._lib.check(self.eng.lib.kge_set_exchange_trace(self.eng.h, C.c_void_p(self._trace.data_ptr() if on else 0)))
+
+    def exchange_phases_us(self):
+        """-> dict of the last exchange launch's phase durations in microseconds (needs trace_exchange(True))."""
+        t = self._trace.cpu().tolist()
+        d = lambda a, b: (t[b] - t[a]) / 1e3
+        return {"zero_next_gradient_block": d(0, 1), "entry_barrier_wait": d(1, 2), "reduce_scatter_optimizer_all_gather": d(2, 3),
+                "cta0_fence_and_report": d(3, 4), "wait_for_last_cta": d(4, 5), "exit_flag_exchange": d(5, 6), "kernel_total": d(0, 6)}
 
     def reduce_loss_(self):
         """SUM the [batch loss, regulariser loss] accumulators over ranks (for logging).  p2p: every rank holds its shard of

@@ -46,6 +46,10 @@ WORKLOADS = {
                  n_triples=None, batch=8192, optimizer="lazy_adam", lr=1e-3),
 }
 CFG = WORKLOADS["cfg2"]
+# Multi-GPU parity: the two runs sum the same fp32 gradient contributions in a different order, and Adam turns a relative
+# gradient difference d into an update difference of about lr*d per step whatever the size of the parameter -- so the
+# absolute tolerance is stated relative to how far the parameters MOVED (a missing contribution would be O(1) of that).
+PARITY_ATOL_OF_UPDATE = 2e-3
 
 
 def internal_k(c):
@@ -341,7 +345,7 @@ def extra_dp_parity(make_engine, dev, rank, world, ent0, rel0, data_np, steps=3)
     """K data-parallel steps vs the same K steps on ONE GPU on the concatenated batch (rank 0 runs the single-GPU side)."""
     import torch
     import torch.distributed as dist
-    from ampligraph_b200.parallel import DataParallelTrainer
+    from ampligraph_b200.parallel import DataParallelTrainer, tables_close
     c, B = CFG, CFG["batch"]
     eta = c["eta"]
     dp = DataParallelTrainer(make_engine, mode=os.environ.get("KGE_B200_DP_MODE", "auto"))
@@ -372,13 +376,13 @@ def extra_dp_parity(make_engine, dev, rank, world, ent0, rel0, data_np, steps=3)
         ref_e, ref_r = (x.cpu().numpy() for x in ref.get_embeddings())
         err = max(np.abs(got_e - ref_e).max() / max(np.abs(ref_e).max(), 1e-30), np.abs(got_r - ref_r).max() / max(np.abs(ref_r).max(), 1e-30))
         upd = max(np.abs(ref_e - ent0).max(), 1e-30)
-        ok = bool(np.allclose(got_e, ref_e, rtol=2e-4, atol=2e-6) and np.allclose(got_r, ref_r, rtol=2e-4, atol=2e-6)
+        ok = bool(tables_close(got_e, ref_e, ent0, 2e-4, PARITY_ATOL_OF_UPDATE)[0] and tables_close(got_r, ref_r, rel0, 2e-4, PARITY_ATOL_OF_UPDATE)[0]
                   and abs(loss - ref_loss) <= 1e-4 * abs(ref_loss) and bool((lo == hi).all().item()))
         out = {"steps": steps, "mode": dp.mode, "global_batch": world * B, "max_rel_err": float(err),
                "max_abs_err_over_max_update": float(max(np.abs(got_e - ref_e).max(), np.abs(got_r - ref_r).max()) / upd),
                "loss_rel_err": float(abs(loss - ref_loss) / abs(ref_loss)), "replicas_identical": bool((lo == hi).all().item()),
-               "ok": ok, "criterion": "tables allclose(rtol 2e-4, atol 2e-6) vs single-GPU on the concatenated batch, "
-                                      "summed loss within 1e-4, all replicas bit-identical"}
+               "ok": ok, "criterion": "tables allclose(rtol 2e-4, atol 2e-3 x the largest parameter update) vs single-GPU on the "
+                                      "concatenated batch, summed loss within 1e-4, all replicas bit-identical"}
         ref.close()
     dp.close()
     return out
@@ -390,7 +394,7 @@ def extra_sharded(name, dev, rank, world, flush, peak, n_ent=None, steps=5, warm
     import torch
     import torch.distributed as dist
     from ampligraph_b200.engine import KGEEngine
-    from ampligraph_b200.parallel import ShardedTrainer
+    from ampligraph_b200.parallel import ShardedTrainer, tables_close
     c = WORKLOADS[name]
     E = n_ent or c["n_ent"]
     B, eta, R = c["batch"], c["eta"], c["n_rel"]
@@ -425,12 +429,14 @@ def extra_sharded(name, dev, rank, world, flush, peak, n_ent=None, steps=5, warm
             ref_loss = ref.read_loss()
             ref_e, ref_r = (x.cpu().numpy() for x in ref.get_embeddings())
             err = max(np.abs(got_e - ref_e).max() / np.abs(ref_e).max(), np.abs(got_r - ref_r).max() / np.abs(ref_r).max())
-            ok = bool(np.allclose(got_e, ref_e, rtol=3e-4, atol=3e-6) and np.allclose(got_r, ref_r, rtol=3e-4, atol=3e-6)
+            upd = max(np.abs(ref_e - ent0).max(), 1e-30)
+            ok = bool(tables_close(got_e, ref_e, ent0, 3e-4, PARITY_ATOL_OF_UPDATE)[0] and tables_close(got_r, ref_r, rel0, 3e-4, PARITY_ATOL_OF_UPDATE)[0]
                       and abs(loss - ref_loss) <= 1e-4 * abs(ref_loss))
             out["sharded_parity"] = {"steps": parity_steps, "global_batch": world * B, "max_rel_err": float(err),
+                                     "max_abs_err_over_max_update": float(max(np.abs(got_e - ref_e).max(), np.abs(got_r - ref_r).max()) / upd),
                                      "loss_rel_err": float(abs(loss - ref_loss) / abs(ref_loss)), "ok": ok,
-                                     "criterion": "gathered shards allclose(rtol 3e-4, atol 3e-6) vs single-GPU on the "
-                                                  "concatenated batch, summed loss within 1e-4"}
+                                     "criterion": "gathered shards allclose(rtol 3e-4, atol 2e-3 x the largest parameter update) vs "
+                                                  "single-GPU on the concatenated batch, summed loss within 1e-4"}
             ref.close()
         tr.close()
         del tr
@@ -617,6 +623,31 @@ def main_ours(args):
                 return out
             guarded(extra, "cfg5_shape_single_gpu", cfg5_one)
         else:
+            def exchange_phases():
+                """phase stamps of the exchange kernel (kge_set_exchange_trace), 7 traced steps, median; every rank's total"""
+                if dp.mode not in ("p2p", "nvls"):
+                    return {"mode": dp.mode}
+                dp.trace_exchange(True)
+                rows = []
+                for i in range(7):
+                    flush.fill_(i)
+                    step(10_000 + i)
+                    sync_all()
+                    rows.append(dp.exchange_phases_us())
+                dp.trace_exchange(False)
+                med = {k: float(np.median([r[k] for r in rows])) for k in rows[0]}
+                tot = torch.tensor([med["kernel_total"]], dtype=torch.float64, device=dev)
+                allt = [torch.zeros_like(tot) for _ in range(world)]
+                dist.all_gather(allt, tot)
+                med["kernel_total_per_rank"] = [float(t.item()) for t in allt]
+                med["mode"] = dp.mode
+                med["note"] = ("%globaltimer stamps inside kge_optim_exchange_kernel, rank 0's view; entry_barrier_wait includes the "
+                               "skew between the ranks' train kernels")
+                return med
+            res = {}
+            guarded(res, "v", exchange_phases)
+            if rank == 0:
+                extra["exchange_phases_us"] = res["v"]
             res = {}
             guarded(res, "v", lambda: extra_dp_parity(make_engine, dev, rank, world, ent0, rel0, data_np))
             if rank == 0:
@@ -627,7 +658,7 @@ def main_ours(args):
                 extra["cfg4_row_sharded"] = res["v"]
             res = {}
             per = int(os.environ.get("KGE_BENCH_CFG5_ENT_PER_GPU", "1250000"))
-            nq = int(os.environ.get("KGE_BENCH_CFG5_RANK_B", "64"))
+            nq = int(os.environ.get("KGE_BENCH_CFG5_RANK_B", "1024"))
             guarded(res, "v", lambda: extra_sharded("cfg5", dev, rank, world, None, peak, n_ent=per * world, steps=4, warmup=2,
                                                     rank_queries=nq))
             if rank == 0:

@@ -298,6 +298,15 @@ int kge_optimizer_step_exchange(kge_handle *h, const kge_optimizer_config *opt_e
                                 int64_t row_end, uint32_t *const *peer_flags, uint32_t token, int32_t phases,
                                 double *reg_loss_dev, void *stream);
 
+/* Diagnostics for the call above: stamps_dev = 8 x uint64 of device memory (caller-owned, kept alive) that every
+ * following kge_optimizer_step_exchange launch overwrites with %globaltimer nanoseconds at its phase boundaries --
+ * [0] CTA 0 enters, [1] CTA 0 zeroed its part of the next gradient block, [2] CTA 0 passed the entry barrier (all ranks
+ * arrived), [3] CTA 0 finished its reduce-scatter/optimizer/all-gather share, [4] CTA 0 fenced and reported done,
+ * [5] the last CTA of the grid reported done and signals the peers, [6] every peer signalled: the kernel ends.
+ * NULL switches tracing off (the default; the kernel then executes no extra stores).  bench.py prints the phase
+ * breakdown of the data-parallel step from these. */
+int kge_set_exchange_trace(kge_handle *h, uint64_t *stamps_dev);
+
 /* The flag barrier alone (one tiny kernel): signal `token` into slot `slot` (0 or 1) of every rank's flag pad, then
  * wait until all ranks signalled.  Used by the row-sharded trainer around its local optimizer. */
 int kge_peer_barrier(kge_handle *h, int32_t world, int32_t rank, uint32_t *const *peer_flags, int32_t slot,

@@ -532,6 +532,36 @@ def test_regulariser_pair_and_l1_l2():
     eng.close()
 
 
+@pytest.mark.parametrize("model,k,eta", [("ComplEx", 200, 10), ("HolE", 50, 7), ("DistMult", 200, 32), ("ComplEx", 30, 1), ("DistMult", 7, 3)])
+def test_resident_fast_path_equals_general_kernel(model, k, eta, monkeypatch):
+    """kge_train_res_kernel (the resident trilinear fast path) against kge_train_kernel forced by KGE_B200_TRAIN_KERNEL=general:
+    identical arithmetic per score, so scores are bit-equal; gradients agree to atomic-order noise; both match the oracle
+    elsewhere (test_forward_backward_vs_oracle runs through the fast path by default)."""
+    rng = np.random.default_rng(71)
+    E, R, B = 900, 9, 777
+    ent, rel = _tables(model, E, R, k, rng, scale=0.3)
+    t = _triples(E, R, B, rng)
+    neg_ent, neg_keep = _negatives(E, B, eta, rng)
+    out = {}
+    for which in ("fast", "general"):
+        if which == "general":
+            monkeypatch.setenv("KGE_B200_TRAIN_KERNEL", "general")
+        else:
+            monkeypatch.delenv("KGE_B200_TRAIN_KERNEL", raising=False)
+        eng = _engine(model, k, eta, E, R, loss="self_adversarial")
+        assert eng.lib.kge_rows_resident(eng.h)
+        eng.set_embeddings(ent, rel)
+        sp = torch.empty(B, device="cuda"); sn = torch.empty(eta * B, device="cuda")
+        eng.forward_backward(_dev(t), (_dev(neg_ent), _dev(neg_keep)), scores_pos=sp, scores_neg=sn)
+        torch.cuda.synchronize()
+        out[which] = (sp.cpu().numpy(), sn.cpu().numpy(), eng.g_ent.cpu().numpy().copy(), eng.g_rel.cpu().numpy().copy(), eng.read_loss())
+        eng.close()
+    f, g = out["fast"], out["general"]
+    assert (f[0] == g[0]).all() and (f[1] == g[1]).all()
+    assert _close(f[2], g[2], rtol=2e-5) and _close(f[3], g[3], rtol=2e-5)
+    assert abs(f[4] - g[4]) <= 1e-6 * abs(g[4])
+
+
 def test_exchange_kernel_world1_equals_plain_optimizer():
     """kge_optimizer_step_exchange with world = 1 (peer pointers = own pointers, in-kernel flag barriers against itself)
     is the plain dense optimizer on the concatenated [ent|rel] block, zeroes the other gradient block and does not hang;

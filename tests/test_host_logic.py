@@ -326,3 +326,16 @@ def test_bench_arms_share_config_and_honour_steps():
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert "min(args.steps" not in src and "min(args.warmup" not in src
     assert set(bench.WORKLOADS) == {"cfg2", "cfg3", "cfg4", "cfg5"} and bench.WORKLOADS["cfg5"]["n_ent"] == 10_000_000
+
+
+def test_tables_close_is_relative_to_the_update():
+    """parallel.tables_close: the absolute tolerance scales with how far the parameters moved."""
+    from ampligraph_b200.parallel import tables_close
+    init = np.zeros((4, 8), np.float32)
+    ref = init + 3e-3                      # every parameter moved by 3e-3
+    ok, err = tables_close(ref + 4e-6, ref, init)      # 1.3e-3 of the update: summation-order noise
+    assert ok and 1e-3 < err < 2e-3
+    ok, err = tables_close(ref + 3e-5, ref, init)      # 1e-2 of the update: a real difference
+    assert not ok
+    lost = ref.copy(); lost[2] = init[2]               # a row whose update was lost
+    assert not tables_close(lost, ref, init)[0]
