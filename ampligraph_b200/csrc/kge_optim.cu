@@ -308,16 +308,16 @@ __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeA
     const long long nthreads = (long long)gridDim.x * blockDim.x;
 
     KGE_TRACE(0, blockIdx.x == 0);
+    // phase 1a: announce this rank's arrival FIRST.  The release only has to cover the training kernel's gradient
+    // scatters (complete at the kernel boundary); issued after the zeroing below it would also wait for those stores.
+    if ((x.phases & 1) && threadIdx.x < 32) flags_signal(x.flags, WORLD, rank, 0, x.token, threadIdx.x);
     // zero the next step's local gradient block: independent of the peers, overlaps the barrier wait
     if (x.zero_grad)
         for (long long i = tid; i < x.total4; i += nthreads) __stcg(x.zero_grad + i, z);
     KGE_TRACE(1, blockIdx.x == 0);
 
-    if (x.phases & 1) {
-        if (threadIdx.x < 32) {
-            flags_signal(x.flags, WORLD, rank, 0, x.token, threadIdx.x);
-            flags_wait(x.flags, WORLD, rank, 0, x.token, threadIdx.x);
-        }
+    if (x.phases & 1) {  // phase 1b: every rank has entered the kernel
+        if (threadIdx.x < 32) flags_wait(x.flags, WORLD, rank, 0, x.token, threadIdx.x);
         __syncthreads();
     }
     KGE_TRACE(2, blockIdx.x == 0);

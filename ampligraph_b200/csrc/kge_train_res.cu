@@ -11,6 +11,8 @@
 // one 64-bit base per row plus the lane's byte offset, the shard/window/group machinery does not exist, and the
 // corruption sort is one ballot pair.  Arithmetic per element is identical to the general kernel's (same f32x2 FMAs in
 // the same order), so both produce the same scores; gradients differ only in the order of the fp32 atomics.
+#include <stdlib.h>
+
 #include "kge_train_common.cuh"
 
 namespace kge {
@@ -64,6 +66,16 @@ __device__ __forceinline__ void bulk_load_s(uint32_t smem_dst, const void *gmem_
                  "l"(gmem_src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void sts4(uint32_t a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// shared::cta -> global, element-wise fp32 add performed by the copy engine / L2 (SASS UBLKRED): no LSU lane slots
+__device__ __forceinline__ void bulk_reduce_add_s(void *gmem_dst, uint32_t smem_src, uint32_t bytes)
+{
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes)
+                 : "memory");
+}
 // The front end rematerialises cheap values (kernel parameters, %tid-derived addresses) inside the long per-positive
 // loop instead of keeping them in registers -- a dozen ld.param / shift / mad per trip of the inner loops.  Passing a
 // value through an empty asm makes it opaque: it is computed once and stays in its register.
@@ -78,7 +90,12 @@ __device__ __forceinline__ void red4(char *row, uint32_t byte_off, float4 v) { r
 // the end of the row read its last chunk with zero query vectors (exact zeros in every sum) and never store.
 // Shared-memory slot of a warp (same carve-up as kge_train_kernel, computed by kge_create):
 //   [ s | p | o | eta replaced rows ] [ sc: eta_pad floats ] [ nid ] [ (unused) ] [ jorig ] [ mbarrier ]
-template <int HALVES, int NIT, int THREADS>
+// SPLIT: how the gradient rows of the replaced entities leave the SM.  The kernel is bound by the LSU's RED rate (about one
+// lane-atomic per 1.3 cycles per SM whatever its width: 13 rows x 100 float4 per positive = 157 us for cfg2, measured
+// 150 us), so part of the rows takes the OTHER road to L2: the gradient row g*Q overwrites the gathered row in the slot
+// (st.shared.v4, 4 cycles per 512 B) and the copy engine adds the whole row with cp.reduce.async.bulk (UBLKRED).
+//   0: every row by red.global.add.v4.f32;  1: the second row of every pair by bulk reduce;  2: all replaced rows by bulk reduce.
+template <int HALVES, int NIT, int THREADS, int SPLIT>
 __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -157,6 +174,7 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
 
         // ---- gather (A2): one bulk copy per row, s | p | o | replaced rows in slot order ----
         const int nrow = 3 + eta;
+        if constexpr (SPLIT > 0) bulk_wait_read_all();  // the copy engine has read the previous positive's staged gradient rows
         if (lane == 0) mbar_expect_tx_s(bar_s, (uint32_t)nrow * row_bytes);
         __syncwarp();
         for (int r = lane; r < nrow; r += 32) {
@@ -288,6 +306,15 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
                 if constexpr (HALVES == 2) red_add_v4(reinterpret_cast<float *>(g1 + 512 * it), g * qi[it]);
             }
         };
+        // the same row for the copy engine: g * Q overwrites the gathered row (each lane writes only the chunks it alone reads)
+        auto stage_row = [&](uint32_t r, float g, const float4(&qr)[NIT], const float4(&qi)[NIT]) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                if (!live[it]) break;
+                sts4(r + off[it], g * qr[it]);
+                if constexpr (HALVES == 2) sts4(r + off[it] + hsB, g * qi[it]);
+            }
+        };
         auto grad_side = [&](int lo, int hi, const float4(&qr)[NIT], const float4(&qi)[NIT], float4(&Wr)[NIT], float4(&Wi)[NIT]) {
             for (int t = lo; t < hi; t += 2) {
                 const bool has_b = t + 1 < hi;
@@ -308,12 +335,24 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
                         Wi[it] = f4fma(gb, bi, Wi[it]);
                     }
                 }
-                red_row(ida, ga, qr, qi);
-                if (has_b) red_row(idb, gb, qr, qi);
+                if constexpr (SPLIT == 2) stage_row(ra, ga, qr, qi); else red_row(ida, ga, qr, qi);
+                if (has_b) {
+                    if constexpr (SPLIT >= 1) stage_row(rb, gb, qr, qi); else red_row(idb, gb, qr, qi);
+                }
             }
         };
         grad_side(0, n0, Q0r, Q0i, W0r, W0i);
         grad_side(n0, eta, Q1r, Q1i, W1r, W1i);
+        if constexpr (SPLIT > 0) {
+            fence_proxy_async_smem();  // the staged rows (generic proxy) are visible to the copy engine (async proxy)
+            __syncwarp();
+            if (lane < eta) {
+                const int rel_t = lane < n0 ? lane : lane - n0;  // position inside its side: pairs are (even, odd)
+                if (SPLIT == 2 || (rel_t & 1))
+                    bulk_reduce_add_s(grad_ent + (size_t)lds_i(nid_s + 4u * (uint32_t)lane) * ld, rows_s + (uint32_t)(3 + lane) * lwB, row_bytes);
+            }
+            bulk_commit();
+        }
 
         // ---- gradient rows of s, p, o: bilinearity folds every corruption's share into W ----
         {
@@ -345,6 +384,7 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
         }
         __syncwarp();  // every lane has read the slot before the next positive's gather overwrites it
     }
+    if constexpr (SPLIT > 0) bulk_wait_all();
     if (p.loss_out && p.mode == KGE_STEP_FUSED && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_out, loss_acc);
 }
 
@@ -355,11 +395,11 @@ bool train_res_applicable(const TrainParams &p, int nit)
     return trilinear && p.resident && p.shard_world <= 1 && p.eta <= 32 && p.stash == nullptr && nit <= 2 && p.n_cb == 1;
 }
 
-template <int HALVES, int NIT>
+template <int HALVES, int NIT, int SPLIT>
 static cudaError_t launch_res(const TrainParams &p, int sm_count, int threads, size_t smem, cudaStream_t st)
 {
     constexpr int THREADS = KGE_TRAIN_THREADS(KGE_COMPLEX, NIT);
-    auto kern = kge_train_res_kernel<HALVES, NIT, THREADS>;
+    auto kern = kge_train_res_kernel<HALVES, NIT, THREADS, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -371,12 +411,30 @@ static cudaError_t launch_res(const TrainParams &p, int sm_count, int threads, s
     return cudaGetLastError();
 }
 
+template <int SPLIT>
+static cudaError_t launch_res_split(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st)
+{
+    const bool two = p.model != KGE_DISTMULT;
+    if (nit <= 1) return two ? launch_res<2, 1, SPLIT>(p, sm_count, threads, smem, st) : launch_res<1, 1, SPLIT>(p, sm_count, threads, smem, st);
+    return two ? launch_res<2, 2, SPLIT>(p, sm_count, threads, smem, st) : launch_res<1, 2, SPLIT>(p, sm_count, threads, smem, st);
+}
+
+// default split of the gradient scatter between the LSU (red.global) and the copy engine (cp.reduce.async.bulk);
+// KGE_B200_SCATTER_SPLIT=0|1|2 overrides (A/B runs, tests of every instantiation)
+#ifndef KGE_DEFAULT_SCATTER_SPLIT
+#define KGE_DEFAULT_SCATTER_SPLIT 0
+#endif
+
 cudaError_t launch_train_res(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st)
 {
     if (p.B == 0) return cudaSuccess;
-    const bool two = p.model != KGE_DISTMULT;
-    if (nit <= 1) return two ? launch_res<2, 1>(p, sm_count, threads, smem, st) : launch_res<1, 1>(p, sm_count, threads, smem, st);
-    return two ? launch_res<2, 2>(p, sm_count, threads, smem, st) : launch_res<1, 2>(p, sm_count, threads, smem, st);
+    int split = KGE_DEFAULT_SCATTER_SPLIT;
+    if (const char *e = getenv("KGE_B200_SCATTER_SPLIT")) split = atoi(e);
+    switch (split) {
+    case 1: return launch_res_split<1>(p, nit, sm_count, threads, smem, st);
+    case 2: return launch_res_split<2>(p, nit, sm_count, threads, smem, st);
+    default: return launch_res_split<0>(p, nit, sm_count, threads, smem, st);
+    }
 }
 
 }  // namespace kge
