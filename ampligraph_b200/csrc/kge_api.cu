@@ -1,6 +1,7 @@
 // kge_api.cu -- the extern "C" boundary of libkge_b200.so (see include/kge_b200.h).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -22,6 +23,7 @@ struct kge_handle {
     unsigned long long *exchange_trace;  // caller-owned 8 x uint64 phase stamps of the next exchange launches, or nullptr
     // training launch geometry
     int nit, G, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats, resident;
+    int res_warps, res_rows_bytes, res_region_bytes;  // slot geometry of the resident trilinear fast path (kge_train_res.cu); res_warps = 0: not applicable
     int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
     float *stash;                // caller-owned row stash for sharded runs (kge_set_row_stash) or nullptr
     long long stash_rows;
@@ -162,6 +164,21 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     int warps = h->max_smem / h->region_bytes;
     if (warps > max_warps) warps = max_warps;
     h->warps = warps;  // 0 => even (3+1) windows do not fit (reported by kge_train_step)
+
+    // ---- the resident trilinear fast path (kge_train_res.cu): DistMult / ComplEx / HolE, one window, eta <= 32; its slot
+    // holds s, o and the eta replaced rows (the relation row lives in registers) + sc | nid | jorig + one mbarrier.
+    // Same residency rule as above, with its own (one row smaller) slot.
+    h->res_warps = 0;
+    if ((cfg->scoring == KGE_DISTMULT || cfg->scoring == KGE_COMPLEX || cfg->scoring == KGE_HOLE) && h->n_cb == 1 &&
+        h->nit <= 2 && cfg->eta <= 32 && cfg->neg_group <= 0) {
+        const int res_aux = (3 * h->eta_pad * 4 + 8 + 15) / 16 * 16;
+        h->res_rows_bytes = (2 + cfg->eta) * row_bytes;
+        h->res_region_bytes = h->res_rows_bytes + res_aux;
+        int rw = h->max_smem / h->res_region_bytes;
+        if (rw > max_warps) rw = max_warps;
+        const int min_res = max_warps < KGE_MIN_RESIDENT_WARPS ? max_warps : KGE_MIN_RESIDENT_WARPS;
+        if (rw >= min_res) h->res_warps = rw;
+    }
 
     if (cfg->scoring == KGE_ROTATE) {
         cudaError_t e2 = cudaMalloc(&h->rot, (size_t)cfg->n_rel * L.ld * sizeof(float));
@@ -383,6 +400,16 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
             p.stamp_ent_shard[q] = map->stamp_ent[q];
             if (!map->stamp_ent[q]) p.stamp_ent = nullptr;  // all or nothing
         }
+    }
+    // KGE_B200_TRAIN_KERNEL=general keeps every shape on the general kernel (A/B runs, and the tests that cover its resident
+    // trilinear instantiations); default: the specialised kernel of kge_train_res.cu where it applies
+    const char *force = getenv("KGE_B200_TRAIN_KERNEL");
+    if (h->res_warps > 0 && p.shard_world <= 1 && p.stash == nullptr && !(force && strcmp(force, "general") == 0)) {
+        p.rows_bytes = h->res_rows_bytes;
+        p.region_bytes = h->res_region_bytes;
+        KGE_CUDA(launch_train_res(p, h->nit, h->sm_count, h->res_warps * 32, (size_t)h->res_warps * h->res_region_bytes, st),
+                 "kge_train_step");
+        return KGE_OK;
     }
     KGE_CUDA(launch_train(p, h->nit, h->sm_count, h->warps * 32, (size_t)h->warps * h->region_bytes, st),
              "kge_train_step");

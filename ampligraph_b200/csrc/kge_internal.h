@@ -47,8 +47,8 @@ struct TrainParams {
 
 // grid = min(occupancy * sm_count, ceil(B / warps))
 cudaError_t launch_train(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st);
-// kge_train_res.cu: the resident trilinear fast path (DistMult / ComplEx / HolE, all rows of a positive resident, eta <= 32, one table)
-bool train_res_applicable(const TrainParams &p, int nit);
+// kge_train_res.cu: the resident trilinear fast path (DistMult / ComplEx / HolE, all rows of a positive resident, eta <= 32, one
+// table); p.rows_bytes / p.region_bytes carry ITS slot geometry (kge_create: res_*), threads = res_warps * 32
 cudaError_t launch_train_res(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_rotation_table(const float *rel, float *rot, long long n_rel, int kp, int ld, float div,
                                   cudaStream_t st);

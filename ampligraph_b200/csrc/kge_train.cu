@@ -22,8 +22,6 @@
 // moves once: (3+eta) rows in, (3+eta) gradient rows out = 2(3+eta)*ld*4 bytes
 // per positive.
 #include <math.h>
-#include <stdlib.h>
-#include <string.h>
 
 #include <type_traits>
 
@@ -539,6 +537,8 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
     const int lw = p.slot_floats;              // slot stride (>= HALVES*wk)
     const int n_cb = RESIDENT ? 1 : p.n_cb;    // column windows per row
     const int n_groups = RESIDENT ? 1 : (eta + G - 1) / G;
+    // (making these loop invariants opaque to the front end, as kge_train_res.cu does, changes nothing here:
+    // cfg3 131 -> 133 us, cfg4 / cfg5w unchanged, profiles/r2f_kbench_general_keep.log)
     constexpr bool resident = RESIDENT;
     // slot: s, p, o windows, then group buffer 0 and (non-resident only) group buffer 1: the next group is
     // gathered while the current one is being processed, which hides the gather latency (NVLink latency
@@ -860,11 +860,6 @@ static cudaError_t launch_train_model(const TrainParams &p, int nit, int sm_coun
 cudaError_t launch_train(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st)
 {
     if (p.B == 0) return cudaSuccess;
-    // KGE_B200_TRAIN_KERNEL=general keeps every shape on this file's kernel (A/B runs, and the tests that cover its
-    // resident trilinear instantiations); default: the specialised kernel of kge_train_res.cu where it applies
-    const char *force = getenv("KGE_B200_TRAIN_KERNEL");
-    if (train_res_applicable(p, nit) && !(force && strcmp(force, "general") == 0))
-        return launch_train_res(p, nit, sm_count, threads, smem, st);
     switch (p.model) {
     case KGE_TRANSE: return launch_train_model<KGE_TRANSE>(p, nit, sm_count, threads, smem, st);
     case KGE_DISTMULT: return launch_train_model<KGE_DISTMULT>(p, nit, sm_count, threads, smem, st);

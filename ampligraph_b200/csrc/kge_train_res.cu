@@ -11,8 +11,6 @@
 // one 64-bit base per row plus the lane's byte offset, the shard/window/group machinery does not exist, and the
 // corruption sort is one ballot pair.  Arithmetic per element is identical to the general kernel's (same f32x2 FMAs in
 // the same order), so both produce the same scores; gradients differ only in the order of the fp32 atomics.
-#include <stdlib.h>
-
 #include "kge_train_common.cuh"
 
 namespace kge {
@@ -66,16 +64,6 @@ __device__ __forceinline__ void bulk_load_s(uint32_t smem_dst, const void *gmem_
                  "l"(gmem_src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void sts4(uint32_t a, float4 v)
-{
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-// shared::cta -> global, element-wise fp32 add performed by the copy engine / L2 (SASS UBLKRED): no LSU lane slots
-__device__ __forceinline__ void bulk_reduce_add_s(void *gmem_dst, uint32_t smem_src, uint32_t bytes)
-{
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes)
-                 : "memory");
-}
 // The front end rematerialises cheap values (kernel parameters, %tid-derived addresses) inside the long per-positive
 // loop instead of keeping them in registers -- a dozen ld.param / shift / mad per trip of the inner loops.  Passing a
 // value through an empty asm makes it opaque: it is computed once and stays in its register.
@@ -88,14 +76,16 @@ __device__ __forceinline__ void red4(char *row, uint32_t byte_off, float4 v) { r
 // HALVES = 1: DistMult (f = sum s p o, DistMult.py:48); HALVES = 2: ComplEx / HolE (ComplEx.py:52-62; HolE.py:45 scales by
 // 2/k, folded into the gradient scalars).  Lane l owns float4 chunks c = l + 32*it (it < NIT) of every half-row; lanes past
 // the end of the row read its last chunk with zero query vectors (exact zeros in every sum) and never store.
-// Shared-memory slot of a warp (same carve-up as kge_train_kernel, computed by kge_create):
-//   [ s | p | o | eta replaced rows ] [ sc: eta_pad floats ] [ nid ] [ (unused) ] [ jorig ] [ mbarrier ]
-// SPLIT: how the gradient rows of the replaced entities leave the SM.  The kernel is bound by the LSU's RED rate (about one
-// lane-atomic per 1.3 cycles per SM whatever its width: 13 rows x 100 float4 per positive = 157 us for cfg2, measured
-// 150 us), so part of the rows takes the OTHER road to L2: the gradient row g*Q overwrites the gathered row in the slot
-// (st.shared.v4, 4 cycles per 512 B) and the copy engine adds the whole row with cp.reduce.async.bulk (UBLKRED).
-//   0: every row by red.global.add.v4.f32;  1: the second row of every pair by bulk reduce;  2: all replaced rows by bulk reduce.
-template <int HALVES, int NIT, int THREADS, int SPLIT>
+// Shared-memory slot of a warp (kge_create: res_rows_bytes / res_region_bytes):
+//   [ s | o | eta replaced rows ] [ sc: eta_pad floats ] [ nid ] [ jorig ] [ mbarrier ]
+// The relation row is NOT staged: each lane loads its chunks of p straight into registers (ld.global.nc, issued before
+// the wait for the gather, so the latency hides behind it) and keeps them until the gradient rows of s, p, o are formed.
+// One row less per positive is what lets a 12th warp fit beside cfg2's 11 (12 x (12 x 1600 + 160) B = 226.9 KB).
+// Gradient rows leave the SM as red.global.add.v4.f32 straight from registers.  Sending part of them down the copy
+// engine's road instead (g*Q staged over the gathered row with st.shared.v4, one cp.reduce.async.bulk per row) was
+// measured on B200 and is slower: cfg2 152 us -> 170 us with every second replaced row, 178 us with all of them
+// (profiles/r2d_kbench_scatter_split*.log); without any scatter the kernel takes 123 us (r2d_kbench_noscatter_fast.log).
+template <int HALVES, int NIT, int THREADS>
 __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -105,7 +95,7 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
     uint32_t rows_s = smem_u32(smem_raw) + (uint32_t)warp * (uint32_t)p.region_bytes;
     uint32_t sc_s = rows_s + (uint32_t)p.rows_bytes;
     uint32_t nid_s = sc_s + 4u * (uint32_t)p.eta_pad;
-    uint32_t jor_s = nid_s + 8u * (uint32_t)p.eta_pad;
+    uint32_t jor_s = nid_s + 4u * (uint32_t)p.eta_pad;
     uint32_t bar_s = jor_s + 4u * (uint32_t)p.eta_pad;
     KGE_KEEP32(rows_s); KGE_KEEP32(sc_s); KGE_KEEP32(nid_s); KGE_KEEP32(jor_s); KGE_KEEP32(bar_s);
     float *const sc = reinterpret_cast<float *>(smem_raw + (size_t)warp * p.region_bytes + p.rows_bytes);  // for loss_and_dscores
@@ -173,14 +163,23 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
         __syncwarp();
 
         // ---- gather (A2): one bulk copy per row, s | p | o | replaced rows in slot order ----
-        const int nrow = 3 + eta;
-        if constexpr (SPLIT > 0) bulk_wait_read_all();  // the copy engine has read the previous positive's staged gradient rows
+        const int nrow = 2 + eta;
         if (lane == 0) mbar_expect_tx_s(bar_s, (uint32_t)nrow * row_bytes);
         __syncwarp();
         for (int r = lane; r < nrow; r += 32) {
-            const int id = r == 0 ? s_id : r == 1 ? p_id : r == 2 ? o_id : lds_i(nid_s + 4u * (uint32_t)(r - 3));
-            const float *src = (r == 1 ? p.rel : p.ent) + (size_t)id * ld;
-            bulk_load_s(rows_s + (uint32_t)r * lwB, src, row_bytes, bar_s);
+            const int id = r == 0 ? s_id : r == 1 ? o_id : lds_i(nid_s + 4u * (uint32_t)(r - 2));
+            bulk_load_s(rows_s + (uint32_t)r * lwB, p.ent + (size_t)id * ld, row_bytes, bar_s);
+        }
+        // this lane's chunks of the relation row, straight to registers
+        float4 pr[NIT], pi[NIT];
+        {
+            const char *prow = reinterpret_cast<const char *>(p.rel + (size_t)p_id * ld);
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                pr[it] = __ldg(reinterpret_cast<const float4 *>(prow + off[it]));
+                if constexpr (HALVES == 2) pi[it] = __ldg(reinterpret_cast<const float4 *>(prow + off[it] + hsB));
+                if (!live[it]) { pr[it] = f4zero(); pi[it] = f4zero(); }  // every query vector carries a factor of p
+            }
         }
         char *const gs_row = reinterpret_cast<char *>(grad_ent + (size_t)s_id * ld);
         char *const gp_row = reinterpret_cast<char *>(p.grad_rel + (size_t)p_id * ld);
@@ -200,22 +199,18 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
                 const uint32_t a = rows_s + off[it];
                 if constexpr (HALVES == 2) {
                     const float4 sr = lds4(a), si = lds4(a + hsB);
-                    float4 pr = lds4(a + lwB), pi = lds4(a + lwB + hsB);
-                    const float4 orr = lds4(a + 2u * lwB), oi = lds4(a + 2u * lwB + hsB);
-                    if (!live[it]) { pr = f4zero(); pi = f4zero(); }  // every query vector carries a factor of p
-                    Q0r[it] = f4fma(pi, oi, pr * orr);
-                    Q0i[it] = pr * oi - pi * orr;
-                    Q1r[it] = sr * pr - si * pi;
-                    Q1i[it] = f4fma(sr, pi, si * pr);
+                    const float4 orr = lds4(a + lwB), oi = lds4(a + lwB + hsB);
+                    Q0r[it] = f4fma(pi[it], oi, pr[it] * orr);
+                    Q0i[it] = pr[it] * oi - pi[it] * orr;
+                    Q1r[it] = sr * pr[it] - si * pi[it];
+                    Q1i[it] = f4fma(sr, pi[it], si * pr[it]);
                     acc = f4fma(sr, Q0r[it], acc);
                     acc = f4fma(si, Q0i[it], acc);
                     W0i[it] = W1i[it] = f4zero();
                 } else {
-                    const float4 vs = lds4(a), vo = lds4(a + 2u * lwB);
-                    float4 vp = lds4(a + lwB);
-                    if (!live[it]) vp = f4zero();
-                    Q0r[it] = vp * vo;
-                    Q1r[it] = vs * vp;
+                    const float4 vs = lds4(a), vo = lds4(a + lwB);
+                    Q0r[it] = pr[it] * vo;
+                    Q1r[it] = vs * pr[it];
                     acc = f4fma(vs, Q0r[it], acc);
                 }
                 W0r[it] = W1r[it] = f4zero();
@@ -227,7 +222,7 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
         auto score_side = [&](int lo, int hi, const float4(&qr)[NIT], const float4(&qi)[NIT]) {
             int t = lo;
             for (; hi - t >= 3; t += 4) {
-                const uint32_t r0 = rows_s + (uint32_t)(3 + t) * lwB, r1 = r0 + lwB, r2 = r1 + lwB;
+                const uint32_t r0 = rows_s + (uint32_t)(2 + t) * lwB, r1 = r0 + lwB, r2 = r1 + lwB;
                 const uint32_t r3 = (t + 3 < hi) ? r2 + lwB : r2;  // a trip of three: the fourth row aliases the third and is dropped
                 float4 a = f4zero(), b = f4zero(), c = f4zero(), d = f4zero();
 #pragma unroll
@@ -250,7 +245,7 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
             }
             if (t < hi) {  // one or two rows left
                 const bool has_b = t + 1 < hi;
-                const uint32_t ra = rows_s + (uint32_t)(3 + t) * lwB, rb = has_b ? ra + lwB : ra;
+                const uint32_t ra = rows_s + (uint32_t)(2 + t) * lwB, rb = has_b ? ra + lwB : ra;
                 float4 a = f4zero(), b = f4zero();
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
@@ -306,20 +301,11 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
                 if constexpr (HALVES == 2) red_add_v4(reinterpret_cast<float *>(g1 + 512 * it), g * qi[it]);
             }
         };
-        // the same row for the copy engine: g * Q overwrites the gathered row (each lane writes only the chunks it alone reads)
-        auto stage_row = [&](uint32_t r, float g, const float4(&qr)[NIT], const float4(&qi)[NIT]) {
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                if (!live[it]) break;
-                sts4(r + off[it], g * qr[it]);
-                if constexpr (HALVES == 2) sts4(r + off[it] + hsB, g * qi[it]);
-            }
-        };
         auto grad_side = [&](int lo, int hi, const float4(&qr)[NIT], const float4(&qi)[NIT], float4(&Wr)[NIT], float4(&Wi)[NIT]) {
             for (int t = lo; t < hi; t += 2) {
                 const bool has_b = t + 1 < hi;
                 const uint32_t tb = (uint32_t)(has_b ? t + 1 : t);
-                const uint32_t ra = rows_s + (uint32_t)(3 + t) * lwB, rb = rows_s + (3u + tb) * lwB;
+                const uint32_t ra = rows_s + (uint32_t)(2 + t) * lwB, rb = rows_s + (2u + tb) * lwB;
                 const float ga = scale * lds_f(sc_s + 4u * (uint32_t)t);
                 const float gb = has_b ? scale * lds_f(sc_s + 4u * tb) : 0.f;
                 const int ida = lds_i(nid_s + 4u * (uint32_t)t), idb = lds_i(nid_s + 4u * tb);
@@ -335,24 +321,12 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
                         Wi[it] = f4fma(gb, bi, Wi[it]);
                     }
                 }
-                if constexpr (SPLIT == 2) stage_row(ra, ga, qr, qi); else red_row(ida, ga, qr, qi);
-                if (has_b) {
-                    if constexpr (SPLIT >= 1) stage_row(rb, gb, qr, qi); else red_row(idb, gb, qr, qi);
-                }
+                red_row(ida, ga, qr, qi);
+                if (has_b) red_row(idb, gb, qr, qi);
             }
         };
         grad_side(0, n0, Q0r, Q0i, W0r, W0i);
         grad_side(n0, eta, Q1r, Q1i, W1r, W1i);
-        if constexpr (SPLIT > 0) {
-            fence_proxy_async_smem();  // the staged rows (generic proxy) are visible to the copy engine (async proxy)
-            __syncwarp();
-            if (lane < eta) {
-                const int rel_t = lane < n0 ? lane : lane - n0;  // position inside its side: pairs are (even, odd)
-                if (SPLIT == 2 || (rel_t & 1))
-                    bulk_reduce_add_s(grad_ent + (size_t)lds_i(nid_s + 4u * (uint32_t)lane) * ld, rows_s + (uint32_t)(3 + lane) * lwB, row_bytes);
-            }
-            bulk_commit();
-        }
 
         // ---- gradient rows of s, p, o: bilinearity folds every corruption's share into W ----
         {
@@ -363,43 +337,35 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
                 const uint32_t o = off[it], a = rows_s + o;
                 if constexpr (HALVES == 2) {
                     const float4 sr = lds4(a), si = lds4(a + hsB);
-                    const float4 pr = lds4(a + lwB), pi = lds4(a + lwB + hsB);
-                    const float4 orr = lds4(a + 2u * lwB), oi = lds4(a + 2u * lwB + hsB);
+                    const float4 orr = lds4(a + lwB), oi = lds4(a + lwB + hsB);
                     const float4 Ur = f4fma(gP, sr, W0r[it]), Ui = f4fma(gP, si, W0i[it]);    // everything that sat in the subject slot
                     const float4 Xr = f4fma(gP, orr, W1r[it]), Xi = f4fma(gP, oi, W1i[it]);   // everything that sat in the object slot
-                    red4(gs_row, o, f4fma(pi, Xi, pr * Xr));                                  // d/ds f(s,p,X)
-                    red4(gs_row, o + hsB, pr * Xi - pi * Xr);
-                    red4(go_row, o, Ur * pr - Ui * pi);                                       // d/do f(U,p,o)
-                    red4(go_row, o + hsB, f4fma(Ur, pi, Ui * pr));
+                    red4(gs_row, o, f4fma(pi[it], Xi, pr[it] * Xr));                          // d/ds f(s,p,X)
+                    red4(gs_row, o + hsB, pr[it] * Xi - pi[it] * Xr);
+                    red4(go_row, o, Ur * pr[it] - Ui * pi[it]);                               // d/do f(U,p,o)
+                    red4(go_row, o + hsB, f4fma(Ur, pi[it], Ui * pr[it]));
                     red4(gp_row, o, f4fma(Ur, orr, Ui * oi) + f4fma(sr, W1r[it], si * W1i[it]));   // d/dp [f(U,p,o) + f(s,p,W1)]
                     red4(gp_row, o + hsB, (Ur * oi - Ui * orr) + (sr * W1i[it] - si * W1r[it]));
                 } else {
-                    const float4 vs = lds4(a), vp = lds4(a + lwB), vo = lds4(a + 2u * lwB);
+                    const float4 vs = lds4(a), vo = lds4(a + lwB);
                     const float4 U = f4fma(gP, vs, W0r[it]), X = f4fma(gP, vo, W1r[it]);
-                    red4(gs_row, o, vp * X);
-                    red4(go_row, o, U * vp);
+                    red4(gs_row, o, pr[it] * X);
+                    red4(go_row, o, U * pr[it]);
                     red4(gp_row, o, f4fma(U, vo, vs * W1r[it]));
                 }
             }
         }
         __syncwarp();  // every lane has read the slot before the next positive's gather overwrites it
     }
-    if constexpr (SPLIT > 0) bulk_wait_all();
     if (p.loss_out && p.mode == KGE_STEP_FUSED && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_out, loss_acc);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
-bool train_res_applicable(const TrainParams &p, int nit)
-{
-    const bool trilinear = p.model == KGE_DISTMULT || p.model == KGE_COMPLEX || p.model == KGE_HOLE;
-    return trilinear && p.resident && p.shard_world <= 1 && p.eta <= 32 && p.stash == nullptr && nit <= 2 && p.n_cb == 1;
-}
-
-template <int HALVES, int NIT, int SPLIT>
+template <int HALVES, int NIT>
 static cudaError_t launch_res(const TrainParams &p, int sm_count, int threads, size_t smem, cudaStream_t st)
 {
     constexpr int THREADS = KGE_TRAIN_THREADS(KGE_COMPLEX, NIT);
-    auto kern = kge_train_res_kernel<HALVES, NIT, THREADS, SPLIT>;
+    auto kern = kge_train_res_kernel<HALVES, NIT, THREADS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -411,30 +377,12 @@ static cudaError_t launch_res(const TrainParams &p, int sm_count, int threads, s
     return cudaGetLastError();
 }
 
-template <int SPLIT>
-static cudaError_t launch_res_split(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st)
-{
-    const bool two = p.model != KGE_DISTMULT;
-    if (nit <= 1) return two ? launch_res<2, 1, SPLIT>(p, sm_count, threads, smem, st) : launch_res<1, 1, SPLIT>(p, sm_count, threads, smem, st);
-    return two ? launch_res<2, 2, SPLIT>(p, sm_count, threads, smem, st) : launch_res<1, 2, SPLIT>(p, sm_count, threads, smem, st);
-}
-
-// default split of the gradient scatter between the LSU (red.global) and the copy engine (cp.reduce.async.bulk);
-// KGE_B200_SCATTER_SPLIT=0|1|2 overrides (A/B runs, tests of every instantiation)
-#ifndef KGE_DEFAULT_SCATTER_SPLIT
-#define KGE_DEFAULT_SCATTER_SPLIT 0
-#endif
-
 cudaError_t launch_train_res(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st)
 {
     if (p.B == 0) return cudaSuccess;
-    int split = KGE_DEFAULT_SCATTER_SPLIT;
-    if (const char *e = getenv("KGE_B200_SCATTER_SPLIT")) split = atoi(e);
-    switch (split) {
-    case 1: return launch_res_split<1>(p, nit, sm_count, threads, smem, st);
-    case 2: return launch_res_split<2>(p, nit, sm_count, threads, smem, st);
-    default: return launch_res_split<0>(p, nit, sm_count, threads, smem, st);
-    }
+    const bool two = p.model != KGE_DISTMULT;
+    if (nit <= 1) return two ? launch_res<2, 1>(p, sm_count, threads, smem, st) : launch_res<1, 1>(p, sm_count, threads, smem, st);
+    return two ? launch_res<2, 2>(p, sm_count, threads, smem, st) : launch_res<1, 2>(p, sm_count, threads, smem, st);
 }
 
 }  // namespace kge

@@ -96,13 +96,16 @@ class DataParallelTrainer:
                 self.eng = make_engine(self._symmetric_alloc)
                 reject_lazy("lazy_" if self.eng.lazy else "", self.world)
                 self._finish_p2p_setup()
-                if mode == "nvls":
-                    mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
-                    if not mc:
-                        raise RuntimeError("symmetric memory has no multicast mapping on this system (NVLS unavailable)")
+                # NVLS moves 2/N of a block per rank per step through the links instead of 2(N-1)/N: it wins from 4 GPUs up
+                # (measured, profiles/); at N = 2 the switch round trip of the local contribution makes it slower than p2p
+                want_nvls = mode == "nvls" or (mode == "auto" and self.world >= int(os.environ.get("KGE_B200_NVLS_MIN_WORLD", "4")))
+                mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if want_nvls else 0
+                if mode == "nvls" and not mc:
+                    raise RuntimeError("symmetric memory has no multicast mapping on this system (NVLS unavailable)")
+                if mc:
                     ld = self.eng.ld
                     self._mc = {k: mc + self._row_off[k] * ld * 4 for k in ("table", "g0", "g1")}
-                self.mode = "nvls" if mode == "nvls" else "p2p"
+                self.mode = "nvls" if mc else "p2p"
             except NotImplementedError:
                 raise
             except Exception as e:  # no symmetric memory / no peer access: NCCL path

@@ -560,7 +560,8 @@ def main_ours(args):
     c0 = time.perf_counter()
     g0.record()
     for i in range(args.steps):
-        flush.fill_(i & 0xff)  # evict L2 (126 MB) outside the timed events
+        if os.environ.get("KGE_BENCH_NOFLUSH") != "1":  # (diagnostic switch; the reported numbers always flush)
+            flush.fill_(i & 0xff)  # evict L2 (126 MB) outside the timed events
         step(args.warmup + i, evs[i])
     g1.record()
     cpu_enqueue_ms = 1e3 * (time.perf_counter() - c0) / args.steps  # host time to enqueue one step (flush included)
@@ -568,6 +569,40 @@ def main_ours(args):
     gpu_timeline_ms = g0.elapsed_time(g1) / args.steps                # device time per step, flush included
     launches = eng.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("KGE_BENCH_DEBUG") == "1" and rank == 0:
+        print("per-step kernel us:", [round(1e3 * e[0].elapsed_time(e[1]), 1) for e in evs], file=sys.stderr)
+        print("per-step tail us:", [round(1e3 * e[1].elapsed_time(e[2]), 1) for e in evs], file=sys.stderr)
+    if os.environ.get("KGE_BENCH_DEBUG") == "1" and rank == 0 and world == 1:
+        def probe(tag, batch_fn, with_opt, sync_each, fresh=None):
+            e_ = fresh or eng
+            ts = []
+            for i in range(12):
+                flush.fill_(i)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                e_.forward_backward(batch_fn(i), None, seed=1234, step=500 + i)
+                b_.record()
+                if with_opt:
+                    e_.apply_gradients()
+                if sync_each:
+                    torch.cuda.synchronize()
+                ts.append((a, b_))
+            torch.cuda.synchronize()
+            print("probe %-40s median %.1f us" % (tag, 1e3 * float(np.median([x.elapsed_time(y) for x, y in ts]))), file=sys.stderr)
+        probe("same engine, bench batches, opt, nosync", batch_of, True, False)
+        probe("same engine, bench batches, opt, sync", batch_of, True, True)
+        probe("same engine, bench batches, no opt, sync", batch_of, False, True)
+        one = batch_of(0).clone()
+        probe("same engine, one cloned batch, no opt, sync", lambda i: one, False, True)
+        rngp = np.random.default_rng(0)
+        uni = torch.as_tensor(np.stack([rngp.integers(0, CFG["n_ent"], B), rngp.integers(0, CFG["n_rel"], B), rngp.integers(0, CFG["n_ent"], B)], 1).astype(np.int32)).to(dev)
+        probe("same engine, uniform batch, no opt, sync", lambda i: uni, False, True)
+        fresh = make_engine(None)
+        fresh.init_glorot_uniform(1)
+        probe("fresh engine (glorot kernel init), bench batches", batch_of, False, True, fresh)
+        fresh.set_embeddings(ent0, rel0)
+        probe("fresh engine (numpy tables), bench batches", batch_of, False, True, fresh)
+        fresh.close()
     t_step = sum(e[0].elapsed_time(e[2]) for e in evs)  # ms
     t_kern = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps  # ms, fused fwd+bwd kernel
     tt = torch.tensor([t_step], dtype=torch.float64, device=dev)
@@ -606,6 +641,32 @@ def main_ours(args):
     peak, peak_src = measured_hbm_peak()
 
     # ---- extra: the other BASELINE configs at their stated sizes + N>1 self-checks (outside the headline region) ----
+    def exchange_phases():
+        """phase stamps of the exchange kernel (kge_set_exchange_trace), 7 traced steps, median; every rank's total"""
+        if dp.mode not in ("p2p", "nvls"):
+            return {"mode": dp.mode}
+        dp.trace_exchange(True)
+        rows = []
+        for i in range(7):
+            flush.fill_(i)
+            step(10_000 + i)
+            sync_all()
+            rows.append(dp.exchange_phases_us())
+        dp.trace_exchange(False)
+        med = {k: float(np.median([r[k] for r in rows])) for k in rows[0]}
+        tot = torch.tensor([med["kernel_total"]], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(tot) for _ in range(world)]
+        dist.all_gather(allt, tot)
+        med["kernel_total_per_rank"] = [float(t.item()) for t in allt]
+        med["mode"] = dp.mode
+        med["note"] = ("%globaltimer stamps inside kge_optim_exchange_kernel, rank 0's view; entry_barrier_wait includes the "
+                       "skew between the ranks' train kernels")
+        return med
+    phases = None
+    if world > 1:  # cheap (7 traced steps), so it is measured even with --no-extra
+        res = {}
+        guarded(res, "v", exchange_phases)
+        phases = res["v"]
     extra = {}
     if not args.no_extra:
         if world == 1:
@@ -629,31 +690,6 @@ def main_ours(args):
                 return out
             guarded(extra, "cfg5_shape_single_gpu", cfg5_one)
         else:
-            def exchange_phases():
-                """phase stamps of the exchange kernel (kge_set_exchange_trace), 7 traced steps, median; every rank's total"""
-                if dp.mode not in ("p2p", "nvls"):
-                    return {"mode": dp.mode}
-                dp.trace_exchange(True)
-                rows = []
-                for i in range(7):
-                    flush.fill_(i)
-                    step(10_000 + i)
-                    sync_all()
-                    rows.append(dp.exchange_phases_us())
-                dp.trace_exchange(False)
-                med = {k: float(np.median([r[k] for r in rows])) for k in rows[0]}
-                tot = torch.tensor([med["kernel_total"]], dtype=torch.float64, device=dev)
-                allt = [torch.zeros_like(tot) for _ in range(world)]
-                dist.all_gather(allt, tot)
-                med["kernel_total_per_rank"] = [float(t.item()) for t in allt]
-                med["mode"] = dp.mode
-                med["note"] = ("%globaltimer stamps inside kge_optim_exchange_kernel, rank 0's view; entry_barrier_wait includes the "
-                               "skew between the ranks' train kernels")
-                return med
-            res = {}
-            guarded(res, "v", exchange_phases)
-            if rank == 0:
-                extra["exchange_phases_us"] = res["v"]
             res = {}
             guarded(res, "v", lambda: extra_dp_parity(make_engine, dev, rank, world, ent0, rel0, data_np))
             if rank == 0:
@@ -688,9 +724,12 @@ def main_ours(args):
                 "config": workload_config(world), "clocks": clocks,
                 "arm": {"exchange": {"p2p": "barrier + gradient reduce-scatter + sharded Adam + parameter all-gather + barrier in ONE "
                                             "kernel over NVLink peer memory (kge_optimizer_step_exchange)",
+                                     "nvls": "barrier + in-switch gradient reduce (multimem.ld_reduce) + sharded Adam + in-switch parameter "
+                                             "broadcast (multimem.st) + barrier in ONE kernel (kge_optimizer_step_exchange, multicast mappings)",
                                      "nccl": "NCCL all-reduce of gradient tables + full optimizer", "single": "n/a"}.get(dp.mode, dp.mode),
                         "launches_per_step": launches / max(args.steps, 1),
-                        "host_enqueue_ms_per_step": cpu_enqueue_ms, "device_timeline_ms_per_step_with_flush": gpu_timeline_ms},
+                        "host_enqueue_ms_per_step": cpu_enqueue_ms, "device_timeline_ms_per_step_with_flush": gpu_timeline_ms,
+                        "exchange_phases_us": phases},
                 "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": B * 3 * 4, "d2h_bytes_per_step": 16,
                         "api": "ScoringBasedEmbeddingModel.train_on_batches (pinned host batches; copy stream prefetch; "
                                "per-step loss read one step late)", "last_loss": e2e_losses[-1] if e2e_losses else None},

@@ -1,0 +1,4 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+KGE_BENCH_DEBUG=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-extra --no-cpu > gpurun_out/g_bench.json 2> gpurun_out/g_bench.err; grep -E "probe|per-step kernel" gpurun_out/g_bench.err | cut -c1-300

@@ -532,14 +532,11 @@ def test_regulariser_pair_and_l1_l2():
     eng.close()
 
 
-@pytest.mark.parametrize("split", ["0", "1", "2"])
 @pytest.mark.parametrize("model,k,eta", [("ComplEx", 200, 10), ("HolE", 50, 7), ("DistMult", 200, 32), ("ComplEx", 30, 1), ("DistMult", 7, 3)])
-def test_resident_fast_path_equals_general_kernel(model, k, eta, split, monkeypatch):
+def test_resident_fast_path_equals_general_kernel(model, k, eta, monkeypatch):
     """kge_train_res_kernel (the resident trilinear fast path) against kge_train_kernel forced by KGE_B200_TRAIN_KERNEL=general:
     identical arithmetic per score, so scores are bit-equal; gradients agree to atomic-order noise; both match the oracle
-    elsewhere (test_forward_backward_vs_oracle runs through the fast path by default).  split: how the fast path's gradient
-    rows are scattered (KGE_B200_SCATTER_SPLIT: 0 all red.global, 1 half / 2 all replaced rows by cp.reduce.async.bulk)."""
-    monkeypatch.setenv("KGE_B200_SCATTER_SPLIT", split)
+    elsewhere (test_forward_backward_vs_oracle runs through the fast path by default)."""
     rng = np.random.default_rng(71)
     E, R, B = 900, 9, 777
     ent, rel = _tables(model, E, R, k, rng, scale=0.3)

@@ -109,7 +109,7 @@ rng = np.random.default_rng(0)
 for model, k, opt in (("RotatE", 24, "adam"), ("ComplEx", 40, "adam"), ("ComplEx", 40, "lazy_adam"), ("DistMult", 300, "lazy_adam")):
     E, R, eta, B, steps = 1001, 7, 5, 300, 3   # E not divisible by world: last shard is short
     if k == 300: eta = 40                      # non-resident geometry: negative groups + the row stash through peer memory
-    K = 2 * k
+    K = k if model in ("TransE", "DistMult") else 2 * k
     ent = rng.uniform(-.2, .2, (E, K)).astype(np.float32); rel = rng.uniform(-.2, .2, (R, K)).astype(np.float32)
     data = np.stack([rng.integers(0, E, steps*world*B), rng.integers(0, R, steps*world*B), rng.integers(0, E, steps*world*B)], 1).astype(np.int32)
     neg_ent = rng.integers(0, E, (steps*world, B*eta)).astype(np.int32); neg_keep = rng.integers(0, 2, (steps*world, B*eta)).astype(np.uint8)
