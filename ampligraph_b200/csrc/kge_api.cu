@@ -27,6 +27,7 @@ struct kge_handle {
     int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
     float *stash;                // caller-owned row stash for sharded runs (kge_set_row_stash) or nullptr
     long long stash_rows;
+    int hot_ent[2];              // kge_set_hot_entities (-1: none)
 };
 
 // Make the handle's device current for the duration of an entry point (two handles on different GPUs
@@ -164,6 +165,7 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     int warps = h->max_smem / h->region_bytes;
     if (warps > max_warps) warps = max_warps;
     h->warps = warps;  // 0 => even (3+1) windows do not fit (reported by kge_train_step)
+    h->hot_ent[0] = h->hot_ent[1] = -1;
 
     // ---- the resident trilinear fast path (kge_train_res.cu): DistMult / ComplEx / HolE, one window, eta <= 32; its slot
     // holds s, o and the eta replaced rows (the relation row lives in registers) + sc | nid | jorig + one mbarrier.
@@ -390,6 +392,8 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
     p.stamp = (int)(step & 0x3fffffffu) + 1;
     p.stamp_ent = h->stamp_ent;
     p.stamp_rel = h->stamp_rel;
+    p.hot_ent[0] = h->hot_ent[0];
+    p.hot_ent[1] = h->hot_ent[1];
     p.stash = (h->stash && h->stash_rows >= B * (int64_t)h->cfg.eta) ? h->stash : nullptr;
     if (map && map->world > 1) {
         p.shard_world = map->world;
@@ -508,6 +512,19 @@ extern "C" int kge_set_row_stamps(kge_handle *h, int32_t *ent_stamps_dev, int32_
 }
 
 extern "C" int kge_rows_resident(const kge_handle *h) { return h ? (h->resident ? 1 : 0) : -1; }
+
+extern "C" int kge_set_hot_entities(kge_handle *h, const int32_t *ids_host, int32_t n)
+{
+    KGE_CHECK_HANDLE(h, "kge_set_hot_entities");
+    if (n < 0 || (n > 0 && !ids_host)) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_set_hot_entities: bad arguments");
+    h->hot_ent[0] = h->hot_ent[1] = -1;
+    for (int i = 0; i < n && i < 2; ++i) {
+        if (ids_host[i] < 0 || ids_host[i] >= h->cfg.n_ent) return fail(KGE_ERR_INVALID_ARGUMENT, "kge_set_hot_entities: id %d out of range", ids_host[i]);
+        if (i == 1 && ids_host[1] == ids_host[0]) break;
+        h->hot_ent[i] = ids_host[i];
+    }
+    return KGE_OK;
+}
 
 extern "C" int kge_set_row_stash(kge_handle *h, float *stash_dev, int64_t rows)
 {

@@ -42,6 +42,7 @@ struct TrainParams {
     int stamp;
     int *stamp_ent, *stamp_rel;
     int *stamp_ent_shard[KGE_MAX_PEERS];
+    int hot_ent[2];  // entities whose subject/object gradient rows are summed per warp before they are scattered (-1: none); fast path only
     float *stash;  // [B, eta, ld] local copy of the replaced rows gathered by the score pass (sharded runs) or nullptr
 };
 

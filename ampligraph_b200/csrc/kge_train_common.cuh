@@ -136,8 +136,14 @@ __device__ __forceinline__ float warp_sum4t(float v0, float v1, float v2, float 
 // per-positive loss and dL/dscore (warp-cooperative; lanes stride over j).
 // in: P, sc[j] = N_j.  out: sc[j] = dL/dN_j, returns loss_i, *dP.
 // --------------------------------------------------------------------------
+// x / y for y in a range where the IEEE slow path (denormal operands) cannot matter: reciprocal + multiply, no FCHK branch
+#ifdef KGE_FAST_LOSS_MATH
+__device__ __forceinline__ float fdiv(float x, float y) { return __fdividef(x, y); }
+#else
+__device__ __forceinline__ float fdiv(float x, float y) { return x / y; }
+#endif
 __device__ __forceinline__ float log_sigmoid(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
-__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf(float x) { return fdiv(1.f, 1.f + expf(-x)); }
 #define KGE_CLIP_LO (-75.0f)  // loss_functions.py:32
 #define KGE_CLIP_HI (75.0f)   // loss_functions.py:35
 
@@ -199,10 +205,10 @@ static __device__ __forceinline__ float loss_and_dscores(const TrainParams &p, f
             const float e = on ? expf(p.alpha * N - mx) : 0.f;
             const float x = -N - p.margin, t = expf(-fabsf(x));
             const float lj = fminf(x, 0.f) - log1pf(t);
-            const float sg = ((x < 0.f) ? 1.f : t) / (1.f + t);
+            const float sg = fdiv((x < 0.f) ? 1.f : t, 1.f + t);
             float z = e, sl = e * lj;
             warp_sum2(z, sl);
-            const float S = sl / z, pj = e / z;
+            const float S = fdiv(sl, z), pj = fdiv(e, z);
             if (on) sc[lane] = w * (pj * sg - p.alpha * pj * (lj - S));
             loss = -log_sigmoid(p.margin + P) - w * S;
             dP = -sigmoidf(-(p.margin + P));

@@ -67,6 +67,9 @@ __device__ __forceinline__ void bulk_load_s(uint32_t smem_dst, const void *gmem_
 // The front end rematerialises cheap values (kernel parameters, %tid-derived addresses) inside the long per-positive
 // loop instead of keeping them in registers -- a dozen ld.param / shift / mad per trip of the inner loops.  Passing a
 // value through an empty asm makes it opaque: it is computed once and stays in its register.
+#ifndef KGE_HOT
+#define KGE_HOT 2  // entities whose subject/object gradient rows are privatised per warp (1 or 2)
+#endif
 #define KGE_KEEP32(x) asm volatile("" : "+r"(x))
 #define KGE_KEEP64(x) asm volatile("" : "+l"(x))
 #define KGE_KEEPF(x) asm volatile("" : "+f"(x))
@@ -133,6 +136,18 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
     const bool stamping = p.stamp_ent != nullptr && p.mode != KGE_STEP_FORWARD_ONLY;
     uint32_t phase = 0u;
     double loss_acc = 0.0;
+    // Hot-entity privatisation.  On a skewed graph a few entities own a large share of all subject / object slots (Zipf(1)
+    // over 14.5 k entities: the first holds 10 %, the first two 15 %), and every one of those positives adds 100 float4 to
+    // the SAME gradient row: ~42,000 atomics per 128-byte line per step, which the L2 serialises per address -- measured
+    // 170 us against 145 us for the same kernel on uniformly drawn triples, depending on which L2 slices the hot lines
+    // share (profiles/r2g_bench_probes.log).  The caller names up to KGE_HOT entities (kge_set_hot_entities; the facade
+    // takes the most frequent ones of the training set); each warp sums their subject / object gradient rows in registers
+    // over all the positives it processes and issues ONE set of REDs per hot row when it retires.
+    int hot0 = p.hot_ent[0], hot1 = KGE_HOT > 1 ? p.hot_ent[1] : -1;
+    KGE_KEEP32(hot0); KGE_KEEP32(hot1);
+    float4 H0r[NIT], H0i[NIT], H1r[NIT], H1i[NIT];  // (the second set folds away when KGE_HOT == 1)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) H0r[it] = H0i[it] = H1r[it] = H1i[it] = f4zero();
 
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B; i += n_warps) {
@@ -340,22 +355,46 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
                     const float4 orr = lds4(a + lwB), oi = lds4(a + lwB + hsB);
                     const float4 Ur = f4fma(gP, sr, W0r[it]), Ui = f4fma(gP, si, W0i[it]);    // everything that sat in the subject slot
                     const float4 Xr = f4fma(gP, orr, W1r[it]), Xi = f4fma(gP, oi, W1i[it]);   // everything that sat in the object slot
-                    red4(gs_row, o, f4fma(pi[it], Xi, pr[it] * Xr));                          // d/ds f(s,p,X)
-                    red4(gs_row, o + hsB, pr[it] * Xi - pi[it] * Xr);
-                    red4(go_row, o, Ur * pr[it] - Ui * pi[it]);                               // d/do f(U,p,o)
-                    red4(go_row, o + hsB, f4fma(Ur, pi[it], Ui * pr[it]));
+                    const float4 gsr = f4fma(pi[it], Xi, pr[it] * Xr), gsi = pr[it] * Xi - pi[it] * Xr;      // d/ds f(s,p,X)
+                    const float4 gor = Ur * pr[it] - Ui * pi[it], goi = f4fma(Ur, pi[it], Ui * pr[it]);      // d/do f(U,p,o)
+                    if (s_id == hot0) { H0r[it] = H0r[it] + gsr; H0i[it] = H0i[it] + gsi; }
+                    else if (KGE_HOT > 1 && s_id == hot1) { H1r[it] = H1r[it] + gsr; H1i[it] = H1i[it] + gsi; }
+                    else { red4(gs_row, o, gsr); red4(gs_row, o + hsB, gsi); }
+                    if (o_id == hot0) { H0r[it] = H0r[it] + gor; H0i[it] = H0i[it] + goi; }
+                    else if (KGE_HOT > 1 && o_id == hot1) { H1r[it] = H1r[it] + gor; H1i[it] = H1i[it] + goi; }
+                    else { red4(go_row, o, gor); red4(go_row, o + hsB, goi); }
                     red4(gp_row, o, f4fma(Ur, orr, Ui * oi) + f4fma(sr, W1r[it], si * W1i[it]));   // d/dp [f(U,p,o) + f(s,p,W1)]
                     red4(gp_row, o + hsB, (Ur * oi - Ui * orr) + (sr * W1i[it] - si * W1r[it]));
                 } else {
                     const float4 vs = lds4(a), vo = lds4(a + lwB);
                     const float4 U = f4fma(gP, vs, W0r[it]), X = f4fma(gP, vo, W1r[it]);
-                    red4(gs_row, o, pr[it] * X);
-                    red4(go_row, o, U * pr[it]);
+                    const float4 gsr = pr[it] * X, gor = U * pr[it];
+                    if (s_id == hot0) H0r[it] = H0r[it] + gsr;
+                    else if (KGE_HOT > 1 && s_id == hot1) H1r[it] = H1r[it] + gsr;
+                    else red4(gs_row, o, gsr);
+                    if (o_id == hot0) H0r[it] = H0r[it] + gor;
+                    else if (KGE_HOT > 1 && o_id == hot1) H1r[it] = H1r[it] + gor;
+                    else red4(go_row, o, gor);
                     red4(gp_row, o, f4fma(U, vo, vs * W1r[it]));
                 }
             }
         }
         __syncwarp();  // every lane has read the slot before the next positive's gather overwrites it
+    }
+    // retire: this warp's share of the hot rows (zeros when it met none of them: skip)
+    if (p.mode != KGE_STEP_FORWARD_ONLY) {
+#pragma unroll
+        for (int h = 0; h < KGE_HOT; ++h) {
+            const int id = h ? hot1 : hot0;
+            if (id < 0) continue;
+            char *const row = reinterpret_cast<char *>(grad_ent + (size_t)id * ld);
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                if (!live[it]) continue;
+                red4(row, off[it], h ? H1r[it] : H0r[it]);
+                if constexpr (HALVES == 2) red4(row, off[it] + hsB, h ? H1i[it] : H0i[it]);
+            }
+        }
     }
     if (p.loss_out && p.mode == KGE_STEP_FUSED && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_out, loss_acc);
 }

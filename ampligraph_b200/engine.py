@@ -162,6 +162,18 @@ class KGEEngine:
             _lib.check(self.lib.kge_set_row_stash(self.h, _ptr(self.row_stash), need))
         return self.row_stash
 
+    def set_hot_entities(self, triples=None, ids=None):
+        """Hot-entity hint (kge_set_hot_entities): the two most frequent subject/object ids of `triples` (numpy / torch
+        [N,3] of indexed triples) or explicit `ids`; None/empty clears it."""
+        if ids is None and triples is not None:
+            t = triples.detach().cpu().numpy() if torch.is_tensor(triples) else np.asarray(triples)
+            cnt = np.bincount(np.concatenate([t[:, 0], t[:, 2]]).astype(np.int64), minlength=self.n_ent)
+            top = np.argsort(-cnt, kind="stable")[:2]
+            ids = [int(e) for e in top if cnt[e] > 0]
+        arr = np.asarray(ids if ids is not None else [], dtype=np.int32)
+        _lib.check(self.lib.kge_set_hot_entities(self.h, arr.ctypes.data_as(C.c_void_p), int(arr.size)))
+        self.hot_entities = arr.tolist()
+
     def set_embeddings(self, ent_dense=None, rel_dense=None):
         """dense [rows, internal_k] (numpy / torch) -> padded device layout."""
         for dense, table, rows in ((ent_dense, self.ent, self.ent_rows), (rel_dense, self.rel, self.n_rel)):

@@ -213,6 +213,7 @@ class ScoringBasedEmbeddingModel:
         if self.engine is None:
             self._build_engine()
         eng = self.engine
+        eng.set_hot_entities(triples=triples)  # the most frequent entities of the training set: their gradient rows are summed per warp
         data = self._to_dev(triples, np.int32)  # uploaded once; batches are device-side slices
         n = data.shape[0]
         weights = None
@@ -327,6 +328,9 @@ class ScoringBasedEmbeddingModel:
                 raise ValueError("train_on_batches needs max_ent_size/max_rel_size (ids are already indexed)")
             self._build_engine()
         eng = self.engine
+        if getattr(self, "hot_entities_from", None) is not None:  # streamed training sees no training set to count: an indexed
+            eng.set_hot_entities(triples=self.hot_entities_from)   # [N,3] array may be attached for the hot-entity hint of fit()
+            self.hot_entities_from = None
         dev = eng.device
         user_loss = isinstance(self.compiled_loss, loss_functions.LossFunctionWrapper)
         depth = max(2, int(prefetch))

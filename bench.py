@@ -523,6 +523,8 @@ def main_ours(args):
     ent0, rel0 = glorot(CFG["n_ent"], K, rng), glorot(CFG["n_rel"], K, rng)
     eng.set_embeddings(ent0, rel0)  # same tables on every rank
     data_np = synthetic_kg(CFG["n_ent"], CFG["n_rel"], CFG["n_triples"])
+    if os.environ.get("KGE_BENCH_HOT", "1") != "0":
+        eng.set_hot_entities(triples=data_np)  # what ScoringBasedEmbeddingModel.fit does with its training set
     nb = len(data_np) // B  # full batches only, so every step does identical work
     data = torch.as_tensor(data_np).to(dev)
     pinned = torch.as_tensor(data_np).pin_memory()
@@ -602,6 +604,13 @@ def main_ours(args):
         probe("fresh engine (glorot kernel init), bench batches", batch_of, False, True, fresh)
         fresh.set_embeddings(ent0, rel0)
         probe("fresh engine (numpy tables), bench batches", batch_of, False, True, fresh)
+        te, tr_ = eng.get_embeddings()
+        fresh.set_embeddings(te, tr_)
+        probe("fresh engine (TRAINED tables), bench batches", batch_of, False, True, fresh)
+        probe("fresh engine (TRAINED tables), uniform batch", lambda i: uni, False, True, fresh)
+        eng.set_embeddings(ent0, rel0)
+        probe("bench engine reset to numpy tables, bench batches", batch_of, False, True)
+        eng.set_embeddings(te, tr_)
         fresh.close()
     t_step = sum(e[0].elapsed_time(e[2]) for e in evs)  # ms
     t_kern = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps  # ms, fused fwd+bwd kernel
@@ -625,6 +634,7 @@ def main_ours(args):
     from ampligraph_b200.latent_features import loss_functions, optimizers
     model.compile(optimizer=optimizers.get("adam", {"learning_rate": CFG["lr"]}),
                   loss=loss_functions.get(CFG["loss"], CFG["loss_params"]))
+    model.hot_entities_from = data_np  # train_on_batches has no training set to count: give it the one fit() would see
     host_batches = [pinned[j * B:(j + 1) * B] for j in range(nb)]
     hb = lambda i: host_batches[(i * world + rank) % nb]
     model.train_on_batches([hb(i) for i in range(max(args.warmup, 3))])

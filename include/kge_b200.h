@@ -217,6 +217,15 @@ typedef struct kge_shard_map {
  * row into it (cp.async.bulk shared->global) and the gradient pass re-reads the LOCAL copy instead
  * of pulling the row through NVLink again, halving the peer traffic. */
 int kge_set_row_stash(kge_handle *h, float *stash_dev, int64_t rows);
+
+/* Hot-entity hint for kge_train_step (optional; results are unchanged up to fp32 summation order).  On a skewed graph a
+ * handful of entities occupy a large share of all subject / object slots of a batch, and every such positive adds a full
+ * gradient row to the SAME row of grad_ent: tens of thousands of atomics per 128-byte line per step, which the L2
+ * serialises per address.  ids_host = the most frequent entities of the training set, most frequent first (HOST array;
+ * the first two are used, n = 0 clears the hint): the resident trilinear kernel sums their subject / object gradient rows
+ * in registers per warp and scatters each once per launch.  The reference has no counterpart (TensorFlow's
+ * unsorted_segment_sum deduplicates all rows, optimizers.py:166 -> legacy apply_gradients). */
+int kge_set_hot_entities(kge_handle *h, const int32_t *ids_host, int32_t n);
 /* 1 when all 3+eta row windows of a positive stay in shared memory (single gather, the stash is never
  * used), 0 when the kernel works in negative groups / column windows, -1 for a NULL handle. */
 int kge_rows_resident(const kge_handle *h);

@@ -541,25 +541,32 @@ def test_resident_fast_path_equals_general_kernel(model, k, eta, monkeypatch):
     E, R, B = 900, 9, 777
     ent, rel = _tables(model, E, R, k, rng, scale=0.3)
     t = _triples(E, R, B, rng)
+    hot = rng.random(B)
+    t[hot < 0.2, 0] = 5; t[(hot > 0.15) & (hot < 0.4), 2] = 5; t[hot > 0.85, 0] = 17; t[(hot > 0.6) & (hot < 0.7), 2] = 17  # skewed graph
     neg_ent, neg_keep = _negatives(E, B, eta, rng)
     out = {}
-    for which in ("fast", "general"):
+    for which in ("fast", "fast_hot", "general"):
         if which == "general":
             monkeypatch.setenv("KGE_B200_TRAIN_KERNEL", "general")
         else:
             monkeypatch.delenv("KGE_B200_TRAIN_KERNEL", raising=False)
         eng = _engine(model, k, eta, E, R, loss="self_adversarial")
         assert eng.lib.kge_rows_resident(eng.h)
+        if which == "fast_hot":  # kge_set_hot_entities: entities 5 and 17 are summed per warp and scattered once
+            eng.set_hot_entities(triples=t)
+            assert sorted(eng.hot_entities) == [5, 17]
         eng.set_embeddings(ent, rel)
         sp = torch.empty(B, device="cuda"); sn = torch.empty(eta * B, device="cuda")
         eng.forward_backward(_dev(t), (_dev(neg_ent), _dev(neg_keep)), scores_pos=sp, scores_neg=sn)
         torch.cuda.synchronize()
         out[which] = (sp.cpu().numpy(), sn.cpu().numpy(), eng.g_ent.cpu().numpy().copy(), eng.g_rel.cpu().numpy().copy(), eng.read_loss())
         eng.close()
-    f, g = out["fast"], out["general"]
-    assert (f[0] == g[0]).all() and (f[1] == g[1]).all()
-    assert _close(f[2], g[2], rtol=2e-5) and _close(f[3], g[3], rtol=2e-5)
-    assert abs(f[4] - g[4]) <= 1e-6 * abs(g[4])
+    g = out["general"]
+    for which in ("fast", "fast_hot"):
+        f = out[which]
+        assert (f[0] == g[0]).all() and (f[1] == g[1]).all(), which
+        assert _close(f[2], g[2], rtol=2e-5) and _close(f[3], g[3], rtol=2e-5), which
+        assert abs(f[4] - g[4]) <= 1e-6 * abs(g[4]), which
 
 
 def test_exchange_kernel_world1_equals_plain_optimizer():
