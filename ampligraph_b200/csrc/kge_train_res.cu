@@ -68,7 +68,7 @@ __device__ __forceinline__ void bulk_load_s(uint32_t smem_dst, const void *gmem_
 // loop instead of keeping them in registers -- a dozen ld.param / shift / mad per trip of the inner loops.  Passing a
 // value through an empty asm makes it opaque: it is computed once and stays in its register.
 #ifndef KGE_HOT
-#define KGE_HOT 2  // entities whose subject/object gradient rows are privatised per warp (1 or 2)
+#define KGE_HOT 1  // entities whose subject/object gradient rows are privatised per warp (1 or 2; measured on B200: 1 -> 150.8 us, 2 -> 153.2 us in bench.py, and 2 costs the uniform case 3 us: profiles/r2i_kbench_hot*.log)
 #endif
 #define KGE_KEEP32(x) asm volatile("" : "+r"(x))
 #define KGE_KEEP64(x) asm volatile("" : "+l"(x))

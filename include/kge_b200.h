@@ -222,7 +222,7 @@ int kge_set_row_stash(kge_handle *h, float *stash_dev, int64_t rows);
  * handful of entities occupy a large share of all subject / object slots of a batch, and every such positive adds a full
  * gradient row to the SAME row of grad_ent: tens of thousands of atomics per 128-byte line per step, which the L2
  * serialises per address.  ids_host = the most frequent entities of the training set, most frequent first (HOST array;
- * the first two are used, n = 0 clears the hint): the resident trilinear kernel sums their subject / object gradient rows
+ * the first KGE_HOT = 1 is used (a second one measured slower), n = 0 clears the hint): the resident trilinear kernel sums their subject / object gradient rows
  * in registers per warp and scatters each once per launch.  The reference has no counterpart (TensorFlow's
  * unsorted_segment_sum deduplicates all rows, optimizers.py:166 -> legacy apply_gradients). */
 int kge_set_hot_entities(kge_handle *h, const int32_t *ids_host, int32_t n);
