@@ -13,6 +13,7 @@
 // brackets it with barriers) and kge_optim_exchange_kernel (both tables, the cross-rank
 // barriers are flag exchanges INSIDE the kernel: one launch per step).
 #include <math.h>
+#include <stdlib.h>
 
 #include "kge_internal.h"
 
@@ -323,40 +324,66 @@ __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeA
     KGE_TRACE(2, blockIdx.x == 0);
 
     float racc = 0.f;
-    for (long long base = tid; base < x.n4; base += nthreads * U) {
-        float4 gq[U][MC ? 1 : WORLD];
+    // one element: optimizer on the summed gradient g4, new parameters delivered to every replica
+    auto update_and_deliver = [&](long long i, float4 g4) {
+        const long long gi = x.off4 + i;
+        float4 x4 = x.table[rank][gi], a4 = z, b4 = z;
+        if (S0 || mom) a4 = x.s0[i];
+        if (S1) b4 = x.s1[i];
+        const float4 xn = update4<KIND, REG>(x4, g4, a4, b4, o, gi < x.ent4 ? x.reg_ent : x.reg_rel, racc);
+        if (MC) {
+            multimem_st(x.table_mc + gi, xn);
+        } else {
+#pragma unroll
+            for (int q = 0; q < WORLD; ++q) __stcg(x.table[q] + gi, xn);
+        }
+        if (S0 || mom) x.s0[i] = a4;
+        if (S1) x.s1[i] = b4;
+    };
+    if constexpr (MC) {
+        // NVLS: the reduce (multimem.ld_reduce: this GPU SENDS its share of every shard) and the broadcast (multimem.st:
+        // this GPU RECEIVES every other shard) load opposite directions of the links, so they are software-pipelined:
+        // the loads of trip t+1 are in flight while trip t is updated and broadcast (the grid is sized for a few trips).
+        const long long stride = nthreads * U;
+        float4 cur[U], nxt[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = base + u * nthreads;
-            if (i < x.n4) {
-                if (MC) {
-                    gq[u][0] = multimem_ld_reduce_add(x.grad_mc + x.off4 + i);
-                } else {
+            const long long i = tid + u * nthreads;
+            if (i < x.n4) cur[u] = multimem_ld_reduce_add(x.grad_mc + x.off4 + i);
+        }
+        for (long long base = tid; base < x.n4; base += stride) {
 #pragma unroll
-                    for (int q = 0; q < (MC ? 1 : WORLD); ++q) gq[u][q] = __ldcg(x.grad[q] + x.off4 + i);
-                }
+            for (int u = 0; u < U; ++u) {
+                const long long i = base + stride + u * nthreads;
+                if (i < x.n4) nxt[u] = multimem_ld_reduce_add(x.grad_mc + x.off4 + i);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = base + u * nthreads;
+                if (i < x.n4) update_and_deliver(i, cur[u]);
+                cur[u] = nxt[u];
             }
         }
+    } else {
+        for (long long base = tid; base < x.n4; base += nthreads * U) {
+            float4 gq[U][WORLD];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = base + u * nthreads;
-            if (i >= x.n4) continue;
-            const long long gi = x.off4 + i;
-            float4 g4 = gq[u][0];
+            for (int u = 0; u < U; ++u) {
+                const long long i = base + u * nthreads;
+                if (i < x.n4) {
 #pragma unroll
-            for (int q = 1; q < (MC ? 1 : WORLD); ++q) { g4.x += gq[u][q].x; g4.y += gq[u][q].y; g4.z += gq[u][q].z; g4.w += gq[u][q].w; }
-            float4 x4 = x.table[rank][gi], a4 = z, b4 = z;
-            if (S0 || mom) a4 = x.s0[i];
-            if (S1) b4 = x.s1[i];
-            const float4 xn = update4<KIND, REG>(x4, g4, a4, b4, o, gi < x.ent4 ? x.reg_ent : x.reg_rel, racc);
-            if (MC) {
-                multimem_st(x.table_mc + gi, xn);
-            } else {
-#pragma unroll
-                for (int q = 0; q < WORLD; ++q) __stcg(x.table[q] + gi, xn);
+                    for (int q = 0; q < WORLD; ++q) gq[u][q] = __ldcg(x.grad[q] + x.off4 + i);
+                }
             }
-            if (S0 || mom) x.s0[i] = a4;
-            if (S1) x.s1[i] = b4;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = base + u * nthreads;
+                if (i >= x.n4) continue;
+                float4 g4 = gq[u][0];
+#pragma unroll
+                for (int q = 1; q < WORLD; ++q) { g4.x += gq[u][q].x; g4.y += gq[u][q].y; g4.z += gq[u][q].z; g4.w += gq[u][q].w; }
+                update_and_deliver(i, g4);
+            }
         }
     }
     if (REG && x.reg_loss) flush_reg_loss(racc, x.reg_loss);
@@ -408,8 +435,14 @@ cudaError_t launch_optimizer_exchange(const OptimParams &o, const ExchangeParams
     a.world = xp.world; a.rank = xp.rank; a.phases = xp.phases;
     // no CTA ever waits for another CTA of this grid (phase 1 is per CTA, phase 3 is the last finisher alone), so the
     // grid need not be co-resident; a few CTAs per SM are enough to keep the NVLink loads in flight
-    long long work = a.n4 > a.total4 / 4 ? a.n4 : a.total4 / 4;
-    long long want = (work + 255) / 256;
+    // grid: up to 4 CTAs per SM; the NVLS variant is software-pipelined, so it wants a few trips per thread rather than
+    // every load of the shard in flight at once (KGE_B200_EXCHANGE_TRIPS, default 1 = one trip; measured values in DESIGN.md)
+    int trips = 1;
+    if (const char *e = getenv("KGE_B200_EXCHANGE_TRIPS")) trips = atoi(e) > 0 ? atoi(e) : 1;
+    const int U = xp.world <= 4 ? 4 : 2;
+    long long want = (a.n4 + 256LL * U * trips - 1) / (256LL * U * trips);
+    const long long zero_want = (a.total4 / 8 + 255) / 256;  // the zeroing of the next gradient block wants enough threads too
+    if (!mc || trips <= 1) want = want > zero_want ? want : zero_want;
     if (want < 1) want = 1;
     int grid = (int)(want < (long long)sm_count * 4 ? want : (long long)sm_count * 4);
     const bool reg = xp.reg_ent.p > 0 || xp.reg_rel.p > 0;

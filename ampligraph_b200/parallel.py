@@ -47,17 +47,24 @@ def reject_lazy(optimizer_name, world):
                                   % (optimizer_name, world))
 
 
-def tables_close(got, ref, init, rtol=3e-4, atol_of_update=2e-3):
+def tables_close(got, ref, init, rtol=3e-4, atol_of_update=2e-3, outlier_of_update=5e-2, outlier_fraction=1e-4):
     """Parity criterion for two runs that sum the same fp32 gradient contributions in a different order (multi-GPU vs
-    single GPU): |got - ref| <= atol + rtol*|ref| with atol = atol_of_update * max|ref - init|.  Adam turns a relative
-    gradient difference d into an update difference of about lr*d whatever the size of the parameter, so the absolute
-    part of the tolerance is stated relative to how far the parameters MOVED; a lost or doubled contribution changes a
-    row by O(1) of its update and fails.  Returns (ok, max_abs_err / max_update)."""
+    single GPU).  Adam turns a relative gradient difference d into an update difference of about lr*d whatever the size of
+    the parameter, so the absolute tolerance is stated relative to how far the parameters MOVED (u = max|ref - init|):
+      * all but a fraction `outlier_fraction` of the elements: |got - ref| <= atol_of_update*u + rtol*|ref|;
+      * EVERY element: |got - ref| <= outlier_of_update*u + rtol*|ref| -- an element whose summed gradient cancels to ~0 has
+        its Adam direction decided by rounding noise (measured: up to 6e-3 u on cfg4 over 8 shards, loss equal to 1e-11),
+        whereas a lost or doubled contribution moves a whole row by O(1) u and fails this bound.
+    Returns (ok, max_abs_err / u)."""
     import numpy as np
     got, ref, init = (np.asarray(x, dtype=np.float64) for x in (got, ref, init))
     upd = max(float(np.abs(ref - init).max()), 1e-30)
     err = np.abs(got - ref)
-    return bool((err <= atol_of_update * upd + rtol * np.abs(ref)).all()), float(err.max() / upd)
+    slack = rtol * np.abs(ref)
+    tight = err <= atol_of_update * upd + slack
+    loose = err <= outlier_of_update * upd + slack
+    ok = bool(loose.all()) and float((~tight).mean()) <= outlier_fraction
+    return ok, float(err.max() / upd)
 
 
 _FLAG_WORDS = 64  # uint32 words reserved per rank for the in-kernel barriers (2 slots x up to 8 writers, padded)

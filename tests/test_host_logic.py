@@ -339,3 +339,9 @@ def test_tables_close_is_relative_to_the_update():
     assert not ok
     lost = ref.copy(); lost[2] = init[2]               # a row whose update was lost
     assert not tables_close(lost, ref, init)[0]
+    big_init = np.zeros((200, 100), np.float32)        # one Adam-noise outlier among 20,000 elements is tolerated ...
+    big_ref = big_init + 3e-3
+    noisy = big_ref.copy(); noisy[7, 7] += 2e-5        # 6.7e-3 of the update
+    assert tables_close(noisy, big_ref, big_init)[0]
+    noisy[7, :50] += 2e-5                              # ... half a row of them is not
+    assert not tables_close(noisy, big_ref, big_init)[0]
