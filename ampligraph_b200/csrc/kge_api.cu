@@ -171,14 +171,17 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     // holds s, o and the eta replaced rows (the relation row lives in registers) + sc | nid | jorig + one mbarrier.
     // Same residency rule as above, with its own (one row smaller) slot.
     h->res_warps = 0;
+    // DistMult rows of up to 512 floats (NIT = 4) qualify too: its per-lane state is a third of ComplEx's.
     if ((cfg->scoring == KGE_DISTMULT || cfg->scoring == KGE_COMPLEX || cfg->scoring == KGE_HOLE) && h->n_cb == 1 &&
-        h->nit <= 2 && cfg->eta <= 32 && cfg->neg_group <= 0) {
+        (h->nit <= 2 || cfg->scoring == KGE_DISTMULT) && cfg->eta <= 32 && cfg->neg_group <= 0) {
         const int res_aux = (3 * h->eta_pad * 4 + 8 + 15) / 16 * 16;
         h->res_rows_bytes = (2 + cfg->eta) * row_bytes;
         h->res_region_bytes = h->res_rows_bytes + res_aux;
         int rw = h->max_smem / h->res_region_bytes;
         if (rw > max_warps) rw = max_warps;
-        const int min_res = max_warps < KGE_MIN_RESIDENT_WARPS ? max_warps : KGE_MIN_RESIDENT_WARPS;
+        int min_res = max_warps < KGE_MIN_RESIDENT_WARPS ? max_warps : KGE_MIN_RESIDENT_WARPS;
+        if (h->nit == 4) min_res = KGE_MIN_RESIDENT_WARPS_WIDE;
+        if (const char *ev = getenv("KGE_B200_RES_MIN_WARPS")) min_res = atoi(ev);  // tuning aid
         if (rw >= min_res) h->res_warps = rw;
     }
 

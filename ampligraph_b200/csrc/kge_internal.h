@@ -8,6 +8,7 @@
 #define KGE_MAX_PEERS 8
 #define KGE_MIN_RESIDENT_WARPS 8  // tuned on B200: fewer warps/SM than this costs more than re-gathering
 #define KGE_TARGET_WARPS 10
+#define KGE_MIN_RESIDENT_WARPS_WIDE 6  // the fast path on DistMult rows of 257..512 floats (NIT = 4): cfg3 113.6 us with 6 resident warps against 133 us for the grouped general kernel with 8 (profiles/r2l_*)
 
 namespace kge {
 

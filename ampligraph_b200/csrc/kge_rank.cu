@@ -415,6 +415,207 @@ __global__ void __launch_bounds__(RD_THREADS, 2) kge_rank_dot_kernel(const RankP
     }
 }
 
+// --------------------------------------------------------------------------
+// RotatE specialisation: CTA = 256 candidates x 32 queries (the tile kernel's geometry), thread tile = 4 candidates x
+// 8 queries, accumulators as 16 f32x2 pairs of ADJACENT QUERIES.  As in the DOT kernel the query tile (and, on the
+// subject side, the tile of object rows) is staged transposed ([column][query]), so one broadcast 128-bit read returns
+// four queries of one column and every packed instruction advances two canonical chains: per pair of chain steps the
+// object side issues 2 FADD2 + FMUL2 + FFMA2 (residual, x = re^2 + im^2), 2 FMNMX + 2 MUFU.RSQ, 2 FMUL2 + 2 FFMA2 (the
+// correctly rounded sqrt of kge_rank_common.cuh, same five operations per chain), 2 FSET and one FFMA2 that adds
+// [x >= 2^-101] * sqrt to the accumulators -- 15 issue slots instead of 26.  Every operation is the IEEE operation of the
+// scalar chain (rank_step_rot) on the same operands in the same order: a - b, a * b and fma are sign-symmetric, the
+// negations are operand modifiers, fma(r, 1, acc) == acc + r and fma(r, 0, acc) == acc for finite r.
+// --------------------------------------------------------------------------
+constexpr int RR_QLDS = RK_TQ + 4;                 // row stride of the transposed query tile
+constexpr int RR_Q_FLOATS = 32 * RR_QLDS;          // 16 re columns + 16 im columns
+constexpr int RR_STAGE_FLOATS = RK_E_FLOATS + 2 * RR_Q_FLOATS;
+
+__device__ __forceinline__ unsigned long long rk_sub2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long rk_mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long rk_mul2_ftz(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long rk_fma2v(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void rk_upk2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
+// acc += sqrt_rn_nonneg(re^2 + im^2) for two chains at once (see sqrt_rn_nonneg for the five-operation sqrt)
+__device__ __forceinline__ unsigned long long rk_mod_step2(unsigned long long acc, unsigned long long re, unsigned long long im)
+{
+    const float lo = 3.9443045e-31f;  // 2^-101
+    const unsigned long long x2 = rk_fma2v(im, im, rk_mul2(re, re));
+    float x0, x1, y0, y1, s0, s1;
+    rk_upk2(x2, x0, x1);
+    const float c0 = fmaxf(x0, lo), c1 = fmaxf(x1, lo);
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(c0));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(c1));
+    const unsigned long long xc = rk_pk2(c0, c1), y = rk_pk2(y0, y1);
+    const unsigned long long s = rk_mul2_ftz(xc, y), h = rk_mul2_ftz(y, rk_pk2(0.5f, 0.5f));
+    rk_upk2(s, s0, s1);
+    const unsigned long long r = rk_fma2v(rk_pk2(-s0, -s1), s, xc);  // the negation becomes an operand modifier of the FFMA2
+    const unsigned long long res = rk_fma2v(r, h, s);
+    const unsigned long long flag = rk_pk2(x0 >= lo ? 1.f : 0.f, x1 >= lo ? 1.f : 0.f);
+    return rk_fma2v(res, flag, acc);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(RK_THREADS, 2) kge_rank_rot_kernel(const RankParams p, int32_t *__restrict__ cnt)
+{
+    static_assert(OP == OP_ROT_S || OP == OP_ROT_O, "RotatE only");
+    extern __shared__ __align__(128) float smem[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int cg = warp & 1, qg = warp >> 1;  // 2 candidate groups of 128, 4 query groups of 8
+    const long long c0 = (long long)blockIdx.x * RK_TC, q0 = (long long)blockIdx.y * RK_TQ;
+    const int ld = p.L.ld, kp = p.L.kp;
+    const int n_chunks = (kp + 15) / 16;
+
+    // E staging as in the tile kernel: rows t/8 + 32n (n<8), column quad t%8 (quads 0-3: re columns, 4-7: im columns)
+    const int lrow = t >> 3, c4 = t & 7;
+    const float *erow[8];
+    bool evalid[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        long long c = c0 + lrow + 32 * n;
+        evalid[n] = c < p.n_cand;
+        long long id = evalid[n] ? (p.cand_ids ? (long long)p.cand_ids[c] : p.cand_begin + c) : 0;
+        erow[n] = p.ent + (size_t)id * ld;
+    }
+    // Q (and A) staging, transposed: tile column t%32 (0-15 re, 16-31 im), queries t/32 + 8n (n<4), 4-byte copies
+    const int qd = t & 31, qq = t >> 5;
+
+    auto stage_load = [&](int chunk, int buf) {
+        float *Es = smem + buf * RR_STAGE_FLOATS, *Qs = Es + RK_E_FLOATS, *As = Qs + RR_Q_FLOATS;
+        {
+            const int d = chunk * 16 + 4 * (c4 & 3);
+            const bool cvalid = d < kp;
+            const int col = cvalid ? (c4 < 4 ? 0 : kp) + d : 0;
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                cp_async16(Es + (lrow + 32 * n) * RK_LDS + 4 * c4, erow[n] + col, cvalid && evalid[n]);
+        }
+        const int d = chunk * 16 + (qd & 15);
+        const bool qcvalid = d < kp;
+        const int qcol = (qd < 16 ? 0 : kp) + d;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const long long q = q0 + qq + 8 * n;
+            const bool ok = qcvalid && q < p.b;
+            const size_t src = (size_t)(ok ? q : 0) * ld + (ok ? qcol : 0);
+            cp_async4(Qs + qd * RR_QLDS + qq + 8 * n, p.qvec + src, ok);
+            if (OP == OP_ROT_S) cp_async4(As + qd * RR_QLDS + qq + 8 * n, p.qaux + src, ok);
+        }
+        cp_async_commit();
+    };
+
+    unsigned long long acc[4][4];  // [candidate][query pair]
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[m][i] = 0ull;
+
+    stage_load(0, 0);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < n_chunks) { stage_load(ch + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const float *Es = smem + buf * RR_STAGE_FLOATS + (cg * 128 + lane) * RK_LDS;
+        const float *Qs = smem + buf * RR_STAGE_FLOATS + RK_E_FLOATS + qg * 8;
+        const float *As = Qs + RR_Q_FLOATS;
+#pragma unroll
+        for (int d4 = 0; d4 < 4; ++d4) {
+            float4 er[4], ei[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                er[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 4 * d4);
+                ei[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 16 + 4 * d4);
+            }
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+                const int col = 4 * d4 + dd;
+                unsigned long long qa[4], qb[4], oa[4], ob[4];
+                {
+                    const ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(Qs + col * RR_QLDS);
+                    const ulonglong2 a1 = *reinterpret_cast<const ulonglong2 *>(Qs + col * RR_QLDS + 4);
+                    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(Qs + (16 + col) * RR_QLDS);
+                    const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(Qs + (16 + col) * RR_QLDS + 4);
+                    qa[0] = a0.x; qa[1] = a0.y; qa[2] = a1.x; qa[3] = a1.y;
+                    qb[0] = b0.x; qb[1] = b0.y; qb[2] = b1.x; qb[3] = b1.y;
+                }
+                if (OP == OP_ROT_S) {
+                    const ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(As + col * RR_QLDS);
+                    const ulonglong2 a1 = *reinterpret_cast<const ulonglong2 *>(As + col * RR_QLDS + 4);
+                    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(As + (16 + col) * RR_QLDS);
+                    const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(As + (16 + col) * RR_QLDS + 4);
+                    oa[0] = a0.x; oa[1] = a0.y; oa[2] = a1.x; oa[3] = a1.y;
+                    ob[0] = b0.x; ob[1] = b0.y; ob[2] = b1.x; ob[3] = b1.y;
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const float evr = dd == 0 ? er[m].x : dd == 1 ? er[m].y : dd == 2 ? er[m].z : er[m].w;
+                    const float evi = dd == 0 ? ei[m].x : dd == 1 ? ei[m].y : dd == 2 ? ei[m].z : ei[m].w;
+                    const unsigned long long er2 = rk_pk2(evr, evr), ei2 = rk_pk2(evi, evi);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        unsigned long long re, im;
+                        if (OP == OP_ROT_S) {  // RotatE.py:151-163: qa = cos, qb = sin, (oa, ob) = the object row
+                            re = rk_sub2(rk_fma2v(rk_pk2(-evi, -evi), qb[i], rk_mul2(er2, qa[i])), oa[i]);
+                            im = rk_sub2(rk_fma2v(ei2, qa[i], rk_mul2(er2, qb[i])), ob[i]);
+                        } else {  // RotatE.py:208-216: (qa, qb) = the rotated subject
+                            re = rk_sub2(qa[i], er2);
+                            im = rk_sub2(qb[i], ei2);
+                        }
+                        acc[m][i] = rk_mod_step2(acc[m][i], re, im);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // epilogue: quantise, compare with the positive, count over this warp's 128 candidates
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long q = q0 + qg * 8 + i;
+        const bool qok = q < p.b;
+        const int qp = qok ? p.qpos[q] : 0;
+        int gt = 0, eq = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            float lo, hi;
+            rk_upk2(acc[m][i >> 1], lo, hi);
+            const long long c = c0 + cg * 128 + lane + 32 * m;
+            const bool cok = c < p.n_cand;
+            const float sc = rank_finish<OP>((i & 1) ? hi : lo, p.scale);
+            if (p.scores && qok && cok) p.scores[(size_t)q * p.n_cand + c] = sc;
+            const int qc = quantise(sc);
+            gt += __popc(__ballot_sync(0xffffffffu, cok && (qp < qc)));
+            eq += __popc(__ballot_sync(0xffffffffu, cok && (qp == qc)));
+        }
+        if (lane == 0 && qok) {
+            if (gt) atomicAdd(&cnt[3 * q + 0], gt);
+            if (eq) atomicAdd(&cnt[3 * q + 1], eq);
+        }
+    }
+}
+
 cudaError_t launch_rank_count(const RankParams &p, int32_t *cnt, cudaStream_t st)
 {
     if (p.b == 0 || p.n_cand == 0) return cudaSuccess;
@@ -439,8 +640,16 @@ cudaError_t launch_rank_count(const RankParams &p, int32_t *cnt, cudaStream_t st
     }
     case OP_L1_ADD: KGE_RK(OP_L1_ADD)
     case OP_L1_SUB: KGE_RK(OP_L1_SUB)
-    case OP_ROT_S: KGE_RK(OP_ROT_S)
-    case OP_ROT_O: KGE_RK(OP_ROT_O)
+    case OP_ROT_S:
+    case OP_ROT_O: {
+        const bool subj = rank_op(p.L.model, p.side) == OP_ROT_S;
+        const size_t sm = 2 * RR_STAGE_FLOATS * sizeof(float);
+        auto kern = subj ? kge_rank_rot_kernel<OP_ROT_S> : kge_rank_rot_kernel<OP_ROT_O>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, RK_THREADS, sm, st>>>(p, cnt);
+        break;
+    }
     }
 #undef KGE_RK
     return cudaGetLastError();

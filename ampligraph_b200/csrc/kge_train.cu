@@ -339,24 +339,40 @@ struct Scorer<KGE_TRANSE, NIT> {
 // ---- RotatE (RotatE.py:76-104) --------------------------------------------
 // The relation row handed to this kernel is the per-step rotation table row
 // [cos(phi) | sin(phi)], phi = theta/div (kge_rotation_table_kernel).
-// f = -sum_d |R(phi) s - o|.  With (a,b) = residual/|residual|:
+// f = -sum_d |R(phi) s - o|.  With (a,b) = g * residual/|residual|:
 //   df/do = (a,b); df/ds = -R(-phi)(a,b); df/dphi = a*y_im - b*y_re, y = R(phi) s.
 // The reference's gradient is NaN at an exactly-zero residual; here it is 0.
+//
+// The kernel is FP32-issue bound on this model (profiles/r2a_train_cfg4_ncu_full_summary.json), so the
+// scorer is written to a per-element instruction budget: every float4 operation is two packed f32x2
+// instructions, NEGATED copies of the per-positive vectors (-cos, -sin, -y) are kept in registers so that no
+// residual needs a separate negate or subtract (the residual's sign is irrelevant to the modulus and is
+// folded into the scalar g for the unit vector), the modulus is one MUFU.SQRT, the unit vector one MUFU.RSQ
+// on max(x, tiny) (an exactly-zero residual gives 0 * finite = 0), and lanes past the end of the window are
+// masked arithmetically (they read the window's last chunk; only their stores are predicated) so the row
+// loops carry no divergence bookkeeping.
 template <int NIT>
 struct Scorer<KGE_ROTATE, NIT> {
     static constexpr bool kQuad = false;
-    float4 Cs[NIT], Sn[NIT], Yr[NIT], Yi[NIT], Or_[NIT], Oi[NIT];
-    float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], Aphi[NIT];
+    float4 C[NIT], Sn[NIT], nC[NIT], nS[NIT], Or_[NIT], Oi[NIT], nYr[NIT], nYi[NIT];
+    float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], A1[NIT], A2[NIT];  // df/dphi of the subject side = A1 - A2
+    float nlive[NIT];  // -1 for a lane that owns a chunk of this window, 0 past its end
     int lane, nch, cs = 32, kp, hs;  // cs: chunk stride = lanes on one positive; kp: half stride in HBM rows, hs: half stride of the staged row window
-    // (a, b) = g * residual / |residual|, zero where the residual is exactly zero
+    __device__ __forceinline__ int chunk(int it) const { return min(lane + cs * it, nch - 1); }
+    // sum of the four moduli of (re, im)
+    static __device__ __forceinline__ float modsum(float4 re, float4 im)
+    {
+        const float4 x = f4fma(im, im, re * re);
+        return (sqrt_approx(x.x) + sqrt_approx(x.y)) + (sqrt_approx(x.z) + sqrt_approx(x.w));
+    }
+    // (a, b) = g * (re, im) / |(re, im)|, zero where the residual is exactly zero
     static __device__ __forceinline__ void unit(float4 re, float4 im, float g, float4 &a, float4 &b)
     {
-        const float x0 = fmaf(im.x, im.x, re.x * re.x), x1 = fmaf(im.y, im.y, re.y * re.y);
-        const float x2 = fmaf(im.z, im.z, re.z * re.z), x3 = fmaf(im.w, im.w, re.w * re.w);
-        const float i0 = x0 > 0.f ? g * rsqrtf(x0) : 0.f, i1 = x1 > 0.f ? g * rsqrtf(x1) : 0.f;
-        const float i2 = x2 > 0.f ? g * rsqrtf(x2) : 0.f, i3 = x3 > 0.f ? g * rsqrtf(x3) : 0.f;
-        a = make_float4(re.x * i0, re.y * i1, re.z * i2, re.w * i3);
-        b = make_float4(im.x * i0, im.y * i1, im.z * i2, im.w * i3);
+        const float4 x = f4fma(im, im, re * re);
+        const float4 inv = g * make_float4(rsqrt_approx(fmaxf(x.x, 1e-30f)), rsqrt_approx(fmaxf(x.y, 1e-30f)),
+                                           rsqrt_approx(fmaxf(x.z, 1e-30f)), rsqrt_approx(fmaxf(x.w, 1e-30f)));
+        a = re * inv;
+        b = im * inv;
     }
     __device__ __forceinline__ float prep(const float *s, const float *p, const float *o, int ln)
     {
@@ -364,20 +380,30 @@ struct Scorer<KGE_ROTATE, NIT> {
         float acc = 0.f;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + cs * it;
+            const int c = lane + cs * it;
             float4 sr = f4zero(), si = f4zero();
-            Cs[it] = Sn[it] = Or_[it] = Oi[it] = f4zero();
+            C[it] = Sn[it] = Or_[it] = Oi[it] = f4zero();
+            nlive[it] = 0.f;
             if (c < nch) {
                 sr = f4ld(s + 4 * c); si = f4ld(s + hs + 4 * c);
-                Cs[it] = f4ld(p + 4 * c); Sn[it] = f4ld(p + hs + 4 * c);
+                C[it] = f4ld(p + 4 * c); Sn[it] = f4ld(p + hs + 4 * c);
                 Or_[it] = f4ld(o + 4 * c); Oi[it] = f4ld(o + hs + 4 * c);
+                nlive[it] = -1.f;
             }
-            Yr[it] = sr * Cs[it] - si * Sn[it];
-            Yi[it] = f4fma(sr, Sn[it], si * Cs[it]);
-            Zor[it] = Zoi[it] = Zsr[it] = Zsi[it] = Aphi[it] = f4zero();
-            acc -= f4mod_sum(Yr[it] - Or_[it], Yi[it] - Oi[it]);
+            nC[it] = f4neg(C[it]);
+            nS[it] = f4neg(Sn[it]);
+            nYr[it] = f4fma(si, Sn[it], sr * nC[it]);  // -(sr c - si s)
+            nYi[it] = f4fma(sr, nS[it], si * nC[it]);  // -(sr s + si c)
+            Zor[it] = Zoi[it] = Zsr[it] = Zsi[it] = A1[it] = A2[it] = f4zero();
+            acc = fmaf(modsum(Or_[it] + nYr[it], Oi[it] + nYi[it]), nlive[it], acc);
         }
         return acc;
+    }
+    // o - R(phi) r, as two dependent packed fmas per component
+    __device__ __forceinline__ void neg_residual_subj(int it, float4 rr, float4 ri, float4 &re, float4 &im) const
+    {
+        re = f4fma(ri, Sn[it], f4fma(rr, nC[it], Or_[it]));
+        im = f4fma(ri, nC[it], f4fma(rr, nS[it], Oi[it]));
     }
     template <int SIDE>
     __device__ __forceinline__ void partial2(const float *ra, const float *rb, float &pa, float &pb) const
@@ -385,38 +411,42 @@ struct Scorer<KGE_ROTATE, NIT> {
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + cs * it;
-            if (c < nch) {
-                float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + hs + 4 * c);
-                float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + hs + 4 * c);
-                if (SIDE) {
-                    a -= f4mod_sum(Yr[it] - ar, Yi[it] - ai);
-                    b -= f4mod_sum(Yr[it] - br, Yi[it] - bi);
-                } else {
-                    a -= f4mod_sum((ar * Cs[it] - ai * Sn[it]) - Or_[it], f4fma(ar, Sn[it], ai * Cs[it]) - Oi[it]);
-                    b -= f4mod_sum((br * Cs[it] - bi * Sn[it]) - Or_[it], f4fma(br, Sn[it], bi * Cs[it]) - Oi[it]);
-                }
+            const int c = chunk(it);
+            const float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + hs + 4 * c);
+            const float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + hs + 4 * c);
+            if (SIDE) {  // r - y
+                a = fmaf(modsum(ar + nYr[it], ai + nYi[it]), nlive[it], a);
+                b = fmaf(modsum(br + nYr[it], bi + nYi[it]), nlive[it], b);
+            } else {
+                float4 e0, e1, e2, e3;
+                neg_residual_subj(it, ar, ai, e0, e1);
+                neg_residual_subj(it, br, bi, e2, e3);
+                a = fmaf(modsum(e0, e1), nlive[it], a);
+                b = fmaf(modsum(e2, e3), nlive[it], b);
             }
         }
         pa = a;
         pb = b;
     }
+    // ng = -g: the residuals below are the NEGATED ones, so (a, b) = ng * (-residual) / |residual| has the true sign
     template <int SIDE, class Sink>
-    __device__ __forceinline__ void grad1(float *r, float *grow, float g, int it, int c, bool emit)
+    __device__ __forceinline__ void grad1(float *r, float *grow, float ng, int it, int c, bool emit)
     {
-        float4 rr = f4ld(r + 4 * c), ri = f4ld(r + hs + 4 * c), a, b;
+        const float4 rr = f4ld(r + 4 * c), ri = f4ld(r + hs + 4 * c);
+        float4 a, b;
         if (SIDE) {  // residual = y(s) - r ; df/dr = +(a,b)
-            unit(Yr[it] - rr, Yi[it] - ri, g, a, b);
+            unit(rr + nYr[it], ri + nYi[it], ng, a, b);
             Zor[it] = Zor[it] + a; Zoi[it] = Zoi[it] + b;
             if (emit) { Sink::put(r, grow, 4 * c, 4 * c, a); Sink::put(r, grow, hs + 4 * c, kp + 4 * c, b); }
         } else {  // residual = R(phi) r - o ; df/dr = -R(-phi)(a,b)
-            float4 yr = rr * Cs[it] - ri * Sn[it], yi = f4fma(rr, Sn[it], ri * Cs[it]);
-            unit(yr - Or_[it], yi - Oi[it], g, a, b);
+            const float4 nyr = f4fma(ri, Sn[it], rr * nC[it]), nyi = f4fma(rr, nS[it], ri * nC[it]);  // -R(phi) r
+            unit(Or_[it] + nyr, Oi[it] + nyi, ng, a, b);
             Zsr[it] = Zsr[it] + a; Zsi[it] = Zsi[it] + b;
-            Aphi[it] = Aphi[it] + (a * yi - b * yr);
+            A1[it] = f4fma(b, nyr, A1[it]);  // a*y_im - b*y_re = b*nyr - a*nyi
+            A2[it] = f4fma(a, nyi, A2[it]);
             if (emit) {
-                Sink::put(r, grow, 4 * c, 4 * c, f4neg(f4fma(a, Cs[it], b * Sn[it])));
-                Sink::put(r, grow, hs + 4 * c, kp + 4 * c, a * Sn[it] - b * Cs[it]);
+                Sink::put(r, grow, 4 * c, 4 * c, f4fma(b, nS[it], a * nC[it]));          // -(a c + b s)
+                Sink::put(r, grow, hs + 4 * c, kp + 4 * c, f4fma(b, nC[it], a * Sn[it]));  // a s - b c
             }
         }
     }
@@ -426,11 +456,10 @@ struct Scorer<KGE_ROTATE, NIT> {
     {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            int c = lane + cs * it;
-            if (c < nch) {
-                grad1<SIDE, Sink>(ra, ga_row, ga, it, c, true);
-                grad1<SIDE, Sink>(rb, gb_row, gb, it, c, has_b);  // gb == 0 when !has_b: contributes nothing
-            }
+            const int c = chunk(it);
+            const bool live = lane + cs * it < nch;  // dead lanes run the arithmetic on the last chunk; their accumulators are never read
+            grad1<SIDE, Sink>(ra, ga_row, -ga, it, c, live);
+            grad1<SIDE, Sink>(rb, gb_row, -gb, it, c, live && has_b);  // gb == 0 when !has_b: contributes nothing
         }
     }
     // p row receives d/dtheta = (1/div) d/dphi in its first half, zeros in the second
@@ -444,13 +473,14 @@ struct Scorer<KGE_ROTATE, NIT> {
             int c = lane + cs * it;
             if (c < nch) {
                 float4 a, b;
-                unit(Yr[it] - Or_[it], Yi[it] - Oi[it], gP, a, b);
-                float4 Zr = a + Zor[it], Zi = b + Zoi[it];  // everything with y = R(phi) s
-                Sink::put(s, gs, 4 * c, 4 * c, f4neg(f4fma(Zr, Cs[it], Zi * Sn[it])));
-                Sink::put(s, gs, hs + 4 * c, kp + 4 * c, Zr * Sn[it] - Zi * Cs[it]);
+                unit(Or_[it] + nYr[it], Oi[it] + nYi[it], -gP, a, b);  // gP * (y - o)/|y - o|
+                const float4 Zr = a + Zor[it], Zi = b + Zoi[it];  // everything with y = R(phi) s
+                Sink::put(s, gs, 4 * c, 4 * c, f4fma(Zi, nS[it], Zr * nC[it]));          // -(Zr c + Zi s)
+                Sink::put(s, gs, hs + 4 * c, kp + 4 * c, f4fma(Zi, nC[it], Zr * Sn[it]));  // Zr s - Zi c
                 Sink::put(o, go, 4 * c, 4 * c, a + Zsr[it]);
                 Sink::put(o, go, hs + 4 * c, kp + 4 * c, b + Zsi[it]);
-                Sink::put(p, gp, 4 * c, 4 * c, inv_div * (Aphi[it] + (Zr * Yi[it] - Zi * Yr[it])));
+                // Aphi + (Zr*Yi - Zi*Yr) = (A1 + Zi*nYr) - (A2 + Zr*nYi)
+                Sink::put(p, gp, 4 * c, 4 * c, inv_div * (f4fma(Zi, nYr[it], A1[it]) - f4fma(Zr, nYi[it], A2[it])));
             }
         }
     }
@@ -661,10 +691,12 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                 if (use_stash) stash_rows(buf, cb, j0, gsz);
                 if (g == 0) P += warp_sum(S.prep(srow, prow, orow, lane));
                 float *const nrows = nbuf(buf);
+                // reduce the two partials over the warp (lower half-warp ends up with a's sum, upper with b's) and store
                 auto store = [&](int a, int b, bool has_b, float pa, float pb) {
-                    if (lane == 0) {
-                        if (resident) { sc[j0 + a] = pa; if (has_b) sc[j0 + b] = pb; }
-                        else { sc[j0 + a] += pa; if (has_b) sc[j0 + b] += pb; }
+                    const float v = warp_sum2t(pa, pb, lane);
+                    if ((lane & 15) == 0 && (lane == 0 || has_b)) {
+                        const int t = j0 + (lane ? b : a);
+                        if (resident) sc[t] = v; else sc[t] += v;
                     }
                 };
                 // slots [j0, j0+gsz) of this group: the part below n0 replaced the subject, the rest the object
@@ -692,7 +724,6 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                         const int b = has_b ? a + 1 : a;
                         float pa, pb;
                         S.template partial2<SIDE>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
-                        warp_sum2(pa, pb);
                         store(a, b, has_b, pa, pb);
                     };
                     auto side_range = [&](int lo, int hi, auto side_tag) {
@@ -709,7 +740,6 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                     const int b = has_b ? a + 1 : a;
                     float pa, pb;
                     S.template partial2<0>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
-                    warp_sum2(pa, pb);
                     store(a, b, has_b, pa, pb);
                 }
                 for (int t = b1; t < j0 + gsz; t += 2) {
@@ -718,7 +748,6 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                     const int b = has_b ? a + 1 : a;
                     float pa, pb;
                     S.template partial2<1>(nrows + (size_t)a * lw, nrows + (size_t)b * lw, pa, pb);
-                    warp_sum2(pa, pb);
                     store(a, b, has_b, pa, pb);
                 }
                 }

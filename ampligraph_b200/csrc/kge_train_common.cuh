@@ -92,18 +92,23 @@ struct SinkRed {
     static __device__ __forceinline__ void put(float *, float *grow, int, int goff, float4 v) { red_add_v4(grow + goff, v); }
 };
 
-// |z| = x * rsqrt(x), x = re^2 + im^2: one MUFU.RSQ instead of an IEEE sqrt (and, in the gradient, instead of
-// sqrt + divide).  rsqrtf is accurate to 2 ulp, far inside the 1e-4 training tolerance; the RANKING kernels keep
-// the correctly rounded sqrt because their scores must be bit-identical to the oracle.
-__device__ __forceinline__ float fast_mod(float re, float im)
+// RotatE's modulus and unit vector use the MUFU approximations (sqrt.approx: 2^-23 relative, rsqrt.approx: 2 ulp), far
+// inside the 1e-4 training tolerance; the RANKING kernels keep the correctly rounded sqrt because their scores must be
+// bit-identical to the oracle.
+// single-instruction MUFU forms (flush-to-zero: a denormal x = re^2 + im^2 means a residual below 1e-19)
+__device__ __forceinline__ float sqrt_approx(float x)
 {
-    const float x = fmaf(im, im, re * re);
-    return x > 0.f ? x * rsqrtf(x) : 0.f;
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
-__device__ __forceinline__ float f4mod_sum(float4 re, float4 im)
+__device__ __forceinline__ float rsqrt_approx(float x)
 {
-    return (fast_mod(re.x, im.x) + fast_mod(re.y, im.y)) + (fast_mod(re.z, im.z) + fast_mod(re.w, im.w));
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
+
 
 
 __device__ __forceinline__ void warp_sum2(float &a, float &b)
@@ -113,6 +118,20 @@ __device__ __forceinline__ void warp_sum2(float &a, float &b)
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
     }
+}
+
+// Two warp sums for the price of five shuffles (instead of ten): after the xor-16 step the lower half-warp carries a and
+// the upper one b; four more steps finish each sum inside its half.  On return lanes [0,16) hold sum(a), lanes [16,32) sum(b).
+__device__ __forceinline__ float warp_sum2t(float a, float b, int lane)
+{
+    const bool hi16 = (lane & 16) != 0;
+    float k = hi16 ? b : a;
+    k += __shfl_xor_sync(0xffffffffu, hi16 ? a : b, 16);
+    k += __shfl_xor_sync(0xffffffffu, k, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
 }
 
 // Four warp sums for the price of six shuffles: a transposed butterfly.  After the xor-16 step the lower half-warp

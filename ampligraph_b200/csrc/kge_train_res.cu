@@ -421,7 +421,9 @@ cudaError_t launch_train_res(const TrainParams &p, int nit, int sm_count, int th
     if (p.B == 0) return cudaSuccess;
     const bool two = p.model != KGE_DISTMULT;
     if (nit <= 1) return two ? launch_res<2, 1>(p, sm_count, threads, smem, st) : launch_res<1, 1>(p, sm_count, threads, smem, st);
-    return two ? launch_res<2, 2>(p, sm_count, threads, smem, st) : launch_res<1, 2>(p, sm_count, threads, smem, st);
+    if (nit == 2) return two ? launch_res<2, 2>(p, sm_count, threads, smem, st) : launch_res<1, 2>(p, sm_count, threads, smem, st);
+    if (two) return cudaErrorInvalidValue;  // rows of 512+ floats per half: only DistMult's per-lane state fits the register file (kge_create)
+    return launch_res<1, 4>(p, sm_count, threads, smem, st);
 }
 
 }  // namespace kge
