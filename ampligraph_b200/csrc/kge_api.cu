@@ -19,15 +19,16 @@ struct kge_handle {
     float rot_div;      // RotatE range/pi
     // the only device memory the library owns (allocated once by kge_create, freed by kge_destroy):
     float *rot;              // [n_rel, ld] rotation table (RotatE only)
-    unsigned *done_counter;  // last-CTA counter of kge_optimizer_step_exchange
+    unsigned *done_counter;  // [0]: last-CTA counter of kge_optimizer_step_exchange; [1], [2]: the training kernels' positive counter and retired-warp counter (self-resetting)
     unsigned long long *exchange_trace;  // caller-owned 8 x uint64 phase stamps of the next exchange launches, or nullptr
     // training launch geometry
-    int nit, G, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats, resident;
+    int nit, G, nbuf, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats, resident;
     int res_warps, res_rows_bytes, res_region_bytes;  // slot geometry of the resident trilinear fast path (kge_train_res.cu); res_warps = 0: not applicable
     int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
     float *stash;                // caller-owned row stash for sharded runs (kge_set_row_stash) or nullptr
     long long stash_rows;
     int hot_ent[2];              // kge_set_hot_entities (-1: none)
+    int l2_bytes;                // cudaDeviceProp::l2CacheSize
 };
 
 // Make the handle's device current for the duration of an entry point (two handles on different GPUs
@@ -124,6 +125,7 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     L.K = L.halves * cfg->k;
     h->sm_count = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    h->l2_bytes = prop.l2CacheSize;
     h->score_scale = (cfg->scoring == KGE_HOLE) ? hole_scale(L.K) : 1.f;
     h->rot_div = (cfg->scoring == KGE_ROTATE) ? rotate_divisor(L.K, cfg->max_rel_size > 0 ? cfg->max_rel_size : cfg->n_rel) : 1.f;
 
@@ -138,7 +140,11 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
     h->eta_pad = (cfg->eta + 3) / 4 * 4;
     const int row_bytes = L.halves * h->wk * 4, aux = 4 * h->eta_pad * 4 + 16;  // sc | nid | nside | jorig, two mbarriers
     h->slot_floats = row_bytes / 4;
-    const int max_warps = KGE_TRAIN_THREADS(cfg->scoring, h->nit) / 32;
+    int max_warps = KGE_TRAIN_THREADS(cfg->scoring, h->nit) / 32;
+    int nbuf = 2;  // group buffers of a non-resident slot
+    // tuning aids (scripts/kbench.py): cap the warps per CTA, choose the buffering of non-resident slots
+    if (const char *ev = getenv("KGE_B200_TRAIN_WARPS")) { const int w = atoi(ev); if (w >= 1 && w < max_warps) max_warps = w; }
+    if (const char *ev = getenv("KGE_B200_TRAIN_NBUF")) nbuf = atoi(ev) == 1 ? 1 : 2;
     // Residency policy, tuned on B200 (scripts/kbench.py sweep, profiles/): keep all eta corruptions resident
     // (one gather per row) while >= KGE_MIN_RESIDENT_WARPS warps still fit; otherwise shrink G until
     // min(max_warps, KGE_TARGET_WARPS) warps fit -- the gradient pass then re-gathers the other groups, which
@@ -155,12 +161,13 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
         if (!res || full * min_res > h->max_smem) {
             res = false;
             const int want = max_warps < KGE_TARGET_WARPS ? max_warps : KGE_TARGET_WARPS;
-            while (G > 1 && (long long)((3 + 2 * G) * (long long)row_bytes + aux) * want > h->max_smem) --G;
+            while (G > 1 && (long long)((3 + nbuf * G) * (long long)row_bytes + aux) * want > h->max_smem) --G;
         }
     }
     h->resident = res ? 1 : 0;
     h->G = G;
-    h->rows_bytes = (res ? 3 + G : 3 + 2 * G) * row_bytes;
+    h->nbuf = nbuf;
+    h->rows_bytes = (res ? 3 + G : 3 + nbuf * G) * row_bytes;
     h->region_bytes = h->rows_bytes + aux;
     int warps = h->max_smem / h->region_bytes;
     if (warps > max_warps) warps = max_warps;
@@ -190,8 +197,8 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
         if (e2 != cudaSuccess) { delete h; return cuda_fail(e2, "cudaMalloc(rotation table)"); }
     }
     {
-        cudaError_t e2 = cudaMalloc(&h->done_counter, sizeof(unsigned));
-        if (e2 == cudaSuccess) e2 = cudaMemset(h->done_counter, 0, sizeof(unsigned));
+        cudaError_t e2 = cudaMalloc(&h->done_counter, 4 * sizeof(unsigned));
+        if (e2 == cudaSuccess) e2 = cudaMemset(h->done_counter, 0, 4 * sizeof(unsigned));
         if (e2 != cudaSuccess) { if (h->rot) cudaFree(h->rot); delete h; return cuda_fail(e2, "cudaMalloc(counter)"); }
     }
     *out = h;
@@ -373,6 +380,7 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
     p.ld = h->L.ld;
     p.nch = h->L.kp / 4;
     p.G = h->G;
+    p.nbuf = h->nbuf;
     p.wk = h->wk;
     p.n_cb = h->n_cb;
     p.slot_floats = h->slot_floats;
@@ -411,7 +419,20 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
     // KGE_B200_TRAIN_KERNEL=general keeps every shape on the general kernel (A/B runs, and the tests that cover its resident
     // trilinear instantiations); default: the specialised kernel of kge_train_res.cu where it applies
     const char *force = getenv("KGE_B200_TRAIN_KERNEL");
-    if (h->res_warps > 0 && p.shard_world <= 1 && p.stash == nullptr && !(force && strcmp(force, "general") == 0)) {
+    const bool fast = h->res_warps > 0 && p.shard_world <= 1 && p.stash == nullptr && !(force && strcmp(force, "general") == 0);
+    // Dynamic assignment of positives to warps (kge_train_common.cuh) where it was measured to pay: the resident fast path on
+    // tables that live in L2 with enough positives per warp for the imbalance to matter -- cfg2 145 -> 137 us.  On an
+    // HBM-resident table it LOSES (`big`, 3.2 GB: 668 -> 905 us, reproducibly; the general kernel on cfg4 / cfg5w: +-1 %),
+    // so those keep the static stride (profiles/r2o_kbench_{static,dynamic}.log).  KGE_B200_TRAIN_SCHED=static|dynamic forces.
+    {
+        const char *ev = getenv("KGE_B200_TRAIN_SCHED");
+        const long long n_warps = (long long)h->sm_count * (fast ? h->res_warps : h->warps);
+        bool dyn = fast && B >= 8 * n_warps && 2ll * h->cfg.n_ent * h->L.ld * 4 <= (long long)h->l2_bytes;
+        if (ev && strcmp(ev, "static") == 0) dyn = false;
+        if (ev && strcmp(ev, "dynamic") == 0) dyn = true;
+        p.sched = (dyn && B < (1ll << 24)) ? h->done_counter + 1 : nullptr;  // float counter: exact below 2^24
+    }
+    if (fast) {
         p.rows_bytes = h->res_rows_bytes;
         p.region_bytes = h->res_region_bytes;
         KGE_CUDA(launch_train_res(p, h->nit, h->sm_count, h->res_warps * 32, (size_t)h->res_warps * h->res_region_bytes, st),

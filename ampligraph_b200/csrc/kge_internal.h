@@ -4,6 +4,7 @@
 
 // per-lane register state grows with NIT (float4 chunks per lane): trade threads for registers
 // (RotatE carries 11 float4 vectors of per-positive state per chunk: give it more registers)
+// (RotatE with 12 warps at 168 registers was measured against 8 warps at 229: 273 us vs 267 us on cfg4, profiles/r2m_kbench_cfg4_sweep.log)
 #define KGE_TRAIN_THREADS(model, nit) ((nit) <= 1 ? 512 : (nit) == 2 ? ((model) == KGE_ROTATE ? 256 : 384) : 256)
 #define KGE_MAX_PEERS 8
 #define KGE_MIN_RESIDENT_WARPS 8  // tuned on B200: fewer warps/SM than this costs more than re-gathering
@@ -25,6 +26,7 @@ struct TrainParams {
     unsigned n_ent;
     int model, eta, kp, ld, nch;  // nch = kp/4 float4 chunks per half
     int G;                        // replaced rows resident per pass
+    int nbuf;                     // group buffers per slot (non-resident): 2 = next group prefetched, 1 = fetched on demand
     int wk, n_cb;                 // column window (floats per half) and number of windows per row
     int slot_floats;              // stride between row windows in the shared-memory slot
     int resident;                 // 1: one window, one group, rows stay in place between the passes
@@ -45,6 +47,7 @@ struct TrainParams {
     int *stamp_ent_shard[KGE_MAX_PEERS];
     int hot_ent[2];  // entities whose subject/object gradient rows are summed per warp before they are scattered (-1: none); fast path only
     float *stash;  // [B, eta, ld] local copy of the replaced rows gathered by the score pass (sharded runs) or nullptr
+    unsigned *sched;  // {next positive, retired warps}: dynamic assignment of positives to warps (see next_positive), or nullptr = static stride
 };
 
 // grid = min(occupancy * sm_count, ceil(B / warps))

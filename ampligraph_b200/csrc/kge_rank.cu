@@ -17,6 +17,8 @@
 // order): the kernel is an fp32-FMA register-tiled contraction.  Zero pad columns
 // are exact no-ops in every chain (fma(0,0,a)=a, a+|0|=a, a+sqrt(0)=a).
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "kge_rank_common.cuh"
 
@@ -416,20 +418,29 @@ __global__ void __launch_bounds__(RD_THREADS, 2) kge_rank_dot_kernel(const RankP
 }
 
 // --------------------------------------------------------------------------
-// RotatE specialisation: CTA = 256 candidates x 32 queries (the tile kernel's geometry), thread tile = 4 candidates x
-// 8 queries, accumulators as 16 f32x2 pairs of ADJACENT QUERIES.  As in the DOT kernel the query tile (and, on the
-// subject side, the tile of object rows) is staged transposed ([column][query]), so one broadcast 128-bit read returns
-// four queries of one column and every packed instruction advances two canonical chains: per pair of chain steps the
-// object side issues 2 FADD2 + FMUL2 + FFMA2 (residual, x = re^2 + im^2), 2 FMNMX + 2 MUFU.RSQ, 2 FMUL2 + 2 FFMA2 (the
-// correctly rounded sqrt of kge_rank_common.cuh, same five operations per chain), 2 FSET and one FFMA2 that adds
-// [x >= 2^-101] * sqrt to the accumulators -- 15 issue slots instead of 26.  Every operation is the IEEE operation of the
-// scalar chain (rank_step_rot) on the same operands in the same order: a - b, a * b and fma are sign-symmetric, the
-// negations are operand modifiers, fma(r, 1, acc) == acc + r and fma(r, 0, acc) == acc for finite r.
+// TransE / RotatE specialisation ("pair" kernel): CTA = 256 candidates x 32 queries (the tile kernel's geometry), thread
+// tile = 4 candidates x 8 queries, accumulators as 16 f32x2 pairs of ADJACENT QUERIES.  As in the DOT kernel the query
+// tile (and, on RotatE's subject side, the tile of object rows) is staged transposed ([column][query]), so one broadcast
+// 128-bit read returns four queries of one column and every packed instruction advances two canonical chains:
+//   TransE: acc += |e + q| (or |q - e|) is FADD2 + FADD2 with the absolute value as an operand modifier: one issue slot
+//     per chain step instead of two;
+//   RotatE, per pair of chain steps: 2 FADD2 + FMUL2 + FFMA2 (residual, x = re^2 + im^2; the subject side adds the rotation:
+//     2 FMUL2 + 2 FFMA2), 2 FMNMX + 2 MUFU.RSQ, 2 FMUL2 + 2 FFMA2 (the correctly rounded sqrt of kge_rank_common.cuh,
+//     same five operations per chain), 2 FSET and one FFMA2 that adds [x >= 2^-101] * sqrt -- 15 issue slots instead of 26.
+// Every operation is the IEEE operation of the scalar chain (rank_step / rank_step_rot) on the same operands in the same
+// order: a - b, a * b and fma are sign-symmetric, negations and absolute values are operand modifiers, fma(r, 1, acc) ==
+// acc + r and fma(r, 0, acc) == acc for finite r.
 // --------------------------------------------------------------------------
 constexpr int RR_QLDS = RK_TQ + 4;                 // row stride of the transposed query tile
-constexpr int RR_Q_FLOATS = 32 * RR_QLDS;          // 16 re columns + 16 im columns
+constexpr int RR_Q_FLOATS = 32 * RR_QLDS;          // 32 tile columns (RotatE: 16 re + 16 im)
 constexpr int RR_STAGE_FLOATS = RK_E_FLOATS + 2 * RR_Q_FLOATS;
 
+__device__ __forceinline__ unsigned long long rk_add2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ unsigned long long rk_sub2(unsigned long long a, unsigned long long b)
 {
     unsigned long long d;
@@ -455,6 +466,13 @@ __device__ __forceinline__ unsigned long long rk_fma2v(unsigned long long a, uns
     return d;
 }
 __device__ __forceinline__ void rk_upk2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// acc + |v| for two chains (the absolute value becomes an operand modifier of the FADD2)
+__device__ __forceinline__ unsigned long long rk_add_abs2(unsigned long long acc, unsigned long long v)
+{
+    float lo, hi;
+    rk_upk2(v, lo, hi);
+    return rk_add2(acc, rk_pk2(fabsf(lo), fabsf(hi)));
+}
 
 // acc += sqrt_rn_nonneg(re^2 + im^2) for two chains at once (see sqrt_rn_nonneg for the five-operation sqrt)
 __device__ __forceinline__ unsigned long long rk_mod_step2(unsigned long long acc, unsigned long long re, unsigned long long im)
@@ -476,17 +494,19 @@ __device__ __forceinline__ unsigned long long rk_mod_step2(unsigned long long ac
 }
 
 template <int OP>
-__global__ void __launch_bounds__(RK_THREADS, 2) kge_rank_rot_kernel(const RankParams p, int32_t *__restrict__ cnt)
+__global__ void __launch_bounds__(RK_THREADS, 2) kge_rank_pair_kernel(const RankParams p, int32_t *__restrict__ cnt)
 {
-    static_assert(OP == OP_ROT_S || OP == OP_ROT_O, "RotatE only");
+    static_assert(OP != OP_DOT, "the bilinear models have kge_rank_dot_kernel");
+    constexpr bool ROT = (OP == OP_ROT_S || OP == OP_ROT_O);
     extern __shared__ __align__(128) float smem[];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int cg = warp & 1, qg = warp >> 1;  // 2 candidate groups of 128, 4 query groups of 8
     const long long c0 = (long long)blockIdx.x * RK_TC, q0 = (long long)blockIdx.y * RK_TQ;
     const int ld = p.L.ld, kp = p.L.kp;
-    const int n_chunks = (kp + 15) / 16;
+    const int n_chunks = ROT ? (kp + 15) / 16 : (ld + RK_DK - 1) / RK_DK;
+    const int col_end = ROT ? kp : ld;  // valid columns per half (ROT) / per row
 
-    // E staging as in the tile kernel: rows t/8 + 32n (n<8), column quad t%8 (quads 0-3: re columns, 4-7: im columns)
+    // E staging as in the tile kernel: rows t/8 + 32n (n<8), column quad t%8 (ROT: quads 0-3 re columns, 4-7 im columns)
     const int lrow = t >> 3, c4 = t & 7;
     const float *erow[8];
     bool evalid[8];
@@ -497,22 +517,22 @@ __global__ void __launch_bounds__(RK_THREADS, 2) kge_rank_rot_kernel(const RankP
         long long id = evalid[n] ? (p.cand_ids ? (long long)p.cand_ids[c] : p.cand_begin + c) : 0;
         erow[n] = p.ent + (size_t)id * ld;
     }
-    // Q (and A) staging, transposed: tile column t%32 (0-15 re, 16-31 im), queries t/32 + 8n (n<4), 4-byte copies
+    // Q (and A) staging, transposed: tile column t%32 (ROT: 0-15 re, 16-31 im), queries t/32 + 8n (n<4), 4-byte copies
     const int qd = t & 31, qq = t >> 5;
 
     auto stage_load = [&](int chunk, int buf) {
         float *Es = smem + buf * RR_STAGE_FLOATS, *Qs = Es + RK_E_FLOATS, *As = Qs + RR_Q_FLOATS;
         {
-            const int d = chunk * 16 + 4 * (c4 & 3);
-            const bool cvalid = d < kp;
-            const int col = cvalid ? (c4 < 4 ? 0 : kp) + d : 0;
+            const int d = ROT ? chunk * 16 + 4 * (c4 & 3) : chunk * RK_DK + 4 * c4;
+            const bool cvalid = d < col_end;
+            const int col = cvalid ? (ROT && c4 >= 4 ? kp : 0) + d : 0;
 #pragma unroll
             for (int n = 0; n < 8; ++n)
                 cp_async16(Es + (lrow + 32 * n) * RK_LDS + 4 * c4, erow[n] + col, cvalid && evalid[n]);
         }
-        const int d = chunk * 16 + (qd & 15);
-        const bool qcvalid = d < kp;
-        const int qcol = (qd < 16 ? 0 : kp) + d;
+        const int d = ROT ? chunk * 16 + (qd & 15) : chunk * RK_DK + qd;
+        const bool qcvalid = d < col_end;
+        const int qcol = (ROT && qd >= 16 ? kp : 0) + d;
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
             const long long q = q0 + qq + 8 * n;
@@ -523,6 +543,12 @@ __global__ void __launch_bounds__(RK_THREADS, 2) kge_rank_rot_kernel(const RankP
         }
         cp_async_commit();
     };
+    // four adjacent query pairs of one tile column
+    auto ldq = [](const float *row, unsigned long long (&v)[4]) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(row), b = *reinterpret_cast<const ulonglong2 *>(row + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    };
+    auto comp = [](const float4 &v, int dd) { return dd == 0 ? v.x : dd == 1 ? v.y : dd == 2 ? v.z : v.w; };
 
     unsigned long long acc[4][4];  // [candidate][query pair]
 #pragma unroll
@@ -539,50 +565,58 @@ __global__ void __launch_bounds__(RK_THREADS, 2) kge_rank_rot_kernel(const RankP
         const float *Es = smem + buf * RR_STAGE_FLOATS + (cg * 128 + lane) * RK_LDS;
         const float *Qs = smem + buf * RR_STAGE_FLOATS + RK_E_FLOATS + qg * 8;
         const float *As = Qs + RR_Q_FLOATS;
+        if constexpr (!ROT) {
 #pragma unroll
-        for (int d4 = 0; d4 < 4; ++d4) {
-            float4 er[4], ei[4];
+            for (int d4 = 0; d4 < RK_DK / 4; ++d4) {
+                float4 e[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                er[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 4 * d4);
-                ei[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 16 + 4 * d4);
+                for (int m = 0; m < 4; ++m) e[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 4 * d4);
+#pragma unroll
+                for (int dd = 0; dd < 4; ++dd) {
+                    unsigned long long q[4];
+                    ldq(Qs + (4 * d4 + dd) * RR_QLDS, q);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const float ev = comp(e[m], dd);
+                        const unsigned long long e2 = rk_pk2(ev, ev);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)  // TransE.py:78-84 (e + q) / :107-113 (q - e)
+                            acc[m][i] = rk_add_abs2(acc[m][i], OP == OP_L1_ADD ? rk_add2(e2, q[i]) : rk_sub2(q[i], e2));
+                    }
+                }
             }
+        } else {
 #pragma unroll
-            for (int dd = 0; dd < 4; ++dd) {
-                const int col = 4 * d4 + dd;
-                unsigned long long qa[4], qb[4], oa[4], ob[4];
-                {
-                    const ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(Qs + col * RR_QLDS);
-                    const ulonglong2 a1 = *reinterpret_cast<const ulonglong2 *>(Qs + col * RR_QLDS + 4);
-                    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(Qs + (16 + col) * RR_QLDS);
-                    const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(Qs + (16 + col) * RR_QLDS + 4);
-                    qa[0] = a0.x; qa[1] = a0.y; qa[2] = a1.x; qa[3] = a1.y;
-                    qb[0] = b0.x; qb[1] = b0.y; qb[2] = b1.x; qb[3] = b1.y;
-                }
-                if (OP == OP_ROT_S) {
-                    const ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(As + col * RR_QLDS);
-                    const ulonglong2 a1 = *reinterpret_cast<const ulonglong2 *>(As + col * RR_QLDS + 4);
-                    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(As + (16 + col) * RR_QLDS);
-                    const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(As + (16 + col) * RR_QLDS + 4);
-                    oa[0] = a0.x; oa[1] = a0.y; oa[2] = a1.x; oa[3] = a1.y;
-                    ob[0] = b0.x; ob[1] = b0.y; ob[2] = b1.x; ob[3] = b1.y;
-                }
+            for (int d4 = 0; d4 < 4; ++d4) {
+                float4 er[4], ei[4];
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    const float evr = dd == 0 ? er[m].x : dd == 1 ? er[m].y : dd == 2 ? er[m].z : er[m].w;
-                    const float evi = dd == 0 ? ei[m].x : dd == 1 ? ei[m].y : dd == 2 ? ei[m].z : ei[m].w;
-                    const unsigned long long er2 = rk_pk2(evr, evr), ei2 = rk_pk2(evi, evi);
+                    er[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 4 * d4);
+                    ei[m] = *reinterpret_cast<const float4 *>(Es + 32 * m * RK_LDS + 16 + 4 * d4);
+                }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        unsigned long long re, im;
-                        if (OP == OP_ROT_S) {  // RotatE.py:151-163: qa = cos, qb = sin, (oa, ob) = the object row
-                            re = rk_sub2(rk_fma2v(rk_pk2(-evi, -evi), qb[i], rk_mul2(er2, qa[i])), oa[i]);
-                            im = rk_sub2(rk_fma2v(ei2, qa[i], rk_mul2(er2, qb[i])), ob[i]);
-                        } else {  // RotatE.py:208-216: (qa, qb) = the rotated subject
-                            re = rk_sub2(qa[i], er2);
-                            im = rk_sub2(qb[i], ei2);
+                for (int dd = 0; dd < 4; ++dd) {
+                    const int col = 4 * d4 + dd;
+                    unsigned long long qa[4], qb[4], oa[4], ob[4];
+                    ldq(Qs + col * RR_QLDS, qa);
+                    ldq(Qs + (16 + col) * RR_QLDS, qb);
+                    if (OP == OP_ROT_S) { ldq(As + col * RR_QLDS, oa); ldq(As + (16 + col) * RR_QLDS, ob); }
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const float evr = comp(er[m], dd), evi = comp(ei[m], dd);
+                        const unsigned long long er2 = rk_pk2(evr, evr), ei2 = rk_pk2(evi, evi);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            unsigned long long re, im;
+                            if (OP == OP_ROT_S) {  // RotatE.py:151-163: qa = cos, qb = sin, (oa, ob) = the object row
+                                re = rk_sub2(rk_fma2v(rk_pk2(-evi, -evi), qb[i], rk_mul2(er2, qa[i])), oa[i]);
+                                im = rk_sub2(rk_fma2v(ei2, qa[i], rk_mul2(er2, qb[i])), ob[i]);
+                            } else {  // RotatE.py:208-216: (qa, qb) = the rotated subject
+                                re = rk_sub2(qa[i], er2);
+                                im = rk_sub2(qb[i], ei2);
+                            }
+                            acc[m][i] = rk_mod_step2(acc[m][i], re, im);
                         }
-                        acc[m][i] = rk_mod_step2(acc[m][i], re, im);
                     }
                 }
             }
@@ -619,37 +653,34 @@ __global__ void __launch_bounds__(RK_THREADS, 2) kge_rank_rot_kernel(const RankP
 cudaError_t launch_rank_count(const RankParams &p, int32_t *cnt, cudaStream_t st)
 {
     if (p.b == 0 || p.n_cand == 0) return cudaSuccess;
-    dim3 grid((unsigned)((p.n_cand + RK_TC - 1) / RK_TC), (unsigned)((p.b + RK_TQ - 1) / RK_TQ));
-    const size_t smem = 2 * RK_STAGE_FLOATS * sizeof(float);
-#define KGE_RK(OP)                                                                                           \
-    {                                                                                                        \
-        cudaError_t e = cudaFuncSetAttribute(kge_rank_tile_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem);                                                     \
-        if (e != cudaSuccess) return e;                                                                      \
-        kge_rank_tile_kernel<OP><<<grid, RK_THREADS, smem, st>>>(p, cnt);                                    \
-        break;                                                                                               \
-    }
-    switch (rank_op(p.L.model, p.side)) {
-    case OP_DOT: {
+    const int op = rank_op(p.L.model, p.side);
+    if (op == OP_DOT) {
         dim3 gd((unsigned)((p.n_cand + RD_TC - 1) / RD_TC), (unsigned)((p.b + RD_TQ - 1) / RD_TQ));
         const size_t sm = 2 * RD_STAGE_FLOATS * sizeof(float);
         cudaError_t e = cudaFuncSetAttribute(kge_rank_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         kge_rank_dot_kernel<<<gd, RD_THREADS, sm, st>>>(p, cnt);
-        break;
+        return cudaGetLastError();
     }
-    case OP_L1_ADD: KGE_RK(OP_L1_ADD)
-    case OP_L1_SUB: KGE_RK(OP_L1_SUB)
-    case OP_ROT_S:
-    case OP_ROT_O: {
-        const bool subj = rank_op(p.L.model, p.side) == OP_ROT_S;
-        const size_t sm = 2 * RR_STAGE_FLOATS * sizeof(float);
-        auto kern = subj ? kge_rank_rot_kernel<OP_ROT_S> : kge_rank_rot_kernel<OP_ROT_O>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, RK_THREADS, sm, st>>>(p, cnt);
-        break;
+    dim3 grid((unsigned)((p.n_cand + RK_TC - 1) / RK_TC), (unsigned)((p.b + RK_TQ - 1) / RK_TQ));
+    // KGE_B200_RANK_KERNEL=tile: the scalar tile kernel (one chain per accumulator register) instead of the packed pair kernel --
+    // an A/B and cross-check aid, both run the same canonical chains
+    const char *force = getenv("KGE_B200_RANK_KERNEL");
+    const bool tile = force && strcmp(force, "tile") == 0;
+    const size_t smem = (tile ? 2 * RK_STAGE_FLOATS : 2 * RR_STAGE_FLOATS) * sizeof(float);
+#define KGE_RK(OP)                                                                                           \
+    case OP: {                                                                                               \
+        auto kern = tile ? kge_rank_tile_kernel<OP> : kge_rank_pair_kernel<OP>;                              \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e != cudaSuccess) return e;                                                                      \
+        kern<<<grid, RK_THREADS, smem, st>>>(p, cnt);                                                        \
+        break;                                                                                               \
     }
+    switch (op) {
+    KGE_RK(OP_L1_ADD)
+    KGE_RK(OP_L1_SUB)
+    KGE_RK(OP_ROT_S)
+    KGE_RK(OP_ROT_O)
     }
 #undef KGE_RK
     return cudaGetLastError();

@@ -345,17 +345,16 @@ struct Scorer<KGE_TRANSE, NIT> {
 //
 // The kernel is FP32-issue bound on this model (profiles/r2a_train_cfg4_ncu_full_summary.json), so the
 // scorer is written to a per-element instruction budget: every float4 operation is two packed f32x2
-// instructions, NEGATED copies of the per-positive vectors (-cos, -sin, -y) are kept in registers so that no
-// residual needs a separate negate or subtract (the residual's sign is irrelevant to the modulus and is
-// folded into the scalar g for the unit vector), the modulus is one MUFU.SQRT, the unit vector one MUFU.RSQ
+// instructions (negations and subtractions are operand modifiers of FADD2 / FFMA2, never separate
+// instructions), a residual is two dependent packed fmas per component, the modulus is one MUFU.SQRT, the unit vector one MUFU.RSQ
 // on max(x, tiny) (an exactly-zero residual gives 0 * finite = 0), and lanes past the end of the window are
 // masked arithmetically (they read the window's last chunk; only their stores are predicated) so the row
 // loops carry no divergence bookkeeping.
 template <int NIT>
 struct Scorer<KGE_ROTATE, NIT> {
     static constexpr bool kQuad = false;
-    float4 C[NIT], Sn[NIT], nC[NIT], nS[NIT], Or_[NIT], Oi[NIT], nYr[NIT], nYi[NIT];
-    float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], A1[NIT], A2[NIT];  // df/dphi of the subject side = A1 - A2
+    float4 C[NIT], Sn[NIT], Or_[NIT], Oi[NIT], Yr[NIT], Yi[NIT];
+    float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], Aphi[NIT];
     float nlive[NIT];  // -1 for a lane that owns a chunk of this window, 0 past its end
     int lane, nch, cs = 32, kp, hs;  // cs: chunk stride = lanes on one positive; kp: half stride in HBM rows, hs: half stride of the staged row window
     __device__ __forceinline__ int chunk(int it) const { return min(lane + cs * it, nch - 1); }
@@ -390,20 +389,18 @@ struct Scorer<KGE_ROTATE, NIT> {
                 Or_[it] = f4ld(o + 4 * c); Oi[it] = f4ld(o + hs + 4 * c);
                 nlive[it] = -1.f;
             }
-            nC[it] = f4neg(C[it]);
-            nS[it] = f4neg(Sn[it]);
-            nYr[it] = f4fma(si, Sn[it], sr * nC[it]);  // -(sr c - si s)
-            nYi[it] = f4fma(sr, nS[it], si * nC[it]);  // -(sr s + si c)
-            Zor[it] = Zoi[it] = Zsr[it] = Zsi[it] = A1[it] = A2[it] = f4zero();
-            acc = fmaf(modsum(Or_[it] + nYr[it], Oi[it] + nYi[it]), nlive[it], acc);
+            Yr[it] = f4fma(f4neg(si), Sn[it], sr * C[it]);  // sr c - si s
+            Yi[it] = f4fma(sr, Sn[it], si * C[it]);         // sr s + si c
+            Zor[it] = Zoi[it] = Zsr[it] = Zsi[it] = Aphi[it] = f4zero();
+            acc = fmaf(modsum(Yr[it] - Or_[it], Yi[it] - Oi[it]), nlive[it], acc);
         }
         return acc;
     }
-    // o - R(phi) r, as two dependent packed fmas per component
-    __device__ __forceinline__ void neg_residual_subj(int it, float4 rr, float4 ri, float4 &re, float4 &im) const
+    // R(phi) r - o, as two dependent packed fmas per component
+    __device__ __forceinline__ void residual_subj(int it, float4 rr, float4 ri, float4 &re, float4 &im) const
     {
-        re = f4fma(ri, Sn[it], f4fma(rr, nC[it], Or_[it]));
-        im = f4fma(ri, nC[it], f4fma(rr, nS[it], Oi[it]));
+        re = f4fma(f4neg(ri), Sn[it], f4fma(rr, C[it], f4neg(Or_[it])));
+        im = f4fma(ri, C[it], f4fma(rr, Sn[it], f4neg(Oi[it])));
     }
     template <int SIDE>
     __device__ __forceinline__ void partial2(const float *ra, const float *rb, float &pa, float &pb) const
@@ -414,13 +411,13 @@ struct Scorer<KGE_ROTATE, NIT> {
             const int c = chunk(it);
             const float4 ar = f4ld(ra + 4 * c), ai = f4ld(ra + hs + 4 * c);
             const float4 br = f4ld(rb + 4 * c), bi = f4ld(rb + hs + 4 * c);
-            if (SIDE) {  // r - y
-                a = fmaf(modsum(ar + nYr[it], ai + nYi[it]), nlive[it], a);
-                b = fmaf(modsum(br + nYr[it], bi + nYi[it]), nlive[it], b);
+            if (SIDE) {  // y - r
+                a = fmaf(modsum(Yr[it] - ar, Yi[it] - ai), nlive[it], a);
+                b = fmaf(modsum(Yr[it] - br, Yi[it] - bi), nlive[it], b);
             } else {
                 float4 e0, e1, e2, e3;
-                neg_residual_subj(it, ar, ai, e0, e1);
-                neg_residual_subj(it, br, bi, e2, e3);
+                residual_subj(it, ar, ai, e0, e1);
+                residual_subj(it, br, bi, e2, e3);
                 a = fmaf(modsum(e0, e1), nlive[it], a);
                 b = fmaf(modsum(e2, e3), nlive[it], b);
             }
@@ -428,25 +425,23 @@ struct Scorer<KGE_ROTATE, NIT> {
         pa = a;
         pb = b;
     }
-    // ng = -g: the residuals below are the NEGATED ones, so (a, b) = ng * (-residual) / |residual| has the true sign
     template <int SIDE, class Sink>
-    __device__ __forceinline__ void grad1(float *r, float *grow, float ng, int it, int c, bool emit)
+    __device__ __forceinline__ void grad1(float *r, float *grow, float g, int it, int c, bool emit)
     {
         const float4 rr = f4ld(r + 4 * c), ri = f4ld(r + hs + 4 * c);
         float4 a, b;
         if (SIDE) {  // residual = y(s) - r ; df/dr = +(a,b)
-            unit(rr + nYr[it], ri + nYi[it], ng, a, b);
+            unit(Yr[it] - rr, Yi[it] - ri, g, a, b);
             Zor[it] = Zor[it] + a; Zoi[it] = Zoi[it] + b;
             if (emit) { Sink::put(r, grow, 4 * c, 4 * c, a); Sink::put(r, grow, hs + 4 * c, kp + 4 * c, b); }
         } else {  // residual = R(phi) r - o ; df/dr = -R(-phi)(a,b)
-            const float4 nyr = f4fma(ri, Sn[it], rr * nC[it]), nyi = f4fma(rr, nS[it], ri * nC[it]);  // -R(phi) r
-            unit(Or_[it] + nyr, Oi[it] + nyi, ng, a, b);
+            const float4 yr = f4fma(f4neg(ri), Sn[it], rr * C[it]), yi = f4fma(rr, Sn[it], ri * C[it]);  // R(phi) r
+            unit(yr - Or_[it], yi - Oi[it], g, a, b);
             Zsr[it] = Zsr[it] + a; Zsi[it] = Zsi[it] + b;
-            A1[it] = f4fma(b, nyr, A1[it]);  // a*y_im - b*y_re = b*nyr - a*nyi
-            A2[it] = f4fma(a, nyi, A2[it]);
+            Aphi[it] = f4fma(f4neg(b), yr, f4fma(a, yi, Aphi[it]));  // a*y_im - b*y_re
             if (emit) {
-                Sink::put(r, grow, 4 * c, 4 * c, f4fma(b, nS[it], a * nC[it]));          // -(a c + b s)
-                Sink::put(r, grow, hs + 4 * c, kp + 4 * c, f4fma(b, nC[it], a * Sn[it]));  // a s - b c
+                Sink::put(r, grow, 4 * c, 4 * c, f4fma(f4neg(b), Sn[it], f4neg(a) * C[it]));  // -(a c + b s)
+                Sink::put(r, grow, hs + 4 * c, kp + 4 * c, f4fma(f4neg(b), C[it], a * Sn[it]));  // a s - b c
             }
         }
     }
@@ -458,8 +453,8 @@ struct Scorer<KGE_ROTATE, NIT> {
         for (int it = 0; it < NIT; ++it) {
             const int c = chunk(it);
             const bool live = lane + cs * it < nch;  // dead lanes run the arithmetic on the last chunk; their accumulators are never read
-            grad1<SIDE, Sink>(ra, ga_row, -ga, it, c, live);
-            grad1<SIDE, Sink>(rb, gb_row, -gb, it, c, live && has_b);  // gb == 0 when !has_b: contributes nothing
+            grad1<SIDE, Sink>(ra, ga_row, ga, it, c, live);
+            grad1<SIDE, Sink>(rb, gb_row, gb, it, c, live && has_b);  // gb == 0 when !has_b: contributes nothing
         }
     }
     // p row receives d/dtheta = (1/div) d/dphi in its first half, zeros in the second
@@ -473,14 +468,13 @@ struct Scorer<KGE_ROTATE, NIT> {
             int c = lane + cs * it;
             if (c < nch) {
                 float4 a, b;
-                unit(Or_[it] + nYr[it], Oi[it] + nYi[it], -gP, a, b);  // gP * (y - o)/|y - o|
+                unit(Yr[it] - Or_[it], Yi[it] - Oi[it], gP, a, b);
                 const float4 Zr = a + Zor[it], Zi = b + Zoi[it];  // everything with y = R(phi) s
-                Sink::put(s, gs, 4 * c, 4 * c, f4fma(Zi, nS[it], Zr * nC[it]));          // -(Zr c + Zi s)
-                Sink::put(s, gs, hs + 4 * c, kp + 4 * c, f4fma(Zi, nC[it], Zr * Sn[it]));  // Zr s - Zi c
+                Sink::put(s, gs, 4 * c, 4 * c, f4fma(f4neg(Zi), Sn[it], f4neg(Zr) * C[it]));   // -(Zr c + Zi s)
+                Sink::put(s, gs, hs + 4 * c, kp + 4 * c, f4fma(f4neg(Zi), C[it], Zr * Sn[it]));  // Zr s - Zi c
                 Sink::put(o, go, 4 * c, 4 * c, a + Zsr[it]);
                 Sink::put(o, go, hs + 4 * c, kp + 4 * c, b + Zsi[it]);
-                // Aphi + (Zr*Yi - Zi*Yr) = (A1 + Zi*nYr) - (A2 + Zr*nYi)
-                Sink::put(p, gp, 4 * c, 4 * c, inv_div * (f4fma(Zi, nYr[it], A1[it]) - f4fma(Zr, nYi[it], A2[it])));
+                Sink::put(p, gp, 4 * c, 4 * c, inv_div * f4fma(f4neg(Zi), Yr[it], f4fma(Zr, Yi[it], Aphi[it])));
             }
         }
     }
@@ -570,9 +564,12 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
     // (making these loop invariants opaque to the front end, as kge_train_res.cu does, changes nothing here:
     // cfg3 131 -> 133 us, cfg4 / cfg5w unchanged, profiles/r2f_kbench_general_keep.log)
     constexpr bool resident = RESIDENT;
-    // slot: s, p, o windows, then group buffer 0 and (non-resident only) group buffer 1: the next group is
-    // gathered while the current one is being processed, which hides the gather latency (NVLink latency
-    // when the table is row-sharded over GPUs)
+    // slot: s, p, o windows, then group buffer 0 and (non-resident, p.nbuf == 2) group buffer 1: the next group is
+    // gathered while the current one is being processed, which hides the gather latency inside the warp (NVLink
+    // latency when the table is row-sharded over GPUs).  With p.nbuf == 1 the next group is requested when the
+    // current one has been consumed and the latency is hidden by the OTHER warps of the SM instead: half the
+    // shared memory per warp, so more warps (kge_create picks per shape).
+    const bool dbuf = !RESIDENT && p.nbuf == 2;
     float *srow = rows, *prow = rows + lw, *orow = rows + 2 * lw;
     auto nbuf = [&](int b) { return rows + (size_t)(3 + b * G) * lw; };
     const float scale = p.score_scale;  // HolE 2/k, else 1
@@ -580,7 +577,10 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
     double loss_acc = 0.0;
 
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B; i += n_warps) {
+    float next_draw = 0.f;  // lane 0: this warp's draw from the positive counter (kge_train_common.cuh: dynamic assignment)
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B;
+         i = p.sched ? n_warps + (long long)(unsigned)__shfl_sync(0xffffffffu, next_draw, 0) : i + n_warps) {
+        if (p.sched && lane == 0) next_draw = sched_draw(p.sched);  // consumed by the loop increment, a whole positive later
         const int s_id = p.triples[3 * i], p_id = p.triples[3 * i + 1], o_id = p.triples[3 * i + 2];
         // ---- corruptions of this positive (A3), SORTED BY SIDE as they are drawn ----
         // Slot t of the warp's arrays (nid, sc, the gathered rows, the stash) holds corruption jorig[t]; slots [0, n0)
@@ -682,8 +682,8 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
             __syncwarp();
             issue(0, cb, true, 0, min(G, eta));
             for (int g = 0; g < n_groups; ++g) {
-                const int buf = g & 1, j0 = g * G, gsz = min(G, eta - j0);
-                if (g + 1 < n_groups) {
+                const int buf = dbuf ? (g & 1) : 0, j0 = g * G, gsz = min(G, eta - j0);
+                if (dbuf && g + 1 < n_groups) {
                     if (use_stash) { bulk_wait_read_all(); __syncwarp(); }  // the stash store of group g-1 has read buf^1
                     issue(buf ^ 1, cb, false, j0 + G, min(G, eta - j0 - G));
                 }
@@ -752,6 +752,10 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                 }
                 }
                 __syncwarp();
+                if (!dbuf && g + 1 < n_groups) {  // single buffer: every lane is done with this group, fetch the next one over it
+                    if (use_stash) { bulk_wait_read_all(); __syncwarp(); }  // ... and so is the stash store
+                    issue(0, cb, false, j0 + G, min(G, eta - j0 - G));
+                }
             }
         }
 
@@ -780,14 +784,14 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
             S.nch = min(wk, kp - cb * wk) / 4;
             const int gofs = cb * wk;  // column offset of this window inside a gradient row
             for (int g = n_groups - 1; g >= 0; --g) {
-                const int buf = g & 1, j0 = g * G, gsz = min(G, eta - j0);
+                const int buf = dbuf ? (g & 1) : 0, j0 = g * G, gsz = min(G, eta - j0);
                 const bool top = (g == n_groups - 1);
                 const bool still_there = (cb == n_cb - 1 && top);  // left in place by pass A
                 if (top && !still_there) {  // first visit of this window: s, p, o come along, state is rebuilt
                     __syncwarp();
                     issue(buf, cb, true, j0, gsz, use_stash);
                 }
-                if (g > 0) {  // prefetch the next (lower) group into the other buffer
+                if (dbuf && g > 0) {  // prefetch the next (lower) group into the other buffer
                     __syncwarp();
                     issue(buf ^ 1, cb, false, j0 - G, G, use_stash);
                 }
@@ -812,11 +816,13 @@ __global__ void __launch_bounds__(KGE_TRAIN_THREADS(MODEL, NIT)) kge_train_kerne
                                               has_b ? scale * sc[j0 + b] : 0.f, has_b);
                 }
                 __syncwarp();
+                if (!dbuf && g > 0) issue(0, cb, false, j0 - G, G, use_stash);  // single buffer: the next (lower) group over this one
             }
             S.template finish<Sink>(srow, prow, orow, gs_row + gofs, gp_row + gofs, go_row + gofs, scale * dP, p.inv_div);
         }
         __syncwarp();
     }
+    sched_retire(p.sched, n_warps, lane);
     if (p.loss_out && p.mode == KGE_STEP_FUSED && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_out, loss_acc);
 }
 

@@ -152,6 +152,34 @@ __device__ __forceinline__ float warp_sum4t(float v0, float v1, float v2, float 
 }
 
 // --------------------------------------------------------------------------
+// Dynamic assignment of positives to warps.  A static stride (warp w takes w, w + n_warps, ...) quantises the launch to
+// ceil(B / n_warps) rounds -- cfg2: 27,212 positives over 1,776 warps = 15.3, so a third of the warps run a 16th round
+// while the rest idle (4 %); cfg4: 9.1 -> 10 rounds (9 %).  Instead every warp starts on its own index and draws the
+// following ones from a counter: the draw for the NEXT positive is issued before the current one is processed, so its
+// latency is never seen.  The counters reset themselves: the last warp to retire (all draws are complete by then)
+// zeroes both words, so consecutive launches on one stream need no memset and the scheme survives graph replay.
+// --------------------------------------------------------------------------
+// (a FLOAT counter on purpose: the compiler -- nvcc for atomicAdd(), ptxas for atom.add / atom.inc in inline PTX, u32 and u64,
+// even with a laundered addend -- aggregates a warp's integer atomic adds (VOTE + POPC, one ATOMG) and reads the result back
+// with a shuffle right after it, which puts the whole L2 round trip, microseconds when HBM is saturated, at the top of every
+// positive: measured +35 % on the HBM-resident `big` shape, profiles/r2n_kbench_dynamic.log.  atom.add.f32 is left alone;
+// counts are exact below 2^24, the host falls back to the static stride for larger batches.)
+#define KGE_SCHED_MAX_B (1ll << 24)
+__device__ __forceinline__ float sched_draw(unsigned *sched)  // the caller converts when it consumes the value, not here
+{
+    float v;
+    asm volatile("atom.relaxed.gpu.global.add.f32 %0, [%1], 0f3F800000;" : "=f"(v) : "l"(sched) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sched_retire(unsigned *sched, long long n_warps, int lane)
+{
+    if (sched && lane == 0) {
+        const unsigned d = atomicAdd(sched + 1, 1u);
+        if ((long long)d == n_warps - 1) { sched[0] = 0u; sched[1] = 0u; }
+    }
+}
+
+// --------------------------------------------------------------------------
 // per-positive loss and dL/dscore (warp-cooperative; lanes stride over j).
 // in: P, sc[j] = N_j.  out: sc[j] = dL/dN_j, returns loss_i, *dP.
 // --------------------------------------------------------------------------

@@ -150,7 +150,11 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
     for (int it = 0; it < NIT; ++it) H0r[it] = H0i[it] = H1r[it] = H1i[it] = f4zero();
 
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B; i += n_warps) {
+    // (drawing two or three positives per draw was measured too: no gain / slower, profiles/r2p_kbench_chunk{2,3}.log)
+    float next_draw = 0.f;  // lane 0: this warp's draw from the positive counter (kge_train_common.cuh: dynamic assignment)
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B;
+         i = p.sched ? n_warps + (long long)(unsigned)__shfl_sync(0xffffffffu, next_draw, 0) : i + n_warps) {
+        if (p.sched && lane == 0) next_draw = sched_draw(p.sched);  // consumed by the loop increment, a whole positive later
         // ---- the positive, and its corruptions sorted by side as they are drawn (A3) ----
         int tv = 0;
         if (lane < 3) tv = __ldg(p.triples + 3 * i + lane);
@@ -381,6 +385,7 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
         }
         __syncwarp();  // every lane has read the slot before the next positive's gather overwrites it
     }
+    sched_retire(p.sched, n_warps, lane);
     // retire: this warp's share of the hot rows (zeros when it met none of them: skip)
     if (p.mode != KGE_STEP_FORWARD_ONLY) {
 #pragma unroll

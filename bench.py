@@ -37,13 +37,17 @@ SA = {"margin": 3.0, "alpha": 0.5}
 # BASELINE.json configs[1..4]; B = positives per GPU per step
 WORKLOADS = {
     "cfg2": dict(model="ComplEx", k=200, eta=10, loss="self_adversarial", loss_params=SA, n_ent=14505, n_rel=237,
-                 n_triples=272115, batch=27212, optimizer="adam", lr=1e-3),
+                 n_triples=272115, batch=27212, optimizer="adam", lr=1e-3,
+                 kernel="kge_train_res_kernel<HALVES=2,NIT=2> (resident trilinear fast path)"),
     "cfg3": dict(model="DistMult", k=400, eta=20, loss="pairwise", loss_params={"margin": 1.0}, n_ent=40943, n_rel=11,
-                 n_triples=86835, batch=8684, optimizer="adam", lr=1e-3),
+                 n_triples=86835, batch=8684, optimizer="adam", lr=1e-3,
+                 kernel="kge_train_res_kernel<HALVES=1,NIT=4> (resident trilinear fast path, 6 warps/SM)"),
     "cfg4": dict(model="RotatE", k=200, eta=30, loss="self_adversarial", loss_params=SA, n_ent=123182, n_rel=37,
-                 n_triples=1079040, batch=10791, optimizer="adam", lr=1e-3),
+                 n_triples=1079040, batch=10791, optimizer="adam", lr=1e-3,
+                 kernel="kge_train_kernel<RotatE,NIT=2,grouped> (general kernel, corruptions in groups, next group prefetched)"),
     "cfg5": dict(model="ComplEx", k=1000, eta=50, loss="self_adversarial", loss_params=SA, n_ent=10_000_000, n_rel=1000,
-                 n_triples=None, batch=8192, optimizer="lazy_adam", lr=1e-3),
+                 n_triples=None, batch=8192, optimizer="lazy_adam", lr=1e-3,
+                 kernel="kge_train_kernel<ComplEx,NIT=4,windowed+grouped> (general kernel, 512-column windows, corruptions in groups)"),
 }
 CFG = WORKLOADS["cfg2"]
 # Multi-GPU parity: the two runs sum the same fp32 gradient contributions in a different order, and Adam turns a relative
@@ -267,7 +271,7 @@ def _step_entry(c, ms_step, ms_kernel, world, ld, peak, **more):
          "positives_per_gpu": B, "n_gpus": world,
          "roofline": {"bound": "hbm", "achieved": alg / (ms_kernel / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                       "frac": alg / (ms_kernel / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
-                      "kernel": "kge_train_kernel<%s>" % c["model"]}}
+                      "kernel": c["kernel"]}}
     d.update(more)
     return d
 
@@ -745,7 +749,7 @@ def main_ours(args):
                                "per-step loss read one step late)", "last_loss": e2e_losses[-1] if e2e_losses else None},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "kge_train_kernel<ComplEx,2,resident>",
+                             "traffic": traffic, "kernel": CFG["kernel"],
                              "kernel_ms": t_kern, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                              "note": "cfg2's tables (23 MB) are L2-resident: this kernel is issue/latency bound, not HBM bound, "
                                      "and `achieved` can exceed the HBM peak; extra.cfg5* / extra.cfg4* are the HBM-resident cases"},
