@@ -84,8 +84,11 @@ class KGEEngine:
                 for t_ in (self.ent, self.rel, self.g_ent, self.g_rel):
                     assert t_.is_contiguous() and t_.dtype == torch.float32
             else:
-                self.ent, self.rel = z(self.ent_rows), z(self.n_rel)
-                self.g_ent, self.g_rel = z(self.ent_rows), z(self.n_rel)
+                # one [ent | rel] block per kind (rows have the same width): the dense optimizer then updates both tables
+                # in ONE launch (apply_gradients) -- one launch gap less per step
+                self._pblock, self._gblock = z(self.ent_rows + self.n_rel), z(self.ent_rows + self.n_rel)
+                self.ent, self.rel = self._pblock[:self.ent_rows], self._pblock[self.ent_rows:]
+                self.g_ent, self.g_rel = self._gblock[:self.ent_rows], self._gblock[self.ent_rows:]
             self.loss_acc = torch.zeros(2, dtype=torch.float64, device=self.device)  # [batch loss, reg loss]
         self.set_optimizer(optimizer, optimizer_params, regularizer)
         self.launches = 0  # kernels launched by this engine (bench.py reports it)
@@ -131,18 +134,18 @@ class KGEEngine:
         self.opt_cfg = self.opt_cfgs["ent"]  # hyper-parameters are common to both tables; only the regulariser differs
         self.opt_name = name
         self.t = 0
-        mk = lambda rows, v=0.0: torch.full((rows, self.ld), v, dtype=torch.float32, device=self.device)
-        self.slots = {"ent": [None, None], "rel": [None, None]}
+        # slots as [ent | rel] blocks, like the tables (see __init__): slots[key] are row slices of them
+        mk = lambda v=0.0: torch.full((self.ent_rows + self.n_rel, self.ld), v, dtype=torch.float32, device=self.device)
+        cut = lambda blk: {"ent": None if blk is None else blk[:self.ent_rows], "rel": None if blk is None else blk[self.ent_rows:]}
+        b0 = b1 = None
         if name == "adam":
-            for key, rows in (("ent", self.ent_rows), ("rel", self.n_rel)):
-                self.slots[key] = [mk(rows), mk(rows)]
+            b0, b1 = mk(), mk()
         elif name == "adagrad":
-            for key, rows in (("ent", self.ent_rows), ("rel", self.n_rel)):
-                acc = mk(rows, self.opt_cfg.initial_accumulator_value)
-                self.slots[key] = [acc, None]
+            b0 = mk(self.opt_cfg.initial_accumulator_value)
         elif self.opt_cfg.momentum != 0.0:
-            for key, rows in (("ent", self.ent_rows), ("rel", self.n_rel)):
-                self.slots[key] = [mk(rows), None]
+            b0 = mk()
+        self._sblocks = (b0, b1)
+        self.slots = {key: [cut(b0)[key], cut(b1)[key]] for key in ("ent", "rel")}
         self.stamps = {"ent": None, "rel": None}
         if self.lazy:
             self.stamps = {"ent": torch.zeros(self.ent_rows, dtype=torch.int32, device=self.device),
@@ -226,10 +229,35 @@ class KGEEngine:
         self._last_step = int(step)
         self.launches += 2 if self.scoring_type == "RotatE" else 1
 
+    def _one_block(self):
+        """True when tables, gradients and slots still ARE the [ent | rel] blocks allocated here (callers may rebind them: the
+        multi-GPU trainers do) and both tables share one regulariser: the dense optimizer can take them in one launch."""
+        pb, gb = getattr(self, "_pblock", None), getattr(self, "_gblock", None)
+        if self.lazy or pb is None:
+            return False
+        off = self.ent_rows * self.ld * 4
+
+        def is_split(blk, a, b):
+            if blk is None:
+                return a is None and b is None
+            return a is not None and b is not None and a.data_ptr() == blk.data_ptr() and b.data_ptr() == blk.data_ptr() + off
+
+        ce, cr = self.opt_cfgs["ent"], self.opt_cfgs["rel"]
+        same_reg = all(getattr(ce, f) == getattr(cr, f) for f, _ in ce._fields_)
+        return (same_reg and is_split(pb, self.ent, self.rel) and is_split(gb, self.g_ent, self.g_rel)
+                and is_split(self._sblocks[0], self.slots["ent"][0], self.slots["rel"][0])
+                and is_split(self._sblocks[1], self.slots["ent"][1], self.slots["rel"][1]))
+
     @_traced("kge.optimizer_step")
     def apply_gradients(self):
         """optimizer.apply_gradients on both tables (dense semantics) + LP regulariser."""
         self.t += 1
+        if self._one_block():
+            _lib.check(self.lib.kge_optimizer_step(
+                self.h, C.byref(self.opt_cfgs["ent"]), self.t, _ptr(self._pblock), _ptr(self._gblock), _ptr(self._sblocks[0]),
+                _ptr(self._sblocks[1]), self.ent_rows + self.n_rel, C.c_void_p(self.loss_acc.data_ptr() + 8), self._stream()))
+            self.launches += 1
+            return
         for key, table, grad, rows in (("ent", self.ent, self.g_ent, self.ent_rows),
                                        ("rel", self.rel, self.g_rel, self.n_rel)):
             s0, s1 = self.slots[key]

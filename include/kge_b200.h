@@ -237,7 +237,8 @@ int kge_train_step_sharded(kge_handle *h, int32_t mode, const kge_shard_map *map
                            const float *dpos_dev, const float *dneg_dev, void *stream);
 
 /* OptimizerWrapper.minimize -> legacy apply_gradients (optimizers.py:136-168) for ONE
- * table, dense semantics, plus the LP regulariser's loss/gradient over the whole table
+ * table (or any row-wise concatenation of tables of the same width and regulariser: the engine passes [ent | rel] as one
+ * block, one launch per step), dense semantics, plus the LP regulariser's loss/gradient over the whole table
  * (regularizers.py:14-37; added to the loss at loss_functions.py:215-223).
  *   t            1-based iteration count (Adam bias correction)
  *   slot0/slot1  Adam m,v / SGD momentum,- / Adagrad accumulator,-  ([rows,ld] or NULL)
