@@ -24,6 +24,7 @@ struct kge_handle {
     // training launch geometry
     int nit, G, nbuf, warps, eta_pad, rows_bytes, region_bytes, wk, n_cb, slot_floats, resident;
     int res_warps, res_rows_bytes, res_region_bytes;  // slot geometry of the resident trilinear fast path (kge_train_res.cu); res_warps = 0: not applicable
+    int rot_warps, rot_G, rot_rows_bytes, rot_region_bytes;  // slot geometry of the RotatE fast path (kge_train_rot.cu); rot_warps = 0: not applicable
     int *stamp_ent, *stamp_rel;  // lazy-optimizer row stamps (caller-owned) or nullptr
     float *stash;                // caller-owned row stash for sharded runs (kge_set_row_stash) or nullptr
     long long stash_rows;
@@ -190,6 +191,26 @@ extern "C" int kge_create(const kge_config *cfg, kge_handle **out)
         if (h->nit == 4) min_res = KGE_MIN_RESIDENT_WARPS_WIDE;
         if (const char *ev = getenv("KGE_B200_RES_MIN_WARPS")) min_res = atoi(ev);  // tuning aid
         if (rw >= min_res) h->res_warps = rw;
+    }
+
+    // ---- the RotatE fast path (kge_train_rot.cu): one window, rows of up to 256 floats per half; its slot holds ONLY replaced
+    // rows (s, o and the rotation row live in registers): all eta of them when they fit beside 8 warps, else two buffers of G.
+    h->rot_warps = 0;
+    if (cfg->scoring == KGE_ROTATE && h->n_cb == 1 && h->nit <= 2 && cfg->neg_group <= 0) {
+        const int rot_aux = (4 * h->eta_pad * 4 + 16 + 15) / 16 * 16;  // sc | nid | jorig | side, two mbarriers
+        const int rw = 8;                                                // 256 threads (launch bound of the kernel)
+        const int cap = (h->max_smem / rw - rot_aux) / row_bytes;        // rows per warp
+        int rG = cap >= cfg->eta ? cfg->eta : cap / 2;
+        if (const char *ev = getenv("KGE_B200_ROT_G")) {  // tuning aid: smaller groups
+            const int g = atoi(ev);
+            if (g >= 1 && g <= cap / 2 && g < cfg->eta) rG = g;
+        }
+        if (rG >= 1) {
+            h->rot_warps = rw;
+            h->rot_G = rG;
+            h->rot_rows_bytes = (rG >= cfg->eta ? rG : 2 * rG) * row_bytes;
+            h->rot_region_bytes = h->rot_rows_bytes + rot_aux;
+        }
     }
 
     if (cfg->scoring == KGE_ROTATE) {
@@ -431,6 +452,14 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
         if (ev && strcmp(ev, "static") == 0) dyn = false;
         if (ev && strcmp(ev, "dynamic") == 0) dyn = true;
         p.sched = (dyn && B < (1ll << 24)) ? h->done_counter + 1 : nullptr;  // float counter: exact below 2^24
+    }
+    if (h->rot_warps > 0 && p.shard_world <= 1 && p.stash == nullptr && !(force && strcmp(force, "general") == 0)) {
+        p.G = h->rot_G;
+        p.rows_bytes = h->rot_rows_bytes;
+        p.region_bytes = h->rot_region_bytes;
+        KGE_CUDA(launch_train_rot(p, h->nit, h->sm_count, h->rot_warps * 32, (size_t)h->rot_warps * h->rot_region_bytes, st),
+                 "kge_train_step");
+        return KGE_OK;
     }
     if (fast) {
         p.rows_bytes = h->res_rows_bytes;

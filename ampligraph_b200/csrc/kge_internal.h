@@ -55,6 +55,9 @@ cudaError_t launch_train(const TrainParams &p, int nit, int sm_count, int thread
 // kge_train_res.cu: the resident trilinear fast path (DistMult / ComplEx / HolE, all rows of a positive resident, eta <= 32, one
 // table); p.rows_bytes / p.region_bytes carry ITS slot geometry (kge_create: res_*), threads = res_warps * 32
 cudaError_t launch_train_res(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st);
+// kge_train_rot.cu: the RotatE fast path (one column window, single table, any eta in groups of p.G with two buffers -- or one
+// group when everything fits); p.G / p.rows_bytes / p.region_bytes carry ITS slot geometry (kge_create: rot_*), threads = rot_warps * 32
+cudaError_t launch_train_rot(const TrainParams &p, int nit, int sm_count, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_rotation_table(const float *rel, float *rot, long long n_rel, int kp, int ld, float div,
                                   cudaStream_t st);
 cudaError_t launch_corruptions(const int32_t *triples, long long B, int eta, unsigned long long seed,

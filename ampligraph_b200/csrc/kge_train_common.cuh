@@ -152,6 +152,67 @@ __device__ __forceinline__ float warp_sum4t(float v0, float v1, float v2, float 
 }
 
 // --------------------------------------------------------------------------
+// explicit shared-memory accessors (32-bit shared addresses) and register-pinning helpers of the fast paths
+// (kge_train_res.cu, kge_train_rot.cu)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds4(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_i(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_i(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void mbar_init_s(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RES_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RES_DONE;\n"
+        "bra RES_WAIT_LOOP;\n"
+        "RES_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_s(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// The front end rematerialises cheap values (kernel parameters, %tid-derived addresses) inside the long per-positive
+// loop instead of keeping them in registers -- a dozen ld.param / shift / mad per trip of the inner loops.  Passing a
+// value through an empty asm makes it opaque: it is computed once and stays in its register.
+#define KGE_KEEP32(x) asm volatile("" : "+r"(x))
+#define KGE_KEEP64(x) asm volatile("" : "+l"(x))
+#define KGE_KEEPF(x) asm volatile("" : "+f"(x))
+__device__ __forceinline__ void red4(char *row, uint32_t byte_off, float4 v) { red_add_v4(reinterpret_cast<float *>(row + byte_off), v); }
+
+
+// --------------------------------------------------------------------------
 // Dynamic assignment of positives to warps.  A static stride (warp w takes w, w + n_warps, ...) quantises the launch to
 // ceil(B / n_warps) rounds -- cfg2: 27,212 positives over 1,776 warps = 15.3, so a third of the warps run a 16th round
 // while the rest idle (4 %); cfg4: 9.1 -> 10 rounds (9 %).  Instead every warp starts on its own index and draws the

@@ -44,10 +44,12 @@ WORKLOADS = {
                  kernel="kge_train_res_kernel<HALVES=1,NIT=4> (resident trilinear fast path, 6 warps/SM)"),
     "cfg4": dict(model="RotatE", k=200, eta=30, loss="self_adversarial", loss_params=SA, n_ent=123182, n_rel=37,
                  n_triples=1079040, batch=10791, optimizer="adam", lr=1e-3,
-                 kernel="kge_train_kernel<RotatE,NIT=2,grouped> (general kernel, corruptions in groups, next group prefetched)"),
+                 kernel="kge_train_rot_kernel<NIT=2> (RotatE fast path: replaced rows in two buffers of 8, s / o / rotation row in registers)",
+                 kernel_sharded="kge_train_kernel<RotatE,NIT=2,grouped> (general kernel: peer-memory gathers / scatters, row stash)"),
     "cfg5": dict(model="ComplEx", k=1000, eta=50, loss="self_adversarial", loss_params=SA, n_ent=10_000_000, n_rel=1000,
                  n_triples=None, batch=8192, optimizer="lazy_adam", lr=1e-3,
-                 kernel="kge_train_kernel<ComplEx,NIT=4,windowed+grouped> (general kernel, 512-column windows, corruptions in groups)"),
+                 kernel="kge_train_kernel<ComplEx,NIT=4,windowed+grouped> (general kernel, 512-column windows, corruptions in groups)",
+                 kernel_sharded="kge_train_kernel<ComplEx,NIT=4,windowed+grouped> (general kernel: peer-memory gathers / scatters, row stash)"),
 }
 CFG = WORKLOADS["cfg2"]
 # Multi-GPU parity: the two runs sum the same fp32 gradient contributions in a different order, and Adam turns a relative
@@ -273,6 +275,8 @@ def _step_entry(c, ms_step, ms_kernel, world, ld, peak, **more):
                       "frac": alg / (ms_kernel / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
                       "kernel": c["kernel"]}}
     d.update(more)
+    if world > 1 and "kernel_sharded" in c:
+        d["roofline"]["kernel"] = c["kernel_sharded"]
     return d
 
 

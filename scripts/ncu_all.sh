@@ -32,11 +32,11 @@ launches() {  # launches <name> <count> <cmd...>
 launches bench 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-extra
 launches evaluate 200 python scripts/rbench.py one ComplEx 200 14505 1024
 
-# training kernels: resident ComplEx (cfg2, fast path), resident DistMult NIT=4 (cfg3, fast path), grouped RotatE (cfg4), HBM-resident table
+# training kernels: resident ComplEx (cfg2, fast path), resident DistMult NIT=4 (cfg3, fast path), RotatE fast path (cfg4), HBM-resident table
 # (big: resident geometry, 3.2 GB table), windowed + grouped ComplEx k=1000 (cfg5w: 1.6 GB table)
 cap train_cfg2 'kge_train_res_kernel|kge_optim_kernel' 8 2 python bench.py --steps 5 --warmup 3 --no-cpu --no-extra
 cap train_cfg3 kge_train_res_kernel 2 1 python scripts/kbench.py one cfg3 0
-cap train_cfg4 kge_train_kernel 2 1 python scripts/kbench.py one cfg4 0
+cap train_cfg4 kge_train_rot_kernel 2 1 python scripts/kbench.py one cfg4 0
 cap train_big  kge_train_res_kernel 2 1 python scripts/kbench.py one big 0
 cap train_cfg5w kge_train_kernel 2 1 python scripts/kbench.py one cfg5w 0
 # optimizers: lazy (touched rows only) and the one-launch exchange kernel (world = 1: a multi-rank command must not run under ncu)

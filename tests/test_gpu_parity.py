@@ -533,9 +533,12 @@ def test_regulariser_pair_and_l1_l2():
 
 
 @pytest.mark.parametrize("model,k,eta", [("ComplEx", 200, 10), ("HolE", 50, 7), ("DistMult", 200, 32), ("ComplEx", 30, 1), ("DistMult", 7, 3),
-                                         ("DistMult", 400, 20), ("DistMult", 509, 9)])  # the last two: NIT = 4 rows (cfg3's shape)
+                                         ("DistMult", 400, 20), ("DistMult", 509, 9),  # NIT = 4 rows (cfg3's shape)
+                                         # kge_train_rot_kernel: cfg4's shape (4 groups of 8), everything resident, eta > 32 (two
+                                         # ballot rounds), 5 groups with a short last one, NIT = 1 in groups
+                                         ("RotatE", 200, 30), ("RotatE", 50, 7), ("RotatE", 20, 40), ("RotatE", 256, 33), ("RotatE", 100, 90)])
 def test_resident_fast_path_equals_general_kernel(model, k, eta, monkeypatch):
-    """kge_train_res_kernel (the resident trilinear fast path) against kge_train_kernel forced by KGE_B200_TRAIN_KERNEL=general:
+    """kge_train_res_kernel / kge_train_rot_kernel (the fast paths) against kge_train_kernel forced by KGE_B200_TRAIN_KERNEL=general:
     identical arithmetic per score, so scores are bit-equal; gradients agree to atomic-order noise; both match the oracle
     elsewhere (test_forward_backward_vs_oracle runs through the fast path by default)."""
     rng = np.random.default_rng(71)
@@ -553,7 +556,7 @@ def test_resident_fast_path_equals_general_kernel(model, k, eta, monkeypatch):
             monkeypatch.delenv("KGE_B200_TRAIN_KERNEL", raising=False)
         eng = _engine(model, k, eta, E, R, loss="self_adversarial")
         # (the general kernel processes cfg3's shape in groups of corruptions; the fast path keeps all of them resident on 6 warps)
-        assert eng.lib.kge_rows_resident(eng.h) or (model, k, eta) == ("DistMult", 400, 20)
+        assert eng.lib.kge_rows_resident(eng.h) or (model, k, eta) == ("DistMult", 400, 20) or model == "RotatE"
         if which == "fast_hot":  # kge_set_hot_entities: entities 5 and 17 are summed per warp and scattered once
             eng.set_hot_entities(triples=t)
             assert sorted(eng.hot_entities) == [5, 17]
@@ -581,6 +584,8 @@ def test_dynamic_assignment_of_positives_equals_static_stride(model, k, E, B, mo
     ent, rel = _tables(model, E, R, k, rng, scale=0.3)
     t = _triples(E, R, B, rng)
     out = {}
+    if model == "RotatE":  # its fast path has no dynamic assignment: this case covers the general kernel's
+        monkeypatch.setenv("KGE_B200_TRAIN_KERNEL", "general")
     for mode in ("static", "dynamic"):
         monkeypatch.setenv("KGE_B200_TRAIN_SCHED", mode)
         # (a small step: RotatE's unit-vector gradients amplify atomic-order noise from one step to the next)
