@@ -452,6 +452,11 @@ static int train_step_impl(kge_handle *h, int32_t mode, const kge_shard_map *map
         if (ev && strcmp(ev, "static") == 0) dyn = false;
         if (ev && strcmp(ev, "dynamic") == 0) dyn = true;
         p.sched = (dyn && B < (1ll << 24)) ? h->done_counter + 1 : nullptr;  // float counter: exact below 2^24
+        // The hot-entity privatisation (kge_set_hot_entities) was a remedy for the same imbalance -- warps that drew many
+        // positives of a hot entity fell behind on its serialised atomics -- and with the dynamic assignment it only costs:
+        // bench.py's process 148.5 us with the hint, 138.3 us without (profiles/r2t_bench_probes*.log).  It stays in effect for
+        // the static stride (153.8 vs 168 us there, profiles/r2h_*).
+        if (p.sched) p.hot_ent[0] = p.hot_ent[1] = -1;
     }
     if (h->rot_warps > 0 && p.shard_world <= 1 && p.stash == nullptr && !(force && strcmp(force, "general") == 0)) {
         p.G = h->rot_G;

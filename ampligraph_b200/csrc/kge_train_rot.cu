@@ -39,6 +39,14 @@ __device__ __forceinline__ void rot_unit(float4 re, float4 im, float g, float4 &
     b = im * inv;
 }
 
+// 16-byte read-only load that stays where it is written (asm volatile: the compiler may not sink it to its first use)
+__device__ __forceinline__ float4 ldg4_nc(const char *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 }  // namespace
 
 // Lane l owns float4 chunks c = l + 32*it (it < NIT) of every half-row; lanes past the end of the row read its last chunk,
@@ -116,6 +124,21 @@ __global__ void __launch_bounds__(256) kge_train_rot_kernel(const TrainParams p)
         int tv = 0;
         if (lane < 3) tv = __ldg(p.triples + 3 * i + lane);
         const int s_id = __shfl_sync(0xffffffffu, tv, 0), p_id = __shfl_sync(0xffffffffu, tv, 1), o_id = __shfl_sync(0xffffffffu, tv, 2);
+        // this lane's chunks of s, the rotation row [cos | sin] and o, straight to registers -- requested FIRST, so that their
+        // latency hides behind the corruption draws below (ncu: long-scoreboard was the top stall with the loads placed
+        // where they are consumed, profiles/r2t_train_cfg4_ncu_full_summary.json)
+        float4 sr[NIT], si[NIT], C[NIT], Sn[NIT], Or_[NIT], Oi[NIT];
+        {
+            const char *srow = reinterpret_cast<const char *>(p.ent + (size_t)s_id * ld);
+            const char *prow = reinterpret_cast<const char *>(p.rel + (size_t)p_id * ld);
+            const char *orow = reinterpret_cast<const char *>(p.ent + (size_t)o_id * ld);
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                sr[it] = ldg4_nc(srow + off[it]); si[it] = ldg4_nc(srow + off[it] + hsB);
+                C[it] = ldg4_nc(prow + off[it]); Sn[it] = ldg4_nc(prow + off[it] + hsB);
+                Or_[it] = ldg4_nc(orow + off[it]); Oi[it] = ldg4_nc(orow + off[it] + hsB);
+            }
+        }
         int n0 = 0;
         for (int base = 0; base < eta; base += 32) {
             const int j = base + lane;
@@ -153,26 +176,18 @@ __global__ void __launch_bounds__(256) kge_train_rot_kernel(const TrainParams p)
         }
         __syncwarp();
 
-        // ---- gather (A2): the first group by the copy engine; s, the rotation row and o straight to registers ----
+        // ---- gather (A2): the first group by the copy engine; per-positive state from the rows requested above ----
         issue(0, 0);
-        float4 C[NIT], Sn[NIT], Or_[NIT], Oi[NIT], Yr[NIT], Yi[NIT];
+        float4 Yr[NIT], Yi[NIT];
         float4 Zor[NIT], Zoi[NIT], Zsr[NIT], Zsi[NIT], Aphi[NIT];
         float P;
         {
-            const char *srow = reinterpret_cast<const char *>(p.ent + (size_t)s_id * ld);
-            const char *prow = reinterpret_cast<const char *>(p.rel + (size_t)p_id * ld);  // [cos | sin] of this step's rotation table
-            const char *orow = reinterpret_cast<const char *>(p.ent + (size_t)o_id * ld);
             float acc = 0.f;
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                float4 sr = __ldg(reinterpret_cast<const float4 *>(srow + off[it])), si = __ldg(reinterpret_cast<const float4 *>(srow + off[it] + hsB));
-                C[it] = __ldg(reinterpret_cast<const float4 *>(prow + off[it]));
-                Sn[it] = __ldg(reinterpret_cast<const float4 *>(prow + off[it] + hsB));
-                Or_[it] = __ldg(reinterpret_cast<const float4 *>(orow + off[it]));
-                Oi[it] = __ldg(reinterpret_cast<const float4 *>(orow + off[it] + hsB));
-                if (!live[it]) { sr = si = f4zero(); C[it] = Sn[it] = Or_[it] = Oi[it] = f4zero(); }
-                Yr[it] = f4fma(f4neg(si), Sn[it], sr * C[it]);  // sr c - si s
-                Yi[it] = f4fma(sr, Sn[it], si * C[it]);         // sr s + si c
+                if (!live[it]) { sr[it] = si[it] = f4zero(); C[it] = Sn[it] = Or_[it] = Oi[it] = f4zero(); }
+                Yr[it] = f4fma(f4neg(si[it]), Sn[it], sr[it] * C[it]);  // sr c - si s
+                Yi[it] = f4fma(sr[it], Sn[it], si[it] * C[it]);         // sr s + si c
                 Zor[it] = Zoi[it] = Zsr[it] = Zsi[it] = Aphi[it] = f4zero();
                 acc = fmaf(rot_modsum(Yr[it] - Or_[it], Yi[it] - Oi[it]), nlive[it], acc);
             }
