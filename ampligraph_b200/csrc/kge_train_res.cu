@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(THREADS) kge_train_res_kernel(const TrainParam
     for (int it = 0; it < NIT; ++it) H0r[it] = H0i[it] = H1r[it] = H1i[it] = f4zero();
 
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-    // (drawing two or three positives per draw was measured too: no gain / slower, profiles/r2p_kbench_chunk{2,3}.log)
+    // (measured and rejected: two or three positives per draw -- no gain / slower, profiles/r2p_kbench_chunk{2,3}.log; requesting the
+    // next positive's triple after the score pass, so that the top of a positive waits for nothing -- cfg2 unchanged, cfg3 +3 %,
+    // profiles/r2v_kbench_*triple_prefetch.log)
     float next_draw = 0.f;  // lane 0: this warp's draw from the positive counter (kge_train_common.cuh: dynamic assignment)
     for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp; i < p.B;
          i = p.sched ? n_warps + (long long)(unsigned)__shfl_sync(0xffffffffu, next_draw, 0) : i + n_warps) {
