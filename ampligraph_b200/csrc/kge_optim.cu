@@ -412,6 +412,29 @@ __global__ void __launch_bounds__(256) kge_optim_exchange_kernel(const ExchangeA
     }
 }
 
+// One instantiation of the exchange kernel, on a grid that is CO-RESIDENT: no CTA waits for another CTA of the grid, so a
+// second wave would be correct -- but it starts only when first-wave CTAs retire, i.e. after their system-scope fence, and
+// then runs its share of the exchange alone.  With the grid fixed at 4 CTAs per SM the 70-register variants (3 resident
+// CTAs per SM: world 2) ran a quarter of the shard in such a second wave: "wait for the last CTA" 25 us of a 66 us kernel
+// at N=2 (profiles/r2w_bench_n2.json), 5 us at N=8 where 4 CTAs fit.  The loops are grid-stride, so fewer CTAs only
+// means more trips per thread.
+template <int KIND, bool REG, int WORLD, bool MC>
+static cudaError_t launch_exchange_variant(const ExchangeArgs &a, const OptimParams &o, long long want, int sm_count,
+                                           cudaStream_t st)
+{
+    auto kern = kge_optim_exchange_kernel<KIND, REG, WORLD, MC>;
+    static int occ_cached = 0;  // per instantiation; the query is cheap but this is the per-step path
+    if (occ_cached == 0) {
+        int occ = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0);
+        if (e != cudaSuccess) return e;
+        occ_cached = occ < 1 ? 1 : (occ > 4 ? 4 : occ);
+    }
+    const long long cap = (long long)sm_count * occ_cached;
+    kern<<<(int)(want < cap ? want : cap), 256, 0, st>>>(a, o);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_optimizer_exchange(const OptimParams &o, const ExchangeParams &xp, int sm_count, cudaStream_t st)
 {
     ExchangeArgs a;
@@ -444,14 +467,14 @@ cudaError_t launch_optimizer_exchange(const OptimParams &o, const ExchangeParams
     const long long zero_want = (a.total4 / 8 + 255) / 256;  // the zeroing of the next gradient block wants enough threads too
     if (!mc || trips <= 1) want = want > zero_want ? want : zero_want;
     if (want < 1) want = 1;
-    int grid = (int)(want < (long long)sm_count * 4 ? want : (long long)sm_count * 4);
     const bool reg = xp.reg_ent.p > 0 || xp.reg_rel.p > 0;
-#define KGE_OPTX2(K, W)                                                                   \
-    if (mc) {                                                                             \
-        if (reg) kge_optim_exchange_kernel<K, true, W, true><<<grid, 256, 0, st>>>(a, o); \
-        else kge_optim_exchange_kernel<K, false, W, true><<<grid, 256, 0, st>>>(a, o);    \
-    } else if (reg) kge_optim_exchange_kernel<K, true, W, false><<<grid, 256, 0, st>>>(a, o); \
-    else kge_optim_exchange_kernel<K, false, W, false><<<grid, 256, 0, st>>>(a, o);
+#define KGE_OPTX2(K, W)                                                                          \
+    if (mc) {                                                                                    \
+        if (reg) return launch_exchange_variant<K, true, W, true>(a, o, want, sm_count, st);     \
+        return launch_exchange_variant<K, false, W, true>(a, o, want, sm_count, st);             \
+    }                                                                                            \
+    if (reg) return launch_exchange_variant<K, true, W, false>(a, o, want, sm_count, st);        \
+    return launch_exchange_variant<K, false, W, false>(a, o, want, sm_count, st);
 #define KGE_OPTX(K)                                                                       \
     switch (xp.world) {                                                                   \
     case 1: KGE_OPTX2(K, 1) break;                                                        \
@@ -468,11 +491,11 @@ cudaError_t launch_optimizer_exchange(const OptimParams &o, const ExchangeParams
     case KGE_OPT_SGD: KGE_OPTX(KGE_OPT_SGD) break;
     case KGE_OPT_ADAM: KGE_OPTX(KGE_OPT_ADAM) break;
     case KGE_OPT_ADAGRAD: KGE_OPTX(KGE_OPT_ADAGRAD) break;
-    default: return cudaErrorInvalidValue;
+    default: break;
     }
 #undef KGE_OPTX
 #undef KGE_OPTX2
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
 }
 
 // --------------------------------------------------------------------------
