@@ -3,7 +3,7 @@
 #include "kge_common.cuh"
 
 // per-lane register state grows with NIT (float4 chunks per lane): trade threads for registers
-// (RotatE carries 11 float4 vectors of per-positive state per chunk: give it more registers)
+// (RotatE carries 11 float4 vectors of per-positive state per chunk -- cos, sin, o, y = R s, four Z sums, d/dphi: give it more registers)
 // (RotatE with 12 warps at 168 registers was measured against 8 warps at 229: 273 us vs 267 us on cfg4, profiles/r2m_kbench_cfg4_sweep.log)
 #define KGE_TRAIN_THREADS(model, nit) ((nit) <= 1 ? 512 : (nit) == 2 ? ((model) == KGE_ROTATE ? 256 : 384) : 256)
 #define KGE_MAX_PEERS 8

@@ -223,8 +223,10 @@ int kge_set_row_stash(kge_handle *h, float *stash_dev, int64_t rows);
  * gradient row to the SAME row of grad_ent: tens of thousands of atomics per 128-byte line per step, which the L2
  * serialises per address.  ids_host = the most frequent entities of the training set, most frequent first (HOST array;
  * the first KGE_HOT = 1 is used (a second one measured slower), n = 0 clears the hint): the resident trilinear kernel sums their subject / object gradient rows
- * in registers per warp and scatters each once per launch.  The reference has no counterpart (TensorFlow's
- * unsorted_segment_sum deduplicates all rows, optimizers.py:166 -> legacy apply_gradients). */
+ * in registers per warp and scatters each once per launch.  The hint takes effect where positives are assigned to warps by
+ * a static stride; where kge_train_step assigns them dynamically (the resident kernel on L2-resident tables, see DESIGN.md
+ * 3.2) the imbalance the hint cures does not arise and it is ignored (measured: it would cost 7 %).  The reference has no
+ * counterpart (TensorFlow's unsorted_segment_sum deduplicates all rows, optimizers.py:166 -> legacy apply_gradients). */
 int kge_set_hot_entities(kge_handle *h, const int32_t *ids_host, int32_t n);
 /* 1 when all 3+eta row windows of a positive stay in shared memory (single gather, the stash is never
  * used), 0 when the kernel works in negative groups / column windows, -1 for a NULL handle. */
